@@ -1,0 +1,330 @@
+// Layout and elementwise helpers around the GEMM / Cholesky kernels (all HBM-bound, coalesced along
+// the contiguous dimension; transposing ones go through a padded 32 x 33 shared-memory tile).
+// Each cites the reference loop or BLAS-1/2 call it stands in for.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "launchers.h"
+
+namespace {
+
+inline int status()
+{
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+// ---- symmetric expansion: the reference's uplo='L' Fortran calls read a row-major array through its
+// UPPER triangle (-DHTNORM_COLMAJOR: the lower one).  full = symmetric copy, low = lower copy.
+__global__ void __launch_bounds__(256)
+sym_expand_kernel(const double* __restrict__ src, size_t lds, int n, int lower_src, double* __restrict__ full,
+                  size_t ldf, double* __restrict__ low, size_t ldl)
+{
+    __shared__ double d_t[32][33];  // direct tile   src[bi-rows][bj-cols]
+    __shared__ double t_t[32][33];  // mirrored tile src[bj-rows][bi-cols]
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int i = bi * 32 + r, j = bj * 32 + tx;
+        d_t[r][tx] = (i < n && j < n) ? src[(size_t)i * lds + j] : 0.0;
+        int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+        t_t[r][tx] = (i2 < n && j2 < n) ? src[(size_t)i2 * lds + j2] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i >= n || j >= n) continue;
+        bool direct = lower_src ? (j <= i) : (j >= i);
+        double v = direct ? d_t[r][tx] : t_t[tx][r];
+        if (full) full[(size_t)i * ldf + j] = v;
+        if (low) low[(size_t)i * ldl + j] = (j <= i) ? v : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ src, size_t lds, int rows, int cols, double* __restrict__ dst,
+                 size_t ldd)
+{
+    __shared__ double t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) {
+        int i = r0 + r, j = c0 + tx;
+        t[r][tx] = (i < rows && j < cols) ? src[(size_t)i * lds + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int j = c0 + r, i = r0 + tx;  // dst[j][i] = src[i][j]
+        if (j < cols && i < rows) dst[(size_t)j * ldd + i] = t[tx][r];
+    }
+}
+
+// op: 0 copy (+bias[c]), 1 divide by d[c], 2 multiply by d[c], 3 dst = d[c] - dst
+__global__ void __launch_bounds__(256)
+rowwise_kernel(const double* __restrict__ src, size_t lds, int rows, int cols, const double* __restrict__ d,
+               double* __restrict__ dst, size_t ldd, int op)
+{
+    const size_t total = (size_t)rows * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx / cols;
+        int c = (int)(idx - r * cols);
+        double v;
+        switch (op) {
+            case 0: v = src[r * lds + c]; if (d) v += d[c]; break;
+            case 1: v = src[r * lds + c] / d[c]; break;
+            case 2: v = src[r * lds + c] * d[c]; break;
+            default: v = d[c] - dst[r * ldd + c]; break;
+        }
+        dst[r * ldd + c] = v;
+    }
+}
+
+__global__ void diag_extract_kernel(const double* __restrict__ a, size_t lda, int n, int op, double* __restrict__ d)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = a[(size_t)i * lda + i];
+    if (op == 1) v = sqrt(v);
+    else if (op == 2) v = 1.0 / v;
+    d[i] = v;
+}
+
+__global__ void diag_set_kernel(double* __restrict__ m, size_t ld, int n, const double* __restrict__ v, double cval)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    m[(size_t)i * ld + i] = v ? v[i] : cval;
+}
+
+__global__ void fill_i32_kernel(int* p, size_t n, int v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// y[c] = r[c] - g[c] . mean : one block per row c (ddot, reference src/htnorm.c:65 folded with the mean)
+__global__ void __launch_bounds__(256)
+r_minus_gmean_kernel(const double* __restrict__ g, size_t ldg, int k, const double* __restrict__ mean,
+                     const double* __restrict__ r, double* __restrict__ y)
+{
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) acc += g[(size_t)c * ldg + i] * mean[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+        y[c] = r[c] - s;
+    }
+}
+
+// per-sample k2 x k2 solve, k2 <= 16 (dposv's solve phase, reference src/htnorm.c:169; k2 == 1: :77)
+constexpr int MAXK2 = 16;
+__global__ void __launch_bounds__(128)
+ht_alpha_kernel(size_t nsamples, int k2, const double* d, size_t ldd, const double* __restrict__ c0,
+                const double* __restrict__ ls, size_t ldls, const int* __restrict__ info_s,
+                double* z, size_t ldz, size_t koff)
+{
+    __shared__ double s_l[MAXK2 * MAXK2];
+    __shared__ double s_c0[MAXK2];
+    for (int i = threadIdx.x; i < k2 * k2; i += blockDim.x) s_l[i] = ls[(size_t)(i / k2) * ldls + (i % k2)];
+    for (int i = threadIdx.x; i < k2; i += blockDim.x) s_c0[i] = c0[i];
+    __syncthreads();
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nsamples) return;
+    const bool skip = info_s && *info_s != 0;
+    double v[MAXK2];
+#pragma unroll
+    for (int c = 0; c < MAXK2; c++) v[c] = (c < k2 && !skip) ? s_c0[c] - d[b * ldd + c] : 0.0;
+    if (!skip) {
+        if (k2 == 1) {
+            v[0] = v[0] / s_l[0];
+        } else {
+#pragma unroll
+            for (int i = 0; i < MAXK2; i++) {
+                if (i < k2) {
+                    double s = v[i];
+#pragma unroll
+                    for (int t = 0; t < MAXK2; t++)
+                        if (t < i) s -= s_l[i * k2 + t] * v[t];
+                    v[i] = s / s_l[i * k2 + i];
+                }
+            }
+#pragma unroll
+            for (int i = MAXK2 - 1; i >= 0; i--) {
+                if (i < k2) {
+                    double s = v[i];
+#pragma unroll
+                    for (int t = 0; t < MAXK2; t++)
+                        if (t > i && t < k2) s -= s_l[t * k2 + i] * v[t];
+                    v[i] = s / s_l[i * k2 + i];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXK2; c++)
+        if (c < k2) z[b * ldz + koff + c] = v[c];
+}
+
+// out[b][i] += sum_c cgt[i][c] * alpha[b][c]   (dgemv, reference src/htnorm.c:176, diagonal-cov path)
+__global__ void __launch_bounds__(256)
+ht_diag_project_kernel(size_t nsamples, int k, int k2, const double* __restrict__ cgt, size_t ldc,
+                       const double* __restrict__ alpha, size_t lda, double* __restrict__ out, size_t ldo)
+{
+    const size_t total = nsamples * (size_t)k;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t b = idx / k;
+        int i = (int)(idx - b * k);
+        double acc = 0.0;
+        for (int c = 0; c < k2; c++) acc += cgt[(size_t)i * ldc + c] * alpha[b * lda + c];
+        out[b * ldo + i] += acc;
+    }
+}
+
+// dcol[b][c] = g[c] . y[b]: one warp per sample, up to 16 rows of g per pass
+__global__ void __launch_bounds__(256)
+rows_dot_kernel(size_t nsamples, int k, int k2, const double* __restrict__ g, size_t ldg,
+                const double* __restrict__ y, size_t ldy, double* __restrict__ dcol, size_t ldd)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nsamples) return;
+    for (int c0 = 0; c0 < k2; c0 += 16) {
+        double acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) acc[c] = 0.0;
+        for (int i = lane; i < k; i += 32) {
+            const double yv = y[b * ldy + i];
+#pragma unroll
+            for (int c = 0; c < 16; c++)
+                if (c0 + c < k2) acc[c] += g[(size_t)(c0 + c) * ldg + i] * yv;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            double a = acc[c];
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && c0 + c < k2) dcol[b * ldd + c0 + c] = a;
+        }
+    }
+}
+
+unsigned grid_for(size_t total, int block)
+{
+    size_t g = (total + block - 1) / block;
+    const size_t cap = 148u * 32u;  // grid-stride: a few waves of the 148 SMs
+    return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, int n, int lower_src,
+                               double* full, size_t ldf, double* low, size_t ldl)
+{
+    if (n <= 0) return 0;
+    dim3 grid((n + 31) / 32, (n + 31) / 32);
+    sym_expand_kernel<<<grid, 256, 0, st>>>(src, lds, n, lower_src, full, ldf, low, ldl);
+    return status();
+}
+
+extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
+                              size_t ldd)
+{
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+    return status();
+}
+
+extern "C" int htnk_copy2d(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
+                           size_t ldd, const double* bias)
+{
+    if (rows <= 0 || cols <= 0) return 0;
+    rowwise_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, st>>>(src, lds, rows, cols, bias, dst, ldd, 0);
+    return status();
+}
+
+extern "C" int htnk_coldiv(cudaStream_t st, const double* src, size_t lds, int rows, int cols, const double* d,
+                           double* dst, size_t ldd)
+{
+    if (rows <= 0 || cols <= 0) return 0;
+    rowwise_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, st>>>(src, lds, rows, cols, d, dst, ldd, 1);
+    return status();
+}
+
+extern "C" int htnk_colmul(cudaStream_t st, const double* src, size_t lds, int rows, int cols, const double* d,
+                           double* dst, size_t ldd)
+{
+    if (rows <= 0 || cols <= 0) return 0;
+    rowwise_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, st>>>(src, lds, rows, cols, d, dst, ldd, 2);
+    return status();
+}
+
+extern "C" int htnk_rsub_rows(cudaStream_t st, double* dst, size_t ldd, int rows, int cols, const double* t)
+{
+    if (rows <= 0 || cols <= 0) return 0;
+    rowwise_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, st>>>(dst, ldd, rows, cols, t, dst, ldd, 3);
+    return status();
+}
+
+extern "C" int htnk_diag_extract(cudaStream_t st, const double* a, size_t lda, int n, int op, double* d)
+{
+    if (n <= 0) return 0;
+    diag_extract_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, lda, n, op, d);
+    return status();
+}
+
+extern "C" int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const double* v, double cval)
+{
+    if (n <= 0) return 0;
+    diag_set_kernel<<<(n + 255) / 256, 256, 0, st>>>(m, ld, n, v, cval);
+    return status();
+}
+
+extern "C" int htnk_fill_i32(cudaStream_t st, int* p, size_t n, int v)
+{
+    if (n == 0) return 0;
+    fill_i32_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);
+    return status();
+}
+
+extern "C" int htnk_r_minus_gmean(cudaStream_t st, const double* g, size_t ldg, int k2, int k, const double* mean,
+                                  const double* r, double* y)
+{
+    if (k2 <= 0) return 0;
+    r_minus_gmean_kernel<<<k2, 256, 0, st>>>(g, ldg, k, mean, r, y);
+    return status();
+}
+
+extern "C" int htnk_ht_alpha(cudaStream_t st, size_t nsamples, int k2, const double* d, size_t ldd,
+                             const double* c0, const double* ls, size_t ldls, const int* info_s, double* z,
+                             size_t ldz, size_t koff)
+{
+    if (nsamples == 0) return 0;
+    if (k2 < 1 || k2 > MAXK2) return -202;
+    ht_alpha_kernel<<<(unsigned)((nsamples + 127) / 128), 128, 0, st>>>(nsamples, k2, d, ldd, c0, ls, ldls,
+                                                                      info_s, z, ldz, koff);
+    return status();
+}
+
+extern "C" int htnk_ht_diag_project(cudaStream_t st, size_t nsamples, int k, int k2, const double* cgt,
+                                    size_t ldc, const double* alpha, size_t lda, double* out, size_t ldo)
+{
+    if (nsamples == 0) return 0;
+    ht_diag_project_kernel<<<grid_for(nsamples * (size_t)k, 256), 256, 0, st>>>(nsamples, k, k2, cgt, ldc, alpha,
+                                                                               lda, out, ldo);
+    return status();
+}
+
+extern "C" int htnk_rows_dot(cudaStream_t st, size_t nsamples, int k, int k2, const double* g, size_t ldg,
+                             const double* y, size_t ldy, double* dcol, size_t ldd)
+{
+    if (nsamples == 0) return 0;
+    rows_dot_kernel<<<(unsigned)((nsamples + 7) / 8), 256, 0, st>>>(nsamples, k, k2, g, ldg, y, ldy, dcol, ldd);
+    return status();
+}

@@ -1,0 +1,239 @@
+// FP64 tensor-core GEMM for sm_100a:  C = alpha * A * B^T + beta * C + bias   ("TN": both operands
+// K-contiguous, row-major), built on DMMA  mma.sync.aligned.m8n8k4.f64  (tcgen05 has no f64 kind,
+// so the FP64 tensor path on Blackwell is the warp-level DMMA instruction).
+//
+// This one kernel replaces every dense Level-3 call site of the reference (src/htnorm_blas.h:84-107:
+// dgemm NN/NT/TN, dsymm, dsyrk) and, through blocked drivers in the host layer, dtrmm / dtrsm /
+// the trailing updates of dpotrf:
+//   * sampling   X = Z~ * L~^T + mean     (mode B_LOWER: K range clipped to the non-zero part of L)
+//   * Cholesky   A22 -= L21 * L21^T       (mode C_LOWER: only tiles touching the lower triangle)
+//   * TRSM       X_j = (B_j - X_<j L_j<^T) * inv(L_jj)^T
+//
+// Tiling: CTA tile 128 x BN (BN = 128 / 32 / 8), BK = 16, 8 warps, 3-stage cp.async pipeline.
+// Shared-memory rows are padded to 20 doubles: the DMMA fragment pattern (8 rows x 4 consecutive
+// doubles per half-warp pair) then hits 16 distinct 8-byte bank pairs -> conflict-free LDS.64.
+// BN = 128: warps 2 x 4, warp tile 64 x 32 -> 32 independent DMMAs per k4 step, 12 LDS.64.
+// Tile order: n fastest and descending, so the (few) CTAs that share one 128-row slab of A run
+// together (A streams from HBM once, B stays in L2) and, for B_LOWER, the longest K loops start first.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "launchers.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int LDS = 20;  // padded row length (doubles) of a smem tile
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 256;
+
+struct GemmParams {
+    int M, N, K;
+    double alpha, beta;
+    const double* A;
+    const double* B;
+    double* C;
+    const double* bias;
+    size_t lda, ldb, ldc;
+    int mode, ktri, kext0;
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// rows x BK tile (row-major source, leading dimension ld) -> smem [rows][LDS]; elements outside
+// [0, nrows_valid) x [k0, kend) are zero-filled by cp.async's src-size operand.
+template <int ROWS>
+__device__ __forceinline__ void load_tile(double* s, const double* g, size_t ld, int row0, int nrows_total,
+                                          int k0, int kend, int tid)
+{
+    constexpr int CHUNKS = ROWS * (BK / 2);  // 16-byte chunks
+#pragma unroll
+    for (int it = 0; it < (CHUNKS + NTHREADS - 1) / NTHREADS; it++) {
+        int id = tid + it * NTHREADS;
+        if (CHUNKS % NTHREADS != 0 && id >= CHUNKS) break;
+        int r = id >> 3, ch = id & 7;
+        int grow = row0 + r;
+        int kk = k0 + ch * 2;
+        int rem = kend - kk;
+        int bytes = (grow < nrows_total && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+        const double* src = bytes ? g + (size_t)grow * ld + kk : g;
+        cp_async16(s + r * LDS + ch * 2, src, bytes);
+    }
+}
+
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p)
+{
+    static_assert(WARPS_M * WARPS_N == 8, "8 warps");
+    static_assert(WARPS_M * WM * 8 == BM, "BM");
+    static_assert(WARPS_N * WN * 8 == BN, "BN");
+    extern __shared__ __align__(16) double smem[];
+    constexpr int A_STAGE = BM * LDS;
+    constexpr int B_STAGE = BN * LDS;
+    double* sA = smem;
+    double* sB = smem + STAGES * A_STAGE;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int wm = warp / WARPS_N;
+    const int wn = warp % WARPS_N;
+
+    const int bid = blockIdx.x;
+    const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
+    const int tm = bid / p.tiles_n;
+    const int m0 = tm * BM;
+    const int n0 = tn * BN;
+    if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < n0) return;  // tile entirely above the diagonal
+
+    // K schedule: chunks of BK from segment 1 [0, kend1) then segment 2 [kext0, K)
+    int kend1 = p.K, kbeg2 = p.K, kend2 = p.K;
+    if (p.mode == HTNK_GEMM_B_LOWER) {
+        int n1 = min(p.N, n0 + BN);
+        kend1 = min(n1, p.ktri);
+        kbeg2 = min(p.kext0, p.K);
+    }
+    const int nc1 = (kend1 + BK - 1) / BK;
+    const int nc2 = (kend2 - kbeg2 + BK - 1) / BK;
+    const int nchunks = nc1 + nc2;
+
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            int k0, kend;
+            if (c < nc1) { k0 = c * BK; kend = kend1; }
+            else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
+            int s = c % STAGES;
+            load_tile<BM>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
+            load_tile<BN>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
+        }
+        cp_async_commit();
+    };
+
+    double acc[WM][WN][2];
+#pragma unroll
+    for (int i = 0; i < WM; i++)
+#pragma unroll
+        for (int j = 0; j < WN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) issue(s);
+
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(c + STAGES - 1);
+        const double* a_s = sA + (c % STAGES) * A_STAGE + (wm * WM * 8 + g) * LDS + t4;
+        const double* b_s = sB + (c % STAGES) * B_STAGE + (wn * WN * 8 + g) * LDS + t4;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[WM], bf[WN];
+#pragma unroll
+            for (int i = 0; i < WM; i++) af[i] = a_s[i * 8 * LDS + kk];
+#pragma unroll
+            for (int j = 0; j < WN; j++) bf[j] = b_s[j * 8 * LDS + kk];
+#pragma unroll
+            for (int i = 0; i < WM; i++)
+#pragma unroll
+                for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread holds C[m][n], C[m][n+1] with m = .. + g, n = .. + 2*t4
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < WM; i++) {
+        const int m = m0 + wm * WM * 8 + i * 8 + g;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < WN; j++) {
+            const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
+            if (n >= p.N) continue;
+            double v0 = p.alpha * acc[i][j][0];
+            double v1 = p.alpha * acc[i][j][1];
+            double* cp = p.C + (size_t)m * p.ldc + n;
+            const bool two = (n + 1 < p.N);
+            if (p.bias) {
+                v0 += p.bias[n];
+                if (two) v1 += p.bias[n + 1];
+            }
+            if (vec_ok && two) {
+                if (p.beta != 0.0) {
+                    double2 o = *reinterpret_cast<const double2*>(cp);
+                    v0 += p.beta * o.x;
+                    v1 += p.beta * o.y;
+                }
+                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+            } else {
+                if (p.beta != 0.0) {
+                    v0 += p.beta * cp[0];
+                    if (two) v1 += p.beta * cp[1];
+                }
+                cp[0] = v0;
+                if (two) cp[1] = v1;
+            }
+        }
+    }
+}
+
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN>
+int launch(cudaStream_t st, const GemmParams& p)
+{
+    constexpr size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
+    auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN>;
+    // per-device attribute: set on every launch (cheap) so that any current device is covered
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -201;
+    unsigned grid = (unsigned)p.tiles_m * (unsigned)p.tiles_n;
+    kern<<<grid, NTHREADS, smem, st>>>(p);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+}  // namespace
+
+extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
+                            const double* B, size_t ldb, double beta, double* C, size_t ldc,
+                            const double* bias, int mode, int ktri, int kext0, int bn)
+{
+    if (M <= 0 || N <= 0) return 0;
+    if (K < 0) return -202;
+    if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return -202;
+    if (bn == 0) bn = N > 32 ? 128 : (N > 8 ? 32 : 8);
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.alpha = alpha; p.beta = beta;
+    p.A = A; p.B = B; p.C = C; p.bias = bias;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + bn - 1) / bn;
+    if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
+    switch (bn) {
+        case 128: return launch<128, 2, 4, 8, 4>(st, p);
+        case 32: return launch<32, 8, 1, 2, 4>(st, p);
+        case 8: return launch<8, 8, 1, 2, 1>(st, p);
+        default: return -202;
+    }
+}

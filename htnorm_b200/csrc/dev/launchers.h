@@ -1,0 +1,124 @@
+/* Internal C ABI between the C host layer (csrc/host) and the CUDA translation units
+ * (csrc/dev).  One function = one kernel launch (or a fixed short sequence) on `stream`;
+ * plain pointers and sizes only; every pointer is a DEVICE pointer unless it says host.
+ * Return value: 0 or HTN_E_CUDA (-201) if the launch failed (cudaGetLastError).
+ */
+#ifndef HTNB_LAUNCHERS_H
+#define HTNB_LAUNCHERS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bookkeeping ---- */
+void htnk_count_launch(void);
+unsigned long long htnk_launch_count(void);
+
+/* ---- generators + ziggurat (rng_zig.cu) ---- */
+
+/* where stream b starts: state words (4 per stream, see htn_gen_state) or seeds / seed0 + b */
+typedef struct {
+    int gen;                /* 0 PCG64 (2 x PCG32), 1 Xoroshiro128+ */
+    const uint64_t* seeds;  /* device, nstreams, or NULL */
+    uint64_t seed0;         /* seed_b = seed0 + b when seeds == NULL */
+    uint64_t* states;       /* device, 4 words per stream, or NULL.  If non-NULL the streams START
+                               from these states (seeds ignored) and the advanced states are written back */
+} htnk_streams_t;
+
+/* one run of normals per stream: element j (draw order) goes to out[b*ld + (n-1-j)] after
+ * v = z; if (div) v = z / div[i]; if (mul) v = z * mul[i]; if (add) v = add[i] + v   (i = n-1-j) */
+typedef struct {
+    size_t n;
+    double* out;
+    size_t ld;
+    const double* div;
+    const double* mul;
+    const double* add;
+} htnk_segment_t;
+
+int htnk_raw_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, size_t nwords, uint64_t* out);
+/* nseg = 1 or 2 segments drawn back to back from each stream; ndraws: u32 per stream or NULL */
+int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, int nseg,
+                     const htnk_segment_t* seg, uint32_t* ndraws);
+
+/* ---- FP64 tensor-core GEMM (gemm_f64.cu) ----
+ * C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C + bias[n]      (all row-major)
+ * A, B: 16-byte aligned, lda/ldb even.  C: any ldc.  bias may be NULL.
+ * mode: HTNK_GEMM_FULL; HTNK_GEMM_B_LOWER - B is lower-trapezoidal: B[n][kk] == 0 for
+ *       n < kk < ktri, and columns [kext0, K) are dense (K range per tile is clipped accordingly);
+ *       HTNK_GEMM_C_LOWER - only tiles that touch the lower triangle (m >= n) are computed.
+ * bn: N-tile width, 128 / 32 / 8 (0 = pick from N). */
+enum { HTNK_GEMM_FULL = 0, HTNK_GEMM_B_LOWER = 1, HTNK_GEMM_C_LOWER = 2 };
+int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
+                 const double* B, size_t ldb, double beta, double* C, size_t ldc, const double* bias,
+                 int mode, int ktri, int kext0, int bn);
+
+/* ---- factorisation building blocks (chol.cu) ---- */
+/* Factor the nb x nb (nb <= 128) diagonal block at a (row-major, ld) in place: lower triangle := L,
+ * strictly-upper := 0.  Also writes inv(L) to dinv (128 x 128 row-major, zero padded, lower) and its
+ * transpose to dinvt.  *info (device int) receives col0 + j + 1 at the first pivot <= 0 (only if it
+ * still holds 0). dinv/dinvt may be NULL. */
+int htnk_potf2_inv(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* dinv,
+                   double* dinvt, int* info);
+
+/* ---- layout / elementwise helpers (elementwise.cu) ---- */
+/* src: n x n row-major (ld lds), symmetric, read through its UPPER triangle (lower_src = 0) or LOWER
+ * triangle (lower_src = 1).  full (may be NULL): n x n symmetric copy (ld ldf).  low (may be NULL):
+ * lower triangle copy with zeros above the diagonal (ld ldl). */
+int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, int n, int lower_src, double* full,
+                    size_t ldf, double* low, size_t ldl);
+/* dst[c][r] = src[r][c], src rows x cols */
+int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
+                   size_t ldd);
+/* dst[r][c] = src[r][c] (rows x cols), optional bias[c] added; strided 2-D copy */
+int htnk_copy2d(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
+                size_t ldd, const double* bias);
+/* dst[r][c] = src[r][c] / d[c]  (structured precision, diagonal A: src/htnorm.c:272-280) */
+int htnk_coldiv(cudaStream_t st, const double* src, size_t lds, int rows, int cols, const double* d,
+                double* dst, size_t ldd);
+/* dst[r][c] = src[r][c] * d[c] */
+int htnk_colmul(cudaStream_t st, const double* src, size_t lds, int rows, int cols, const double* d,
+                double* dst, size_t ldd);
+/* dst[r][c] = t[c] - dst[r][c] */
+int htnk_rsub_rows(cudaStream_t st, double* dst, size_t ldd, int rows, int cols, const double* t);
+/* d[i] = a[i*lda + i] (op 0), sqrt of it (op 1), 1 / it (op 2) */
+int htnk_diag_extract(cudaStream_t st, const double* a, size_t lda, int n, int op, double* d);
+/* m[i*ld + i] += (or =) v[i] / constant */
+int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const double* v, double cval);
+int htnk_fill_i32(cudaStream_t st, int* p, size_t n, int v);
+/* y[c] = r[c] - sum_i g[c][i] * mean[i]   (k2 rows) */
+int htnk_r_minus_gmean(cudaStream_t st, const double* g, size_t ldg, int k2, int k, const double* mean,
+                       const double* r, double* y);
+/* hyperplane coefficients, k2 <= 16: per sample b solve (L L^T) alpha = c0 - d[b][:] with the k2 x k2
+ * lower factor ls (leading dimension ldls); k2 == 1 divides by the scalar s11 instead (src/htnorm.c:77).  alpha is
+ * written to z[b*ldz + koff + c].  If *info_s != 0 alpha = 0 (projection skipped, src/htnorm.c:170). */
+int htnk_ht_alpha(cudaStream_t st, size_t nsamples, int k2, const double* d, size_t ldd, const double* c0,
+                  const double* ls, size_t ldls, const int* info_s, double* z, size_t ldz, size_t koff);
+/* diagonal covariance: out[b][i] = y[b][i] + sum_c cgt[i*ldc + c] * alpha[b][c]
+ * where y[b][i] is already in out (mean + sqrt(cov_ii) z) */
+int htnk_ht_diag_project(cudaStream_t st, size_t nsamples, int k, int k2, const double* cgt, size_t ldc,
+                         const double* alpha, size_t lda, double* out, size_t ldo);
+/* dcol[b][c] = sum_i g[c][i] * y[b][i]  (k2 <= 16; diagonal-covariance path) */
+int htnk_rows_dot(cudaStream_t st, size_t nsamples, int k, int k2, const double* g, size_t ldg,
+                  const double* y, size_t ldy, double* dcol, size_t ldd);
+
+/* ---- small independent problems (small_batched.cu) ---- */
+/* One CTA per problem, k <= 128, k2 <= 16: the whole of src/htnorm.c:85-187 for problem b with its own
+ * mean/cov/g/r (back to back) and its own stream; info[b] as the reference's return code. */
+int htnk_ht_small_batched(cudaStream_t st, const htnk_streams_t* s, size_t nproblems, int k, int k2,
+                          const double* mean, const double* cov, const double* g, const double* r,
+                          int diag, int lower_src, double* out, int* info);
+
+/* ---- peak microbenchmarks (peak.cu) ---- */
+double htnk_dmma_peak_tflops(cudaStream_t st, double ms);
+double htnk_dfma_peak_tflops(cudaStream_t st, double ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

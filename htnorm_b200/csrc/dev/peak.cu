@@ -1,0 +1,98 @@
+// Roofline denominators measured in place: FP64 tensor-core (DMMA) and FP64 FMA-pipe throughput.
+// MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 peak the GEMM / Cholesky fractions are
+// quoted against is this microbenchmark: register operands only, 8 independent accumulator chains per
+// warp (DMMA) / per thread (DFMA), every SM saturated with 8 CTAs x 256 threads, CUDA-event timed.
+#include <cuda_runtime.h>
+
+#include "launchers.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* sink, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - 1e-12 * threadIdx.x;
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = i * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[2 * i]), "+d"(c[2 * i + 1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    if (s == 123.456) sink[0] = s;  // never true: keeps the chain alive
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1e-12 * threadIdx.x;
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = i * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+template <typename K>
+double time_kernel(cudaStream_t st, K kern, double flops_per_thread_iter_x32, double ms_target)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = sms * 8;
+    int iters = 2000;
+    double best = -1.0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0, st);
+        kern<<<grid, 256, 0, st>>>(sink, iters, 1.0);
+        htnk_count_launch();
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // flops: warps * iters * per-warp-iteration flops
+        double flops = (double)grid * 8.0 * iters * flops_per_thread_iter_x32;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+        if (rep < 2 && ms > 0) {  // calibrate the loop length to about ms_target
+            double scale = ms_target / ms;
+            if (scale > 64) scale = 64;
+            if (scale < 1.0 / 64) scale = 1.0 / 64;
+            iters = (int)(iters * scale);
+            if (iters < 100) iters = 100;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+}  // namespace
+
+extern "C" double htnk_dmma_peak_tflops(cudaStream_t st, double ms)
+{
+    // per warp per iteration: 8 DMMA m8n8k4 = 8 * 8*8*4*2 flops
+    return time_kernel(st, dmma_peak_kernel, 8.0 * 512.0, ms);
+}
+
+extern "C" double htnk_dfma_peak_tflops(cudaStream_t st, double ms)
+{
+    // per warp per iteration: 32 lanes * 8 FMA * 2 flops
+    return time_kernel(st, dfma_peak_kernel, 32.0 * 8.0 * 2.0, ms);
+}

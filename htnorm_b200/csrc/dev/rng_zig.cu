@@ -1,0 +1,167 @@
+// Generator kernels: raw 64-bit streams and ziggurat normals, one stream per thread.
+//
+// normal_fill is the Z producer of every sampler.  Layout problem: stream b writes element
+// n-1-j of ITS row (reference fill order, src/htnorm_distributions.c:12-13), so a naive
+// thread-per-stream store is strided by the row length.  Each warp therefore stages a 32-stream x
+// 32-element tile in shared memory and writes it out row by row: 256 contiguous bytes per store.
+//
+// Ziggurat control flow is warp-cooperative: all lanes run the table-lookup fast path in lockstep;
+// a lane whose draw fails the fast test parks (its stream cannot advance until the wedge/tail test
+// is resolved) while the others keep drawing; the expensive exp/log path runs for all parked lanes
+// together when a quarter of the warp is parked or nobody can make fast progress.  The sequence of
+// generator calls inside each stream is exactly the reference's (src/htnorm_distributions.c:18-54).
+#include <cuda_runtime.h>
+
+#include "launchers.h"
+#include "rng.cuh"
+
+namespace {
+
+using namespace htn;
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kTile = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int GEN>
+__global__ void __launch_bounds__(128) raw_fill_kernel(const uint64_t* seeds, uint64_t seed0,
+                                                       uint64_t* states, size_t nstreams,
+                                                       size_t nwords, uint64_t* out)
+{
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nstreams) return;
+    GenState g;
+    stream_begin<GEN>(g, seeds, seed0, states, b);
+    for (size_t t = 0; t < nwords; t++) out[b * nwords + t] = gen_next<GEN>(g);
+    stream_end<GEN>(g, states, b);
+}
+
+struct Seg {
+    size_t n;
+    double* out;
+    size_t ld;
+    const double* div;
+    const double* mul;
+    const double* add;
+};
+
+template <int GEN>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size_t nstreams, int nseg,
+                   Seg seg0, Seg seg1, uint32_t* ndraws)
+{
+    __shared__ uint64_t s_ki[256];
+    __shared__ double s_wi[256];
+    __shared__ double s_tile[kWarpsPerBlock][kTile][kTile + 1];
+    zig_stage_tables(s_ki, s_wi);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const size_t warp_base = ((size_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
+    if (warp_base >= nstreams) return;  // whole warp idle
+    const size_t b = warp_base + lane;
+    const bool live = b < nstreams;
+    double(*tile)[kTile + 1] = s_tile[warp];
+
+    GenState g;
+    uint32_t ncalls = 0;
+    if (live) stream_begin<GEN>(g, seeds, seed0, states, b);
+
+    for (int sgi = 0; sgi < nseg; sgi++) {
+        const Seg sg = sgi == 0 ? seg0 : seg1;
+        for (size_t pos0 = 0; pos0 < sg.n; pos0 += kTile) {
+            const int cnt = (int)((sg.n - pos0) < (size_t)kTile ? (sg.n - pos0) : (size_t)kTile);
+            int filled = 0;
+            bool parked = false;
+            ZigDraw d;
+            for (;;) {
+                const bool want = live && !parked && filled < cnt;
+                const unsigned wm = __ballot_sync(kFull, want);
+                const unsigned pm = __ballot_sync(kFull, parked);
+                if (wm == 0 && pm == 0) break;
+                if (wm == 0 || __popc(pm) >= 8) {
+                    if (parked) {
+                        double z;
+                        if (zig_slow<GEN>(g, d, z, ncalls)) tile[lane][filled++] = z;
+                        parked = false;
+                    }
+                    continue;
+                }
+                if (want) {
+                    uint64_t r = gen_next<GEN>(g);
+                    ncalls++;
+                    if (zig_fast(r, s_ki, s_wi, d))
+                        tile[lane][filled++] = d.x;
+                    else
+                        parked = true;
+                }
+            }
+            __syncwarp();
+            // write-out: row rr of the tile = stream warp_base + rr; lane t holds draw pos0 + t
+            const int t = lane;
+            if (t < cnt) {
+                const size_t i = sg.n - 1 - (pos0 + (size_t)t);
+                double dv = sg.div ? sg.div[i] : 1.0;
+                double mv = sg.mul ? sg.mul[i] : 1.0;
+                double av = sg.add ? sg.add[i] : 0.0;
+                for (int rr = 0; rr < 32; rr++) {
+                    const size_t bb = warp_base + rr;
+                    if (bb >= nstreams) break;
+                    double v = tile[rr][t];
+                    if (sg.div) v = __ddiv_rn(v, dv);
+                    if (sg.mul) v = __dmul_rn(v, mv);
+                    if (sg.add) v = __dadd_rn(av, v);
+                    sg.out[bb * sg.ld + i] = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (live) {
+        stream_end<GEN>(g, states, b);
+        if (ndraws) ndraws[b] = ncalls;
+    }
+}
+
+}  // namespace
+
+static unsigned long long g_launches = 0;
+extern "C" void htnk_count_launch(void) { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+extern "C" unsigned long long htnk_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+static int launch_status(void)
+{
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_raw_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, size_t nwords,
+                             uint64_t* out)
+{
+    if (nstreams == 0 || nwords == 0) return 0;
+    unsigned grid = (unsigned)((nstreams + 127) / 128);
+    if (s->gen == 0)
+        raw_fill_kernel<0><<<grid, 128, 0, st>>>(s->seeds, s->seed0, s->states, nstreams, nwords, out);
+    else
+        raw_fill_kernel<1><<<grid, 128, 0, st>>>(s->seeds, s->seed0, s->states, nstreams, nwords, out);
+    return launch_status();
+}
+
+extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, int nseg,
+                                const htnk_segment_t* seg, uint32_t* ndraws)
+{
+    if (nstreams == 0 || nseg <= 0) return 0;
+    Seg a[2] = {{0, nullptr, 0, nullptr, nullptr, nullptr}, {0, nullptr, 0, nullptr, nullptr, nullptr}};
+    for (int i = 0; i < nseg && i < 2; i++)
+        a[i] = Seg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};
+    const size_t per_block = (size_t)kWarpsPerBlock * 32;
+    unsigned grid = (unsigned)((nstreams + per_block - 1) / per_block);
+    if (s->gen == 0)
+        normal_fill_kernel<0><<<grid, kWarpsPerBlock * 32, 0, st>>>(s->seeds, s->seed0, s->states, nstreams,
+                                                                    nseg, a[0], a[1], ndraws);
+    else
+        normal_fill_kernel<1><<<grid, kWarpsPerBlock * 32, 0, st>>>(s->seeds, s->seed0, s->states, nstreams,
+                                                                    nseg, a[0], a[1], ndraws);
+    return launch_status();
+}

@@ -1,0 +1,111 @@
+/* Device context, stream and workspace plumbing of the host layer. */
+#include "htn_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+static _Thread_local char g_err[512] = "";
+
+void htn_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+const char* htn_last_error(void) { return g_err; }
+const char* htn_version(void) { return "htnorm-b200 0.1 (sm_100a)"; }
+unsigned long long htn_launch_count(void) { return htnk_launch_count(); }
+
+int htn_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        htn_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return HTN_E_NO_DEVICE;
+    }
+    return n;
+}
+
+void htn_batch_init(htn_batch_t* b, size_t nsamples)
+{
+    memset(b, 0, sizeof(*b));
+    b->nsamples = nsamples;
+    b->gen = HTN_GEN_PCG64;
+    b->mem = HTN_MEM_HOST;
+    b->device = -1;
+}
+
+static int pool_configured[64];
+
+int htn_ctx_begin(htn_ctx_t* ctx, int device, void* stream, int host_mode)
+{
+    int rc = 0;
+    memset(ctx, 0, sizeof(*ctx));
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        /* there is no CPU fallback: fail loudly */
+        htn_set_error("no CUDA device available (%s); htnorm-b200 has no CPU path",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return HTN_E_NO_DEVICE;
+    }
+    HTN_CUDA(cudaGetDevice(&ctx->prev_device));
+    ctx->device = device < 0 ? ctx->prev_device : device;
+    if (ctx->device >= n) {
+        htn_set_error("device %d out of range (%d devices)", ctx->device, n);
+        return HTN_E_ARG;
+    }
+    if (ctx->device != ctx->prev_device) HTN_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->device < 64 && !pool_configured[ctx->device]) {
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ULL; /* never trim: workspaces are reused call after call */
+        HTN_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        HTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_configured[ctx->device] = 1;
+    }
+    if (host_mode) {
+        HTN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = 1;
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+    }
+done:
+    return rc;
+}
+
+int htn_ctx_end(htn_ctx_t* ctx, int sync)
+{
+    int rc = 0;
+    if (sync || ctx->own_stream) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            htn_set_error("stream synchronize: %s", cudaGetErrorString(e));
+            rc = HTN_E_CUDA;
+        }
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->device != ctx->prev_device) cudaSetDevice(ctx->prev_device);
+    return rc;
+}
+
+int htn_dalloc(htn_ctx_t* ctx, void** p, size_t bytes)
+{
+    *p = NULL;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        htn_set_error("cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        *p = NULL;
+        return e == cudaErrorMemoryAllocation ? HTNORM_ALLOC_ERROR : HTN_E_CUDA;
+    }
+    return 0;
+}
+
+void htn_dfree(htn_ctx_t* ctx, void* p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}

@@ -1,0 +1,411 @@
+/* Hyperplane-truncated MVN sampler: x ~ N(mean, cov) restricted to {x : G x = r}.
+ *
+ * Reference path restated for a batch (src/htnorm.c:85-187, src/htnorm_distributions.c:58-88):
+ *     y = mean + L z,   x = y + cov G^T (G cov G^T)^-1 (r - G y)           (Cong et al. 2017, Alg. 2)
+ * With L = chol(cov), W = G L and c0 = r - G mean this is, for sample b,
+ *     alpha_b = (G cov G^T)^-1 (c0 - W z_b),      x_b = mean + [ L | cov G^T ] [ z_b ; alpha_b ]
+ * i.e. ONE triangular-trapezoidal DMMA GEMM over the whole batch, after a skinny GEMM for W z_b.
+ * Everything that depends only on (cov, G, r, mean) - the O(k^3) factorisation the reference repeats on
+ * every call - is done once per batch call.
+ *
+ * Device buffers (row-major, leading dimensions multiples of 16 doubles):
+ *     F  : k x ldz   [ L (lower, zeros above) | 0 pad | cov G^T (k x k2) | 0 pad ],  ldz = kp + k2p
+ *     Z~ : B x ldz   [ z_b (reverse fill)     | 0 pad | alpha_b          | 0 pad ]
+ * so out = Z~ F^T + mean with the K range of each N tile clipped to L's non-zero part.
+ */
+#include "htn_internal.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define SMALL_K_MAX 128
+#define SMALL_K2_MAX 16
+#define ALPHA_K2_MAX 16
+
+/* set by the shared dense path when the covariance factorisation failed (no draw was made) */
+static _Thread_local int g_cov_failed = 0;
+int htn_ht_last_cov_failed(void) { return g_cov_failed; }
+
+static void streams_view(const htn_streams_t* s, size_t offset, htnk_streams_t* v)
+{
+    v->gen = s->gen;
+    v->seeds = s->seeds ? s->seeds + offset : NULL;
+    v->seed0 = s->seed0 + (uint64_t)offset;
+    v->states = s->states ? s->states + 4 * offset : NULL;
+}
+
+/* k2 x k2 system (G cov G^T) for k2 > 16: D := (c0 - D) (L_s L_s^T)^-1 through the blocked TRSMs */
+static int alpha_large(htn_ctx_t* ctx, htn_factor_t* fs, double* d, size_t ldd, int nrows, int k2,
+                       const double* c0)
+{
+    int rc = 0;
+    HTN_TRY(htnk_rsub_rows(ctx->stream, d, ldd, nrows, k2, c0));
+    HTN_TRY(htn_potrs_rows(ctx, fs, d, ldd, nrows));
+done:
+    return rc;
+}
+
+static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, int k2, int k,
+                           const double* mean, const double* cov, const double* g, const double* r, double* out,
+                           int* first_info)
+{
+    int rc = 0;
+    const int lower_src = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
+    const size_t kp = htn_round_up((size_t)k, 16), k2p = htn_round_up((size_t)k2, 16), ldz = kp + k2p;
+    double *F = NULL, *Sfull = NULL, *Gp = NULL, *CG = NULL, *Sm = NULL, *WT = NULL, *W = NULL, *c0 = NULL;
+    double *Z = NULL, *D = NULL;
+    int* d_info = NULL;
+    htn_factor_t fa, fs;
+    memset(&fa, 0, sizeof(fa));
+    memset(&fs, 0, sizeof(fs));
+    cudaStream_t st = ctx->stream;
+
+    HTN_TRY(htn_dalloc(ctx, (void**)&d_info, 2 * sizeof(int)));
+    HTN_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), st));
+    HTN_TRY(htn_dalloc(ctx, (void**)&F, (size_t)k * ldz * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Sfull, (size_t)k * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Gp, (size_t)k2 * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&CG, (size_t)k2 * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&W, (size_t)k2 * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&WT, (size_t)k * k2p * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Sm, (size_t)k2 * k2p * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&c0, (size_t)k2p * 8));
+    HTN_CUDA(cudaMemsetAsync(F, 0, (size_t)k * ldz * 8, st));
+    HTN_CUDA(cudaMemsetAsync(Sfull, 0, (size_t)k * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(Gp, 0, (size_t)k2 * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(CG, 0, (size_t)k2 * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(W, 0, (size_t)k2 * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(Sm, 0, (size_t)k2 * k2p * 8, st));
+
+    /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
+    /* symmetric copy of cov (as the reference's uplo='L' calls see it) and its lower triangle in F */
+    HTN_TRY(htnk_sym_expand(st, cov, (size_t)k, k, lower_src, Sfull, kp, F, ldz));
+    HTN_TRY(htn_factor_init(ctx, &fa, F, ldz, k, 0));
+    HTN_TRY(htn_potrf(ctx, &fa, d_info)); /* dpotrf: src/htnorm_distributions.c:77 */
+    if (flags & HTN_FLAG_COLMAJOR) /* g is k2 x k column-major = k x k2 row-major */
+        HTN_TRY(htnk_transpose(st, g, (size_t)k2, k, k2, Gp, kp));
+    else
+        HTN_TRY(htnk_copy2d(st, g, (size_t)k, k2, k, Gp, kp, NULL));
+    /* cov G^T -> F[:, kp : kp+k2]   (dsymm, src/htnorm.c:154; dsymv :73) */
+    HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, F + kp, ldz, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    HTN_TRY(htnk_transpose(st, F + kp, ldz, k, k2, CG, kp));
+    /* G cov G^T   (dgemm TN, src/htnorm.c:164; ddot :77) */
+    HTN_TRY(htnk_gemm_tn(st, k2, k2, k, 1.0, Gp, kp, CG, kp, 0.0, Sm, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    if (k2 > 1) { /* dposv's factorisation, src/htnorm.c:169; k2 == 1 divides by the scalar (:77) */
+        HTN_TRY(htn_factor_init(ctx, &fs, Sm, k2p, k2, k2 > ALPHA_K2_MAX));
+        HTN_TRY(htn_potrf(ctx, &fs, d_info + 1));
+        if (k2 > ALPHA_K2_MAX) HTN_TRY(htn_factor_make_u(ctx, &fs));
+    }
+    /* W = G L  via  W^T = L^T G^T  (L^T parked in the Sfull buffer, free from here on) */
+    HTN_TRY(htnk_transpose(st, F, ldz, k, k, Sfull, kp));
+    HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, WT, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    HTN_TRY(htnk_transpose(st, WT, k2p, k, k2, W, kp));
+    HTN_TRY(htnk_r_minus_gmean(st, Gp, kp, k2, k, mean, r, c0));
+
+    int h_info[2] = {0, 0};
+    HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
+    HTN_CUDA(cudaStreamSynchronize(st));
+    if (h_info[0]) { /* cov not positive definite: no draw, out untouched (src/htnorm_distributions.c:78) */
+        *first_info = h_info[0];
+        g_cov_failed = 1;
+        goto done;
+    }
+    *first_info = h_info[1]; /* G cov G^T not PD: the unprojected y is returned (src/htnorm.c:169-177) */
+
+    /* ---- per chunk of samples ---- */
+    size_t chunk = nsamples;
+    const size_t budget = (size_t)6 << 30; /* bytes of Z~ per chunk */
+    if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z, chunk * ldz * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
+    for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
+        const size_t nb = nsamples - b0 < chunk ? nsamples - b0 : chunk;
+        htnk_streams_t sv;
+        streams_view(s, b0, &sv);
+        /* zero the pad / alpha columns, then z_b into columns [0, k) back to front */
+        HTN_CUDA(cudaMemset2DAsync(Z + k, ldz * 8, 0, (ldz - (size_t)k) * 8, nb, st));
+        htnk_segment_t seg = {(size_t)k, Z, ldz, NULL, NULL, NULL};
+        HTN_TRY(htnk_normal_fill(st, &sv, nb, 1, &seg, NULL));
+        if (!h_info[1]) {
+            /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
+            HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Z, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+            if (k2 <= ALPHA_K2_MAX) {
+                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, NULL, Z, ldz, kp));
+            } else {
+                HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
+                HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Z + kp, ldz, NULL));
+            }
+        }
+        /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
+        HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Z, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
+                             (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 128));
+    }
+done:
+    htn_factor_free(ctx, &fa);
+    htn_factor_free(ctx, &fs);
+    htn_dfree(ctx, Z);
+    htn_dfree(ctx, D);
+    htn_dfree(ctx, c0);
+    htn_dfree(ctx, Sm);
+    htn_dfree(ctx, WT);
+    htn_dfree(ctx, W);
+    htn_dfree(ctx, CG);
+    htn_dfree(ctx, Gp);
+    htn_dfree(ctx, Sfull);
+    htn_dfree(ctx, F);
+    htn_dfree(ctx, d_info);
+    return rc;
+}
+
+/* diagonal covariance (conf->diag): no factorisation, HBM-bound elementwise kernels
+ * (src/htnorm_distributions.c:62-66, src/htnorm.c:68-71, 138-148) */
+static int ht_shared_diag(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, int k2, int k,
+                          const double* mean, const double* cov, const double* g, const double* r, double* out,
+                          int* first_info)
+{
+    int rc = 0;
+    const size_t kp = htn_round_up((size_t)k, 16), k2p = htn_round_up((size_t)k2, 16);
+    double *var = NULL, *sd = NULL, *Gp = NULL, *CG = NULL, *CGT = NULL, *Sm = NULL, *D = NULL;
+    int* d_info = NULL;
+    htn_factor_t fs;
+    memset(&fs, 0, sizeof(fs));
+    cudaStream_t st = ctx->stream;
+    HTN_TRY(htn_dalloc(ctx, (void**)&d_info, sizeof(int)));
+    HTN_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    HTN_TRY(htn_dalloc(ctx, (void**)&var, kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&sd, kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Gp, (size_t)k2 * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&CG, (size_t)k2 * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&CGT, (size_t)k * k2p * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Sm, (size_t)k2 * k2p * 8));
+    HTN_CUDA(cudaMemsetAsync(Gp, 0, (size_t)k2 * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(CG, 0, (size_t)k2 * kp * 8, st));
+    HTN_CUDA(cudaMemsetAsync(Sm, 0, (size_t)k2 * k2p * 8, st));
+    HTN_TRY(htnk_diag_extract(st, cov, (size_t)k, k, 0, var));
+    HTN_TRY(htnk_diag_extract(st, cov, (size_t)k, k, 1, sd));
+    if (flags & HTN_FLAG_COLMAJOR)
+        HTN_TRY(htnk_transpose(st, g, (size_t)k2, k, k2, Gp, kp));
+    else
+        HTN_TRY(htnk_copy2d(st, g, (size_t)k, k2, k, Gp, kp, NULL));
+    HTN_TRY(htnk_colmul(st, Gp, kp, k2, k, var, CG, kp));
+    HTN_TRY(htnk_transpose(st, CG, kp, k2, k, CGT, k2p));
+    HTN_TRY(htnk_gemm_tn(st, k2, k2, k, 1.0, Gp, kp, CG, kp, 0.0, Sm, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    if (k2 > 1) {
+        HTN_TRY(htn_factor_init(ctx, &fs, Sm, k2p, k2, k2 > ALPHA_K2_MAX));
+        HTN_TRY(htn_potrf(ctx, &fs, d_info));
+        if (k2 > ALPHA_K2_MAX) HTN_TRY(htn_factor_make_u(ctx, &fs));
+    }
+    int h_info = 0;
+    HTN_CUDA(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HTN_CUDA(cudaStreamSynchronize(st));
+    *first_info = h_info;
+
+    HTN_TRY(htn_dalloc(ctx, (void**)&D, nsamples * k2p * 8));
+    htnk_streams_t sv;
+    streams_view(s, 0, &sv);
+    htnk_segment_t seg = {(size_t)k, out, (size_t)k, NULL, sd, mean};
+    HTN_TRY(htnk_normal_fill(st, &sv, nsamples, 1, &seg, NULL)); /* y = mean + sqrt(cov_ii) z, straight into out */
+    if (!h_info) {
+        HTN_TRY(htnk_rows_dot(st, nsamples, k, k2, Gp, kp, out, (size_t)k, D, k2p));
+        if (k2 <= ALPHA_K2_MAX)
+            HTN_TRY(htnk_ht_alpha(st, nsamples, k2, D, k2p, r, Sm, k2p, NULL, D, k2p, 0));
+        else
+            HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nsamples, k2, r));
+        HTN_TRY(htnk_ht_diag_project(st, nsamples, k, k2, CGT, k2p, D, k2p, out, (size_t)k));
+    }
+done:
+    htn_factor_free(ctx, &fs);
+    htn_dfree(ctx, D);
+    htn_dfree(ctx, Sm);
+    htn_dfree(ctx, CGT);
+    htn_dfree(ctx, CG);
+    htn_dfree(ctx, Gp);
+    htn_dfree(ctx, sd);
+    htn_dfree(ctx, var);
+    htn_dfree(ctx, d_info);
+    return rc;
+}
+
+int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int independent, unsigned flags,
+                  size_t k2, size_t k, const double* mean, const double* cov, const double* g, const double* r,
+                  int diag, double* out, int* d_info_out, int* first_info)
+{
+    int rc = 0;
+    *first_info = 0;
+    g_cov_failed = 0;
+    if (nsamples == 0) return 0;
+    if (k == 0 || k2 == 0 || !mean || !cov || !g || !r || !out || k > 0x7fffffffu / 2 || k2 > k ||
+        nsamples > 0x7fffffffu) {
+        htn_set_error("hyperplane: bad argument (k=%zu k2=%zu nsamples=%zu)", k, k2, nsamples);
+        return HTN_E_ARG;
+    }
+    if (independent) {
+        if (k <= SMALL_K_MAX && k2 <= SMALL_K2_MAX) {
+            int* info_dev = d_info_out;
+            int* tmp = NULL;
+            if (!info_dev) {
+                HTN_TRY(htn_dalloc(ctx, (void**)&tmp, nsamples * sizeof(int)));
+                info_dev = tmp;
+            }
+            htnk_streams_t sv;
+            streams_view(s, 0, &sv);
+            rc = htnk_ht_small_batched(ctx->stream, &sv, nsamples, (int)k, (int)k2, mean, cov, g, r, diag,
+                                       (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
+            htn_dfree(ctx, tmp);
+            *first_info = 0; /* per-problem codes live in the device array */
+            return rc;
+        }
+        /* large independent problems: one factorisation each, through the shared-input path */
+        for (size_t i = 0; i < nsamples && !rc; i++) {
+            htn_streams_t si = *s;
+            si.seeds = s->seeds ? s->seeds + i : NULL;
+            si.seed0 = s->seed0 + i;
+            si.states = s->states ? s->states + 4 * i : NULL;
+            int fi = 0;
+            rc = htn_ht_device(ctx, &si, 1, 0, flags, k2, k, mean + i * k, cov + i * k * k, g + i * k2 * k,
+                               r + i * k2, diag, out + i * k, NULL, &fi);
+            if (!rc && d_info_out) rc = htnk_fill_i32(ctx->stream, d_info_out + i, 1, fi);
+            if (fi && !*first_info) *first_info = fi;
+        }
+        return rc;
+    }
+    if (diag)
+        rc = ht_shared_diag(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
+    else
+        rc = ht_shared_dense(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
+    if (!rc && d_info_out) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
+done:
+    return rc;
+}
+
+/* ---- public entry points ---- */
+
+static int upload(htn_ctx_t* ctx, void** dst, const void* src, size_t bytes)
+{
+    int rc = 0;
+    HTN_TRY(htn_dalloc(ctx, dst, bytes));
+    HTN_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+done:
+    return rc;
+}
+
+int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* conf, double* out, int* info)
+{
+    if (!b || !conf || !out) {
+        htn_set_error("hyperplane batch: NULL argument");
+        return HTN_E_ARG;
+    }
+    const size_t B = b->nsamples, k = conf->gncol, k2 = conf->gnrow;
+    const size_t np = b->independent ? B : 1;
+    htn_ctx_t ctx;
+    int rc = htn_ctx_begin(&ctx, b->device, b->stream, b->mem == HTN_MEM_HOST);
+    if (rc) return rc;
+    int first = 0;
+    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL};
+    if (b->mem == HTN_MEM_DEVICE) {
+        rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
+                           conf->diag, out, info, &first);
+        int rc2 = htn_ctx_end(&ctx, 0);
+        return rc ? rc : rc2;
+    }
+    /* host memory: stage in, run, stage out (synchronous) */
+    void *d_mean = NULL, *d_cov = NULL, *d_g = NULL, *d_r = NULL, *d_seeds = NULL, *d_out = NULL, *d_info = NULL;
+    if (B == 0) goto done;
+    if (k == 0 || k2 == 0 || !conf->mean || !conf->cov || !conf->g || !conf->r) {
+        htn_set_error("hyperplane batch: empty or NULL input");
+        rc = HTN_E_ARG;
+        goto done;
+    }
+    HTN_TRY(upload(&ctx, &d_mean, conf->mean, np * k * 8));
+    HTN_TRY(upload(&ctx, &d_cov, conf->cov, np * k * k * 8));
+    HTN_TRY(upload(&ctx, &d_g, conf->g, np * k2 * k * 8));
+    HTN_TRY(upload(&ctx, &d_r, conf->r, np * k2 * 8));
+    if (b->seeds) {
+        HTN_TRY(upload(&ctx, &d_seeds, b->seeds, B * 8));
+        s.seeds = d_seeds;
+    }
+    HTN_TRY(htn_dalloc(&ctx, &d_out, B * k * 8));
+    HTN_TRY(htn_dalloc(&ctx, &d_info, B * sizeof(int)));
+    HTN_CUDA(cudaMemsetAsync(d_info, 0, B * sizeof(int), ctx.stream));
+    if (b->independent) /* a problem whose cov is not PD leaves its row of `out` as the caller had it */
+        HTN_CUDA(cudaMemcpyAsync(d_out, out, B * k * 8, cudaMemcpyHostToDevice, ctx.stream));
+    HTN_TRY(htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
+                          d_info, &first));
+    {
+        int* h_info = info ? info : malloc(B * sizeof(int));
+        if (!h_info) { rc = HTNORM_ALLOC_ERROR; goto done; }
+        HTN_CUDA(cudaMemcpyAsync(h_info, d_info, B * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        HTN_CUDA(cudaStreamSynchronize(ctx.stream));
+        for (size_t i = 0; i < B && !first; i++)
+            if (h_info[i]) first = h_info[i];
+        if (!info) free(h_info);
+    }
+    /* shared inputs with cov not PD: nothing was drawn, `out` stays untouched (reference behaviour) */
+    if (!(first > 0 && !b->independent && !conf->diag && htn_ht_last_cov_failed()))
+    HTN_CUDA(cudaMemcpyAsync(out, d_out, B * k * 8, cudaMemcpyDeviceToHost, ctx.stream));
+done:
+    htn_dfree(&ctx, d_info);
+    htn_dfree(&ctx, d_out);
+    htn_dfree(&ctx, d_seeds);
+    htn_dfree(&ctx, d_r);
+    htn_dfree(&ctx, d_g);
+    htn_dfree(&ctx, d_cov);
+    htn_dfree(&ctx, d_mean);
+    {
+        int rc2 = htn_ctx_end(&ctx, 1);
+        if (!rc) rc = rc2;
+    }
+    return rc ? rc : first;
+}
+
+/* Single draw through the reference's own signature (include/htnorm.h).  The generator must be one of
+ * this library's (function-pointer identity): its state is uploaded, advanced on the GPU by exactly the
+ * draws the reference would make, and written back. */
+int htn_hyperplane_truncated_mvn(rng_t* rng, const ht_config_t* conf, double* HTN_RESTRICT out)
+{
+    if (!rng || !conf || !out) {
+        htn_set_error("hyperplane: NULL argument");
+        return HTN_E_ARG;
+    }
+    const int kind = htn_rng_kind(rng);
+    if (kind < 0) {
+        htn_set_error("rng_t was not created by rng_pcg64_new*/rng_xrs128p_new*: foreign generators "
+                      "cannot run on the device");
+        return HTN_E_FOREIGN_RNG;
+    }
+    const size_t k = conf->gncol, k2 = conf->gnrow;
+    htn_ctx_t ctx;
+    int rc = htn_ctx_begin(&ctx, -1, NULL, 1);
+    if (rc) return rc;
+    int first = 0;
+    void *d_mean = NULL, *d_cov = NULL, *d_g = NULL, *d_r = NULL, *d_out = NULL, *d_state = NULL;
+    uint64_t h_state[4] = {0, 0, 0, 0};
+    memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
+    if (k == 0 || k2 == 0) { rc = HTN_E_ARG; goto done; }
+    HTN_TRY(upload(&ctx, &d_mean, conf->mean, k * 8));
+    HTN_TRY(upload(&ctx, &d_cov, conf->cov, k * k * 8));
+    HTN_TRY(upload(&ctx, &d_g, conf->g, k2 * k * 8));
+    HTN_TRY(upload(&ctx, &d_r, conf->r, k2 * 8));
+    HTN_TRY(upload(&ctx, &d_state, h_state, sizeof(h_state)));
+    HTN_TRY(upload(&ctx, &d_out, out, k * 8)); /* a failed factorisation must leave out as it was */
+    {
+        htn_streams_t s = {kind, NULL, 0, (uint64_t*)d_state};
+        HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, 0, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL, &first));
+    }
+    HTN_CUDA(cudaMemcpyAsync(out, d_out, k * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    HTN_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(h_state), cudaMemcpyDeviceToHost, ctx.stream));
+    HTN_CUDA(cudaStreamSynchronize(ctx.stream));
+    memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
+done:
+    htn_dfree(&ctx, d_state);
+    htn_dfree(&ctx, d_out);
+    htn_dfree(&ctx, d_r);
+    htn_dfree(&ctx, d_g);
+    htn_dfree(&ctx, d_cov);
+    htn_dfree(&ctx, d_mean);
+    {
+        int rc2 = htn_ctx_end(&ctx, 1);
+        if (!rc) rc = rc2;
+    }
+    return rc ? rc : first;
+}

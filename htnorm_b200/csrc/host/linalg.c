@@ -1,0 +1,129 @@
+/* Blocked dense drivers of the host layer: every O(n^3) step is a sequence of DMMA GEMM launches
+ * (htnk_gemm_tn) around the shared-memory diagonal-block kernel (htnk_potf2_inv).
+ *
+ *   htn_potrf          <-> dpotrf('L')   reference src/htnorm_distributions.c:77,115
+ *   htn_trsm_right_*   <-> dtrsv / the solve phases of dposv, dpotri   src/htnorm_distributions.c:120,
+ *                                                                     src/htnorm.c:169,210,330
+ * All matrices row-major.  "right" solves act on ROWS of X (one row = one sample / one right-hand
+ * side), which keeps every operand K-contiguous for the TN GEMM.
+ */
+#include "htn_internal.h"
+
+#include <string.h>
+
+int htn_factor_init(htn_ctx_t* ctx, htn_factor_t* fa, double* f, size_t ld, int n, int want_u)
+{
+    int rc = 0;
+    memset(fa, 0, sizeof(*fa));
+    fa->n = n;
+    fa->ld = ld;
+    fa->f = f;
+    fa->nblk = (n + HTN_NB - 1) / HTN_NB;
+    size_t blk = (size_t)HTN_NB * HTN_NB * sizeof(double);
+    HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinv, blk * fa->nblk));
+    HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinvt, blk * fa->nblk));
+    HTN_CUDA(cudaMemsetAsync(fa->dinv, 0, blk * fa->nblk, ctx->stream));
+    HTN_CUDA(cudaMemsetAsync(fa->dinvt, 0, blk * fa->nblk, ctx->stream));
+    if (want_u) {
+        HTN_TRY(htn_dalloc(ctx, (void**)&fa->u, (size_t)n * ld * sizeof(double)));
+    }
+done:
+    return rc;
+}
+
+void htn_factor_free(htn_ctx_t* ctx, htn_factor_t* fa)
+{
+    htn_dfree(ctx, fa->dinv);
+    htn_dfree(ctx, fa->dinvt);
+    htn_dfree(ctx, fa->u);
+    fa->dinv = fa->dinvt = fa->u = NULL;
+}
+
+int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa)
+{
+    int rc = 0;
+    if (!fa->u) HTN_TRY(htn_dalloc(ctx, (void**)&fa->u, (size_t)fa->n * fa->ld * sizeof(double)));
+    HTN_CUDA(cudaMemsetAsync(fa->u, 0, (size_t)fa->n * fa->ld * sizeof(double), ctx->stream));
+    HTN_TRY(htnk_transpose(ctx->stream, fa->f, fa->ld, fa->n, fa->n, fa->u, fa->ld));
+done:
+    return rc;
+}
+
+int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
+{
+    int rc = 0;
+    const int n = fa->n;
+    const size_t ld = fa->ld;
+    for (int jb = 0; jb < fa->nblk; jb++) {
+        const int j0 = jb * HTN_NB;
+        const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
+        double* ajj = fa->f + (size_t)j0 * ld + j0;
+        double* dinv = fa->dinv + (size_t)jb * HTN_NB * HTN_NB;
+        double* dinvt = fa->dinvt + (size_t)jb * HTN_NB * HTN_NB;
+        HTN_TRY(htnk_potf2_inv(ctx->stream, ajj, ld, nb, j0, dinv, dinvt, d_info));
+        const int rows = n - j0 - nb;
+        if (rows <= 0) break;
+        double* a21 = fa->f + (size_t)(j0 + nb) * ld + j0;
+        /* panel: L21 = A21 * inv(L11)^T  (in place: one N tile spans the panel, K loop ends before the
+         * epilogue writes) */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, nb, nb, 1.0, a21, ld, dinv, HTN_NB, 0.0, a21, ld, NULL,
+                             HTNK_GEMM_FULL, 0, 0, 128));
+        /* trailing update: A22 -= L21 * L21^T on the lower-triangle tiles */
+        double* a22 = fa->f + (size_t)(j0 + nb) * ld + (j0 + nb);
+        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, a21, ld, a21, ld, 1.0, a22, ld, NULL,
+                             HTNK_GEMM_C_LOWER, 0, 0, 128));
+    }
+done:
+    return rc;
+}
+
+/* X_new * L^T = X : forward over column blocks */
+int htn_trsm_right_lt(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m)
+{
+    int rc = 0;
+    for (int jb = 0; jb < fa->nblk; jb++) {
+        const int j0 = jb * HTN_NB;
+        const int nb = fa->n - j0 < HTN_NB ? fa->n - j0 : HTN_NB;
+        double* xj = x + j0;
+        if (j0 > 0) /* X_j -= X_{<j} * L[j, <j]^T */
+            HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, j0, -1.0, x, ldx, fa->f + (size_t)j0 * fa->ld, fa->ld, 1.0,
+                                 xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
+        /* X_j = X_j * inv(L_jj)^T : B[n][kk] = dinv[n][kk] */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, nb, 1.0, xj, ldx, fa->dinv + (size_t)jb * HTN_NB * HTN_NB, HTN_NB,
+                             0.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
+    }
+done:
+    return rc;
+}
+
+/* X_new * L = X : backward over column blocks; B[n][kk] = L[j1+kk][j0+n] = U[j0+n][j1+kk] */
+int htn_trsm_right_l(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m)
+{
+    int rc = 0;
+    if (!fa->u) {
+        htn_set_error("internal: factor has no transposed copy");
+        return HTN_E_ARG;
+    }
+    for (int jb = fa->nblk - 1; jb >= 0; jb--) {
+        const int j0 = jb * HTN_NB;
+        const int nb = fa->n - j0 < HTN_NB ? fa->n - j0 : HTN_NB;
+        const int j1 = j0 + nb;
+        double* xj = x + j0;
+        if (j1 < fa->n)
+            HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, fa->n - j1, -1.0, x + j1, ldx,
+                                 fa->u + (size_t)j0 * fa->ld + j1, fa->ld, 1.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0,
+                                 0, 128));
+        /* X_j = X_j * inv(L_jj) : B[n][kk] = dinv[kk][n] = dinvt[n][kk] */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, nb, 1.0, xj, ldx, fa->dinvt + (size_t)jb * HTN_NB * HTN_NB,
+                             HTN_NB, 0.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
+    }
+done:
+    return rc;
+}
+
+int htn_potrs_rows(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m)
+{
+    int rc = htn_trsm_right_lt(ctx, fa, x, ldx, m);
+    if (!rc) rc = htn_trsm_right_l(ctx, fa, x, ldx, m);
+    return rc;
+}

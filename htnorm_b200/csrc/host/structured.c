@@ -1,0 +1,296 @@
+/* Structured-precision MVN sampler: x ~ N(mean, (A + Phi^T Omega Phi)^-1), optionally with the
+ * structured mean of Example 4 (Cong et al. 2017, Alg. 4).
+ *
+ * Reference path restated for a batch (src/htnorm.c:217-356, src/htnorm_distributions.c:91-125):
+ *     y1 ~ N(0, A^-1),  y2 ~ N(0, Omega^-1)      (two runs of normals from the SAME stream, y1 first)
+ *     M = Omega^-1 + Phi A^-1 Phi^T,   b = Phi y1 + y2   (struct mean: b = t - b)
+ *     x = mean + y1 + X M^-1 b         (struct mean: x = y1 - X M^-1 b),   X = A^-1 Phi^T
+ * The signs are the REFERENCE's (+1 / -1, src/htnorm.c:229,320,336,343) unless
+ * HTN_FLAG_PAPER_SIGN is set.  An IDENTITY Omega reproduces the reference's memset quirk.
+ *
+ * Once per batch: chol(A), chol(Omega), X^T = Phi A^-1 (two blocked TRSMs instead of the reference's
+ * explicit dpotri + dsymm), M (one DMMA GEMM), chol(M).  Per sample everything is a row of a GEMM / TRSM
+ * over the batch: Y1 = Z1 L_A^-1, B = Z2' + Y1 Phi^T, Alpha = B M^-1, out = Y1 + mean + coef Alpha X^T.
+ */
+#include "htn_internal.h"
+
+#include <string.h>
+
+/* value of every double of the reference's IDENTITY "factor": memset(factor, 1, n * sizeof(double))
+ * (src/htnorm_distributions.c:99) -> bytes 0x01 -> 7.7486e-304; Omega^-1 gets 1 / that (src/htnorm.c:203) */
+static double identity_factor_garbage(void)
+{
+    double d;
+    memset(&d, 1, sizeof(d));
+    return d;
+}
+
+/* stage a dense SPD input: lower triangle into a fresh n x ld buffer, factorise, build L^T */
+static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src, double** buf, htn_factor_t* fa,
+                        int* d_info)
+{
+    int rc = 0;
+    const size_t ld = htn_round_up((size_t)n, 16);
+    HTN_TRY(htn_dalloc(ctx, (void**)buf, (size_t)n * ld * 8));
+    HTN_CUDA(cudaMemsetAsync(*buf, 0, (size_t)n * ld * 8, ctx->stream));
+    HTN_TRY(htnk_sym_expand(ctx->stream, src, (size_t)n, n, lower_src, NULL, 0, *buf, ld));
+    HTN_TRY(htn_factor_init(ctx, fa, *buf, ld, n, 1));
+    HTN_TRY(htn_potrf(ctx, fa, d_info));
+    HTN_TRY(htn_factor_make_u(ctx, fa));
+done:
+    return rc;
+}
+
+int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, size_t n_, size_t p_,
+                  const double* mean, const double* a, const double* phi, const double* omega, int struct_mean,
+                  int a_id, int o_id, double* out, int* d_info_out, int* first_info)
+{
+    int rc = 0;
+    *first_info = 0;
+    if (nsamples == 0) return 0;
+    if (n_ == 0 || p_ == 0 || !mean || !phi || !out || (a_id != IDENTITY && !a) || (o_id != IDENTITY && !omega) ||
+        n_ > 0x3fffffffu || p_ > 0x3fffffffu || nsamples > 0x7fffffffu || a_id < 0 || a_id > 2 || o_id < 0 ||
+        o_id > 2) {
+        htn_set_error("structured precision: bad argument (n=%zu p=%zu nsamples=%zu)", n_, p_, nsamples);
+        return HTN_E_ARG;
+    }
+    const int n = (int)n_, p = (int)p_;
+    const int lower_src = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
+    const size_t pp = htn_round_up(p_, 16), np = htn_round_up(n_, 16);
+    cudaStream_t st = ctx->stream;
+    double *Phip = NULL, *FA = NULL, *FO = NULL, *XT = NULL, *X = NULL, *M = NULL;
+    double *da = NULL, *sda = NULL, *sdo = NULL, *invo = NULL, *Z1 = NULL, *Z2 = NULL;
+    int* d_info = NULL;
+    htn_factor_t fa, fo, fm;
+    memset(&fa, 0, sizeof(fa));
+    memset(&fo, 0, sizeof(fo));
+    memset(&fm, 0, sizeof(fm));
+
+    HTN_TRY(htn_dalloc(ctx, (void**)&d_info, 3 * sizeof(int)));
+    HTN_CUDA(cudaMemsetAsync(d_info, 0, 3 * sizeof(int), st));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Phip, (size_t)n * pp * 8));
+    HTN_CUDA(cudaMemsetAsync(Phip, 0, (size_t)n * pp * 8, st));
+    if (flags & HTN_FLAG_COLMAJOR) /* phi is n x p column-major = p x n row-major */
+        HTN_TRY(htnk_transpose(st, phi, (size_t)n, p, n, Phip, pp));
+    else
+        HTN_TRY(htnk_copy2d(st, phi, (size_t)p, n, p, Phip, pp, NULL));
+
+    /* ---- A: factor (dense) or diagonal (mvn_rand_prec, src/htnorm_distributions.c:96-123) ---- */
+    if (a_id == NORMAL) {
+        HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
+    } else if (a_id == DIAGONAL) {
+        HTN_TRY(htn_dalloc(ctx, (void**)&da, pp * 8));
+        HTN_TRY(htn_dalloc(ctx, (void**)&sda, pp * 8));
+        HTN_TRY(htnk_diag_extract(st, a, (size_t)p, p, 0, da));
+        HTN_TRY(htnk_diag_extract(st, a, (size_t)p, p, 1, sda));
+    }
+    /* ---- Omega ---- */
+    if (o_id == NORMAL) {
+        HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1));
+    } else if (o_id == DIAGONAL) {
+        HTN_TRY(htn_dalloc(ctx, (void**)&sdo, np * 8));
+        HTN_TRY(htn_dalloc(ctx, (void**)&invo, np * 8));
+        HTN_TRY(htnk_diag_extract(st, omega, (size_t)n, n, 1, sdo));
+        HTN_TRY(htnk_diag_extract(st, omega, (size_t)n, n, 2, invo));
+    }
+    /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two TRSMs) ---- */
+    if (a_id == IDENTITY) {
+        XT = Phip;
+    } else {
+        HTN_TRY(htn_dalloc(ctx, (void**)&XT, (size_t)n * pp * 8));
+        HTN_CUDA(cudaMemsetAsync(XT, 0, (size_t)n * pp * 8, st));
+        if (a_id == DIAGONAL) {
+            HTN_TRY(htnk_coldiv(st, Phip, pp, n, p, da, XT, pp));
+        } else {
+            HTN_TRY(htnk_copy2d(st, Phip, pp, n, p, XT, pp, NULL));
+            HTN_TRY(htn_potrs_rows(ctx, &fa, XT, pp, n));
+        }
+    }
+    /* ---- M = Omega^-1 + X^T Phi^T  (compute_precision_inverse, src/htnorm.c:190-214; dgemm/dsyrk :267-300) */
+    HTN_TRY(htn_dalloc(ctx, (void**)&M, (size_t)n * np * 8));
+    HTN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * np * 8, st));
+    if (o_id == NORMAL) {
+        HTN_TRY(htnk_diag_set(st, M, np, n, NULL, 1.0));
+        HTN_TRY(htn_potrs_rows(ctx, &fo, M, np, n));
+    } else if (o_id == DIAGONAL) {
+        HTN_TRY(htnk_diag_set(st, M, np, n, invo, 0.0));
+    } else {
+        HTN_TRY(htnk_diag_set(st, M, np, n, NULL, 1 / identity_factor_garbage()));
+    }
+    HTN_TRY(htnk_gemm_tn(st, n, n, p, 1.0, XT, pp, Phip, pp, 1.0, M, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    HTN_TRY(htn_factor_init(ctx, &fm, M, np, n, 1));
+    HTN_TRY(htn_potrf(ctx, &fm, d_info + 2)); /* dposv, src/htnorm.c:330 */
+    HTN_TRY(htn_factor_make_u(ctx, &fm));
+    /* X = (X^T)^T, p x n: the B operand of the final GEMM */
+    HTN_TRY(htn_dalloc(ctx, (void**)&X, (size_t)p * np * 8));
+    HTN_CUDA(cudaMemsetAsync(X, 0, (size_t)p * np * 8, st));
+    HTN_TRY(htnk_transpose(st, XT, pp, n, p, X, np));
+
+    int h_info[3] = {0, 0, 0};
+    HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
+    HTN_CUDA(cudaStreamSynchronize(st));
+    if (h_info[0]) { /* A not PD: returned before any draw (src/htnorm.c:245) */
+        *first_info = h_info[0];
+        goto finish;
+    }
+
+    double coef = struct_mean ? -1.0 : 1.0;
+    if (flags & HTN_FLAG_PAPER_SIGN) coef = -coef;
+    size_t chunk = nsamples;
+    const size_t budget = (size_t)6 << 30;
+    if (chunk * (pp + np) * 8 > budget) chunk = htn_round_up(budget / ((pp + np) * 8), 128);
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z1, chunk * pp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z2, chunk * np * 8));
+    for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
+        const int nb = (int)(nsamples - b0 < chunk ? nsamples - b0 : chunk);
+        htnk_streams_t sv = {s->gen, s->seeds ? s->seeds + b0 : NULL, s->seed0 + (uint64_t)b0,
+                             s->states ? s->states + 4 * b0 : NULL};
+        htnk_segment_t seg[2] = {{(size_t)p, Z1, pp, a_id == DIAGONAL ? sda : NULL, NULL, NULL},
+                                 {(size_t)n, Z2, np, o_id == DIAGONAL ? sdo : NULL, NULL, NULL}};
+        if (h_info[1]) { /* Omega not PD: y1 was drawn (stream advanced), then the call fails (:246) */
+            HTN_TRY(htnk_normal_fill(st, &sv, (size_t)nb, 1, seg, NULL));
+            continue;
+        }
+        HTN_TRY(htnk_normal_fill(st, &sv, (size_t)nb, 2, seg, NULL));
+        if (a_id == NORMAL) HTN_TRY(htn_trsm_right_l(ctx, &fa, Z1, pp, nb)); /* L^T y1 = z (dtrsv, :120) */
+        if (o_id == NORMAL) HTN_TRY(htn_trsm_right_l(ctx, &fo, Z2, np, nb));
+        /* b = Phi y1 + y2 (dgemm, src/htnorm.c:310) */
+        HTN_TRY(htnk_gemm_tn(st, nb, n, p, 1.0, Z1, pp, Phip, pp, 1.0, Z2, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        double* o = out + b0 * p_;
+        if (struct_mean) { /* src/htnorm.c:314-321 */
+            HTN_TRY(htnk_rsub_rows(st, Z2, np, nb, n, mean));
+            HTN_TRY(htnk_copy2d(st, Z1, pp, nb, p, o, p_, NULL));
+        } else { /* src/htnorm.c:322-326 */
+            HTN_TRY(htnk_copy2d(st, Z1, pp, nb, p, o, p_, mean));
+        }
+        if (h_info[2]) continue; /* M not PD: out keeps y1 (+ mean), as after a failed dposv (:330-346) */
+        HTN_TRY(htn_potrs_rows(ctx, &fm, Z2, np, nb));
+        /* out += coef * alpha X^T  (dgemv / dgemm, src/htnorm.c:332-346) */
+        HTN_TRY(htnk_gemm_tn(st, nb, p, n, coef, Z2, np, X, np, 1.0, o, p_, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    }
+    *first_info = h_info[1] ? h_info[1] : h_info[2];
+finish:
+    if (d_info_out) rc = htnk_fill_i32(st, d_info_out, nsamples, *first_info);
+done:
+    htn_factor_free(ctx, &fa);
+    htn_factor_free(ctx, &fo);
+    htn_factor_free(ctx, &fm);
+    htn_dfree(ctx, Z1);
+    htn_dfree(ctx, Z2);
+    htn_dfree(ctx, X);
+    htn_dfree(ctx, M);
+    if (XT != Phip) htn_dfree(ctx, XT);
+    htn_dfree(ctx, invo);
+    htn_dfree(ctx, sdo);
+    htn_dfree(ctx, sda);
+    htn_dfree(ctx, da);
+    htn_dfree(ctx, FO);
+    htn_dfree(ctx, FA);
+    htn_dfree(ctx, Phip);
+    htn_dfree(ctx, d_info);
+    return rc;
+}
+
+static int upload(htn_ctx_t* ctx, void** dst, const void* src, size_t bytes)
+{
+    int rc = 0;
+    *dst = NULL;
+    if (!src) return 0;
+    HTN_TRY(htn_dalloc(ctx, dst, bytes));
+    HTN_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+done:
+    return rc;
+}
+
+/* host arrays -> device, run, -> host.  states_host (4 words) non-NULL: single draw continuing a generator */
+static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint64_t seed0, uint64_t* states_host,
+                   size_t B, unsigned flags, int device, double* out, int* info)
+{
+    const size_t n = conf->pnrow, p = conf->pncol;
+    htn_ctx_t ctx;
+    int rc = htn_ctx_begin(&ctx, device, NULL, 1);
+    if (rc) return rc;
+    int first = 0;
+    void *d_mean = NULL, *d_a = NULL, *d_phi = NULL, *d_om = NULL, *d_seeds = NULL, *d_out = NULL, *d_info = NULL,
+         *d_state = NULL;
+    if (B == 0) goto done;
+    if (n == 0 || p == 0 || !conf->mean || !conf->phi || !out) {
+        htn_set_error("structured precision: empty or NULL input");
+        rc = HTN_E_ARG;
+        goto done;
+    }
+    HTN_TRY(upload(&ctx, &d_mean, conf->mean, (conf->struct_mean ? n : p) * 8));
+    /* DIAGONAL / IDENTITY matrices are still full square arrays in the reference's API; only the
+     * diagonal is read (src/htnorm_distributions.c:106-107) */
+    if (conf->a_id != IDENTITY) HTN_TRY(upload(&ctx, &d_a, conf->a, p * p * 8));
+    if (conf->o_id != IDENTITY) HTN_TRY(upload(&ctx, &d_om, conf->omega, n * n * 8));
+    HTN_TRY(upload(&ctx, &d_phi, conf->phi, n * p * 8));
+    if (seeds) HTN_TRY(upload(&ctx, &d_seeds, seeds, B * 8));
+    if (states_host) HTN_TRY(upload(&ctx, &d_state, states_host, 32));
+    HTN_TRY(upload(&ctx, &d_out, out, B * p * 8)); /* failed factorisations leave `out` as it was */
+    HTN_TRY(htn_dalloc(&ctx, &d_info, B * sizeof(int)));
+    {
+        htn_streams_t s = {gen, (const uint64_t*)d_seeds, seed0, (uint64_t*)d_state};
+        HTN_TRY(htn_sp_device(&ctx, &s, B, flags, n, p, d_mean, d_a, d_phi, d_om, conf->struct_mean, conf->a_id,
+                              conf->o_id, d_out, d_info, &first));
+    }
+    if (info) HTN_CUDA(cudaMemcpyAsync(info, d_info, B * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    HTN_CUDA(cudaMemcpyAsync(out, d_out, B * p * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (states_host) HTN_CUDA(cudaMemcpyAsync(states_host, d_state, 32, cudaMemcpyDeviceToHost, ctx.stream));
+done:
+    htn_dfree(&ctx, d_state);
+    htn_dfree(&ctx, d_info);
+    htn_dfree(&ctx, d_out);
+    htn_dfree(&ctx, d_seeds);
+    htn_dfree(&ctx, d_om);
+    htn_dfree(&ctx, d_phi);
+    htn_dfree(&ctx, d_a);
+    htn_dfree(&ctx, d_mean);
+    {
+        int rc2 = htn_ctx_end(&ctx, 1);
+        if (!rc) rc = rc2;
+    }
+    return rc ? rc : first;
+}
+
+int htn_structured_precision_mvn_batch(const htn_batch_t* b, const sp_config_t* conf, double* out, int* info)
+{
+    if (!b || !conf || !out) {
+        htn_set_error("structured precision batch: NULL argument");
+        return HTN_E_ARG;
+    }
+    if (b->independent) {
+        htn_set_error("structured precision: independent problems are not supported");
+        return HTN_E_ARG;
+    }
+    if (b->mem == HTN_MEM_HOST)
+        return sp_host(conf, (int)b->gen, b->seeds, b->seed0, NULL, b->nsamples, b->flags, b->device, out, info);
+    htn_ctx_t ctx;
+    int rc = htn_ctx_begin(&ctx, b->device, b->stream, 0);
+    if (rc) return rc;
+    int first = 0;
+    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL};
+    rc = htn_sp_device(&ctx, &s, b->nsamples, b->flags, conf->pnrow, conf->pncol, conf->mean, conf->a, conf->phi,
+                       conf->omega, conf->struct_mean, conf->a_id, conf->o_id, out, info, &first);
+    int rc2 = htn_ctx_end(&ctx, 0);
+    return rc ? rc : rc2;
+}
+
+int htn_structured_precision_mvn(rng_t* rng, const sp_config_t* conf, double* HTN_RESTRICT out)
+{
+    if (!rng || !conf || !out) {
+        htn_set_error("structured precision: NULL argument");
+        return HTN_E_ARG;
+    }
+    const int kind = htn_rng_kind(rng);
+    if (kind < 0) {
+        htn_set_error("rng_t was not created by rng_pcg64_new*/rng_xrs128p_new*: foreign generators "
+                      "cannot run on the device");
+        return HTN_E_FOREIGN_RNG;
+    }
+    uint64_t h_state[4] = {0, 0, 0, 0};
+    memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
+    int rc = sp_host(conf, kind, NULL, 0, h_state, 1, 0, -1, out, NULL);
+    if (rc >= 0 || rc == HTNORM_ALLOC_ERROR) memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
+    return rc;
+}

@@ -1,0 +1,276 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libhtnorm_b200.so),
+against the oracle on the same seeded inputs, against the golden vectors generated from the unmodified
+reference, and - at sizes the oracle cannot reach - through size-independent properties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import REL_TOL, RESID_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h():
+    import htnorm_b200
+    assert htnorm_b200.lib.htn_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return htnorm_b200
+
+
+# ------------------------------------------------------------------ generators / ziggurat (bit-exact)
+
+@pytest.mark.parametrize("gen", ["pcg64", "xrs128p"])
+def test_raw_streams_bit_exact(h, oracle, gold, gen):
+    seeds = gold["rng"]["seeds"]
+    got = h.raw_streams(len(seeds), 64, gen=gen, seeds=seeds)
+    assert np.array_equal(got, gold["rng"][f"raw_{gen}"])
+    got = h.raw_streams(1000, 257, gen=gen, seed0=99)          # ragged sizes, seed0 + i seeding
+    assert np.array_equal(got, oracle.raw(gen, 1000, 257, seed0=99))
+
+
+@pytest.mark.parametrize("gen", ["pcg64", "xrs128p"])
+def test_ziggurat_decisions_bit_exact(h, oracle, gold, gen):
+    seeds = gold["rng"]["seeds"]
+    z, nd = h.standard_normals(len(seeds), 3000, gen=gen, seeds=seeds)
+    gz, gnd = gold["rng"][f"normals_{gen}"], gold["rng"][f"ndraws_{gen}"]
+    assert np.array_equal(nd, gnd), "accept/reject history differs from the reference"
+    # fast path and wedge values are rabs * wi: bit-exact.  Tail values go through log(): <= 2 ulp.
+    same = z.view(np.uint64) == gz.view(np.uint64)
+    assert same.mean() > 0.9995
+    assert np.abs(z - gz).max() <= 4 * np.finfo(float).eps * 8
+    # more streams than a warp, lengths that are not multiples of the 32-wide staging tile
+    for nstreams, n in [(1, 1), (33, 31), (70, 100), (257, 1000)]:
+        z, nd = h.standard_normals(nstreams, n, gen=gen, seed0=7)
+        oz, ond = oracle.normals(gen, nstreams, n, seed0=7)
+        assert np.array_equal(nd, ond)
+        assert np.allclose(z, oz, rtol=0, atol=1e-14)
+        assert (z.view(np.uint64) == oz.view(np.uint64)).mean() > 0.999
+
+
+def test_ziggurat_large_property(h):
+    """full-size property check: 2^16 streams x 1000 normals (BASELINE north-star batch): moments and
+    the 1.0221 draws/normal consumption rate of the reference's ziggurat."""
+    z, nd = h.standard_normals(1 << 16, 1000, gen="pcg64", seed0=12345)
+    assert abs(z.mean()) < 1e-3 and abs(z.var() - 1) < 2e-3
+    assert abs(nd.mean() / 1000 - 1.0221) < 2e-3
+
+
+# ------------------------------------------------------------------ dense building blocks
+
+def _dbg(h):
+    lib = h.lib
+    lib.htn_dbg_gemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_size_t, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+    lib.htn_dbg_potrf_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 16, 128), (200, 130, 50, 128), (37, 5, 1000, 8),
+                                      (300, 20, 77, 32), (1, 1, 1, 8), (257, 300, 130, 128),
+                                      (513, 64, 640, 0)])
+def test_gemm_tn(h, M, N, K, bn):
+    lib = _dbg(h)
+    rng = np.random.default_rng(M * 7 + N)
+    lda = ldb = (K + 15) // 16 * 16
+    A = rng.standard_normal((M, lda))
+    B = rng.standard_normal((N, ldb))
+    for ldc in (N, N + 3):
+        Cm = rng.standard_normal((M, ldc))
+        bias = rng.standard_normal(N)
+        want = Cm.copy()
+        want[:, :N] = 0.5 * A[:, :K] @ B[:, :K].T + 2.0 * Cm[:, :N] + bias
+        rc = lib.htn_dbg_gemm_tn(M, N, K, 0.5, A.ctypes.data, lda, B.ctypes.data, ldb, 2.0, Cm.ctypes.data, ldc,
+                                 bias.ctypes.data, 0, 0, 0, bn)
+        assert rc == 0, h._lib.last_error()
+        assert np.abs(Cm - want).max() < 1e-11 * max(1, K)
+
+
+def test_gemm_lower_trapezoid(h):
+    """mode B_LOWER: K range clipped to the non-zero part of a lower-trapezoidal B plus dense extra columns"""
+    lib = _dbg(h)
+    rng = np.random.default_rng(5)
+    k, k2, M = 300, 3, 150
+    kp = (k + 15) // 16 * 16
+    K = kp + k2
+    ld = kp + 16
+    B = np.zeros((k, ld))
+    B[:, :k] = np.tril(rng.standard_normal((k, k)))
+    B[:, kp:kp + k2] = rng.standard_normal((k, k2))
+    A = np.zeros((M, ld))
+    A[:, :k] = rng.standard_normal((M, k))
+    A[:, kp:kp + k2] = rng.standard_normal((M, k2))
+    Cm = np.zeros((M, k))
+    bias = rng.standard_normal(k)
+    rc = lib.htn_dbg_gemm_tn(M, k, K, 1.0, A.ctypes.data, ld, B.ctypes.data, ld, 0.0, Cm.ctypes.data, k,
+                             bias.ctypes.data, 1, k, kp, 128)
+    assert rc == 0
+    assert np.abs(Cm - (A[:, :K] @ B[:, :K].T + bias)).max() < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 128, 129, 300, 1000])
+def test_potrf_and_solves(h, oracle, n):
+    lib = _dbg(h)
+    rng = np.random.default_rng(n)
+    a = cases.spd(rng, n)
+    l = np.empty((n, n))
+    x0 = rng.standard_normal((5, n))
+    want_l, info = oracle.potrf(a)
+    for op in (1, 2, 3):
+        x = x0.copy()
+        rc = lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, op, 5, x.ctypes.data)
+        assert rc == 0, h._lib.last_error()
+        assert np.abs(l - want_l).max() < 1e-12
+        linv = np.linalg.inv(want_l)
+        want = {1: x0 @ linv.T, 2: x0 @ linv, 3: x0 @ linv.T @ linv}[op]
+        assert np.abs(x - want).max() < 1e-10
+
+
+def test_potrf_not_pd_and_nan(h):
+    lib = _dbg(h)
+    n = 200
+    rng = np.random.default_rng(1)
+    a = cases.spd(rng, n)
+    a[150, 150] = -1.0
+    l = np.empty((n, n))
+    assert lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 0, 0, None) == 151
+    a = cases.spd(rng, n)
+    a[0, 0] = np.nan
+    assert lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 0, 0, None) == 0
+    assert np.isnan(l[:, 0]).all()
+
+
+# ------------------------------------------------------------------ samplers vs golden / oracle
+
+@pytest.mark.parametrize("name", cases.HT_CASES)
+def test_hyperplane_golden(h, gold, name):
+    c = cases.ht_case(name)
+    x, info = h.hyperplane_truncated_mvnorm_batch(c["nsamples"], c["mean"], c["cov"], c["g"], c["r"],
+                                                  diag=c["diag"], gen=c["gen"], seed0=c["seed0"])
+    g = gold["hyperplane"]
+    assert np.array_equal(info, g[name + "__info"])
+    tol = 1e-6 if name == "readme_k1000" else REL_TOL   # README cov = t t^T: kappa ~ 1e9
+    assert rel_err(x, g[name + "__x"]) < tol
+    resid = np.abs(x @ c["g"].T - c["r"]).max(axis=1)
+    scale = np.linalg.norm(c["r"]) if np.linalg.norm(c["r"]) > 0 else 1.0
+    if name != "readme_k1000":
+        assert (resid / scale).max() < RESID_TOL * 10 * max(1.0, np.abs(x).max())
+
+
+def test_hyperplane_independent_golden(h, gold):
+    c = cases.ht_independent_case()
+    x, info = h.hyperplane_truncated_mvnorm_batch(c["nsamples"], c["mean"], c["cov"], c["g"], c["r"],
+                                                  gen=c["gen"], seed0=c["seed0"], independent=True)
+    assert not info.any()
+    assert rel_err(x, gold["hyperplane"]["independent__x"]) < REL_TOL
+
+
+@pytest.mark.parametrize("name", cases.SP_CASES)
+def test_structured_golden(h, gold, name):
+    c = cases.sp_case(name)
+    x, info = h.structured_precision_mvnorm_batch(c["nsamples"], c["mean"], c["a"], c["phi"], c["omega"],
+                                                  c["struct_mean"], c["a_type"], c["o_type"], gen=c["gen"],
+                                                  seed0=c["seed0"])
+    g = gold["structured"]
+    assert np.array_equal(info, g[name + "__info"])
+    assert rel_err(x, g[name + "__x"]) < REL_TOL
+
+
+def test_hyperplane_vs_oracle_fresh_inputs(h, oracle):
+    rng = np.random.default_rng(2024)
+    for (k2, k, B, gen) in [(1, 130, 200, "pcg64"), (5, 257, 150, "xrs128p"), (17, 200, 40, "pcg64"),
+                            (40, 300, 33, "pcg64")]:
+        cov = cases.spd(rng, k)
+        g = rng.standard_normal((k2, k))
+        r = rng.standard_normal(k2)
+        mu = rng.standard_normal(k)
+        seeds = rng.integers(0, 2**63, size=B, dtype=np.uint64)
+        x, info = h.hyperplane_truncated_mvnorm_batch(B, mu, cov, g, r, gen=gen, seeds=seeds)
+        xo, io, _ = oracle.hyperplane(gen, B, mu, cov, g, r, seeds=seeds)
+        assert np.array_equal(info, io)
+        assert rel_err(x, xo) < REL_TOL
+        assert (np.abs(x @ g.T - r).max(axis=1) / np.linalg.norm(r)).max() < RESID_TOL * 50
+
+
+def test_error_codes_and_nan(h):
+    """zero cov -> 1 with out untouched; equal rows of G -> 2 with the unprojected y; NaN -> NaN, info 0
+    (reference tests/test_pyhtnorm.py:46-48, 66-68)."""
+    k = 40
+    rng = np.random.default_rng(3)
+    cov = cases.spd(rng, k)
+    out = np.full((2, k), 7.0)
+    x, info = h.hyperplane_truncated_mvnorm_batch(2, np.zeros(k), np.zeros((k, k)), np.ones((2, k)), np.zeros(2),
+                                                  out=out, raise_on_error=False)
+    assert info.tolist() == [1, 1] and (out == 7.0).all()
+    with pytest.raises(ValueError, match="leading minor"):
+        h.hyperplane_truncated_mvnorm_batch(2, np.zeros(k), np.zeros((k, k)), np.ones((2, k)), np.zeros(2))
+    x, info = h.hyperplane_truncated_mvnorm_batch(2, np.zeros(k), cov, np.ones((2, k)), np.zeros(2),
+                                                  raise_on_error=False)
+    assert info.tolist() == [2, 2] and np.isfinite(x).all()
+    mu = np.zeros(k)
+    mu[0] = np.nan
+    x, info = h.hyperplane_truncated_mvnorm_batch(1, mu, cov, np.ones((1, k)), np.zeros(1))
+    assert info.tolist() == [0] and np.isnan(x).all()
+
+
+def test_single_sample_api_advances_generator(h, oracle):
+    """the reference's own signature: rng state in, advanced state out; two consecutive draws from one
+    generator equal the oracle's two consecutive draws."""
+    import oracle as orc
+    c = cases.ht_case("k4_dense_64")
+    gen = h.HTNGenerator(77, "pcg64")
+    x1 = gen.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"])
+    x2 = gen.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"])
+    xo, _, _ = oracle.hyperplane("pcg64", 1, c["mean"], c["cov"], c["g"], c["r"], seed0=77)
+    assert rel_err(x1[None], xo) < REL_TOL
+    assert not np.allclose(x1, x2)
+    # same seed => same sample, different seed => different (reference tests/test_pyhtnorm.py:109-119)
+    a = h.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"], random_state=5)
+    b = h.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"], random_state=5)
+    d = h.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"], random_state=6)
+    assert np.array_equal(a, b) and not np.allclose(a, d)
+    s = cases.sp_case("nn_plain")
+    y = h.structured_precision_mvnorm(s["mean"], s["a"], s["phi"], s["omega"], random_state=9)
+    yo = oracle.structured("pcg64", 1, s["mean"], s["a"], s["phi"], s["omega"], seed0=9)[0]
+    assert rel_err(y[None], yo) < REL_TOL
+
+
+def test_reference_properties_on_device(h):
+    """properties the reference's tests pin: diag == dense on a diagonal cov; G = 1^T, r = 0 => sum x = 0;
+    regular == diagonal matrix types (tests/test_pyhtnorm.py:51-64, 97-103)."""
+    c = cases.ht_case("k3_diag_40")
+    xd, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], c["cov"], c["g"], c["r"], diag=True, seed0=1)
+    xf, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], c["cov"], c["g"], c["r"], diag=False, seed0=1)
+    assert np.allclose(xd, xf, rtol=0, atol=1e-11)
+    k = 1000
+    rng = np.random.default_rng(5)
+    cov = cases.spd(rng, k)
+    x, _ = h.hyperplane_truncated_mvnorm_batch(64, rng.standard_normal(k), cov, np.ones((1, k)), np.zeros(1))
+    assert np.abs(x.sum(axis=1)).max() < RESID_TOL * 100
+    s = cases.sp_case("dd_plain")
+    a, _ = h.structured_precision_mvnorm_batch(8, s["mean"], s["a"], s["phi"], s["omega"], False, 1, 1, seed0=2)
+    b, _ = h.structured_precision_mvnorm_batch(8, s["mean"], s["a"], s["phi"], s["omega"], False, 0, 0, seed0=2)
+    assert np.allclose(a, b, rtol=0, atol=1e-11)
+
+
+def test_device_pointer_path_and_shard_invariance(h):
+    """torch CUDA tensors go straight through as device pointers; drawing [0,B) in one call equals
+    drawing two shards with offset seeds (the multi-GPU sharding rule of htnorm_b200.dist)."""
+    import torch
+    c = cases.ht_case("k7_dense_333")
+    dev = "cuda:0"
+    t = {k_: torch.from_numpy(np.ascontiguousarray(c[k_])).to(dev) for k_ in ("mean", "cov", "g", "r")}
+    B = 300
+    full, info = h.hyperplane_truncated_mvnorm_batch(B, t["mean"], t["cov"], t["g"], t["r"], seed0=1000)
+    torch.cuda.synchronize()
+    host, _ = h.hyperplane_truncated_mvnorm_batch(B, c["mean"], c["cov"], c["g"], c["r"], seed0=1000)
+    assert np.array_equal(full.cpu().numpy(), host)
+    parts = []
+    for q in range(2):
+        lo, hi = h.shard_range(B, q, 2)
+        o, _ = h.hyperplane_truncated_mvnorm_batch(hi - lo, t["mean"], t["cov"], t["g"], t["r"], seed0=1000 + lo)
+        parts.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(parts), full)
