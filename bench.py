@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched hyperplane-truncated MVN sampling, k = 1000, k2 = 1 (the reference's
+README example shape, BASELINE.json `metric`), samples/s on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path over one batch: ONE call of the batched entry point that
+factorises cov once and draws `--batch` samples (per GPU) from per-sample seeded streams, inputs
+already resident in HBM (`value`), and the same call through the C ABI with HOST buffers, host<->device
+copies inside the timed region (`e2e`).  Prints one JSON line (see README / DESIGN.md section 6).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K, K2 = 1000, 1
+METRIC = "samples/sec (hyperplane-truncated MVN k=1000, k2=1, batched, shared covariance)"
+
+
+def make_inputs(np):
+    """README example shape (README.md:120-125: G = 1^T, r = 0, sum-to-zero) on a well-conditioned SPD
+    covariance (T T^T / d + I), seeded."""
+    import cases
+    rng = np.random.default_rng(1)
+    cov = cases.spd(rng, K)
+    g = np.ones((K2, K))
+    r = np.zeros(K2)
+    mean = rng.random(K)
+    return mean, cov, g, r
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        load = [s for s in sm if s > 0.5 * (mx[0] if mx else 1)] or sm
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(nsamples, nthreads, seed0=12345):
+    """Time the UNMODIFIED reference (oracle/_ref) on `nsamples` samples of the bench workload using
+    `nthreads` host threads (independent samples in parallel, OpenBLAS single-threaded inside each call -
+    the best-throughput way to use the cores for one-sample-per-call code).  Runs in a subprocess so the
+    OpenBLAS thread setting does not leak.  Falls back to the C oracle port if oracle/_ref is absent."""
+    code = f"""
+import os, sys, json, time
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, 'tests'))
+import numpy as np
+sys.argv = ['x']
+import bench
+mean, cov, g, r = bench.make_inputs(np)
+from oracle import Oracle, Reference, have_reference
+if have_reference():
+    ref = Reference(); kind = 'reference'
+    ref.hyperplane('pcg64', {nthreads}, mean, cov, g, r, seed0=1, nthreads={nthreads})   # warm-up
+    x, info, rc = ref.hyperplane('pcg64', {nsamples}, mean, cov, g, r, seed0={seed0}, nthreads={nthreads})
+    sec = ref.last_seconds
+else:
+    orc = Oracle(); kind = 'port'
+    t0 = time.perf_counter()
+    for i in range({nsamples}):     # the port refactorises per call too: one problem per sample
+        orc.hyperplane('pcg64', 1, mean, cov, g, r, seed0={seed0} + i)
+    sec = time.perf_counter() - t0
+print(json.dumps(dict(kind=kind, seconds=sec, nsamples={nsamples})))
+"""
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_baseline(target_seconds=12.0):
+    cores = os.cpu_count() or 1
+    probe = cpu_reference_run(cores, cores)
+    per_round = max(probe["seconds"], 1e-3)
+    rounds = max(1, min(200, int(target_seconds / per_round)))
+    res = cpu_reference_run(cores * rounds, cores)
+    n = res["nsamples"]
+    if res["kind"] == "port":
+        cores_used = 1
+    else:
+        cores_used = cores
+    return {"value": n / res["seconds"], "unit": "samples/s", "cores": cores_used, "kind": res["kind"],
+            "sample": f"{n} samples of the bench workload (k={K}, k2={K2}), one reference call per sample, "
+                      f"{cores_used} host thread(s), OpenBLAS single-threaded per call, {res['seconds']:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, all host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = cores * 16
+    times = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference_run(per_step, cores, seed0=12345 + i * per_step)
+        kind = res["kind"]
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    total = sum(times)
+    value = per_step * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"hyperplane-truncated MVN k={K}, k2={K2} (G=1^T, r=0), PCG64 per-sample seeds",
+                       "samples_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores if kind == "reference" else 1,
+                             "kind": kind,
+                             "sample": f"{per_step} samples per step, one reference call per sample (the "
+                                       "reference refactorises cov on every call)"},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import htnorm_b200 as h
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    B = args.batch                      # per GPU: weak scaling, the batch shards naturally
+    mean, cov, g, r = make_inputs(np)
+    d_in = [torch.from_numpy(x).to(dev) for x in (mean, cov, g, r)]
+    out = torch.empty((B, K), dtype=torch.float64, device=dev)      # 524 MB at B = 65536: larger than L2
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    seed0 = 12345 + rank * B            # rank q draws samples [q B, (q+1) B) of the global batch
+
+    def step(i):
+        h.hyperplane_truncated_mvnorm_batch(B, *d_in, gen="pcg64", seed0=seed0 + i * B * world, out=out, info=info)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- timed: device-resident inputs ----
+    h.phase_timing(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gemm_ms = []
+    phases = []
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        phases.append(h.phase_timing())     # reads events of THIS step (syncs on its last mark)
+    e1.record()
+    barrier()
+    launches = h.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    h.phase_timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * world * args.steps / (ms_total * 1e-3)
+    gemm_ms = [p["gemm"] for p in phases if p["gemm"] > 0]
+
+    # parity spot check inside the bench: constraint residual of the last batch (sum-to-zero)
+    resid = float((out @ d_in[2].T - d_in[3]).abs().max().item())
+
+    # ---- timed: end to end through the C ABI with HOST buffers (pinned), copies inside ----
+    h_in = [torch.from_numpy(x).pin_memory() for x in (mean, cov, g, r)]
+    h_out = torch.empty((B, K), dtype=torch.float64).pin_memory()
+    h_info = torch.empty(B, dtype=torch.int32).pin_memory()
+    np_in = [x.numpy() for x in h_in]
+
+    def step_host(i):
+        h.hyperplane_truncated_mvnorm_batch(B, *np_in, gen="pcg64", seed0=seed0 + i * B * world, out=h_out.numpy(),
+                                            info=h_info.numpy())
+    e2e_steps = max(2, min(args.steps, 5))
+    step_host(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_host(1 + i)                # synchronous: returns when the samples are in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / float(t.item())
+    h2d = 8 * (K * K + K2 * K + K + K2)
+    d2h = 8 * B * K + 4 * B
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        measured = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        dmma_peak = h.fp64_tensor_peak_tflops(local, 100.0)     # in-run FP64 tensor (DMMA) peak
+        alg_flops = B * (K * K + 2.0 * K * K2)                  # per launch of the sampling GEMM
+        gemm_avg = sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
+        achieved = alg_flops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
+        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<128,...> (sampling GEMM out = Z~ F^T + mean)",
+                "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": achieved / dmma_peak if achieved and dmma_peak > 0 else None,
+                "traffic": None,
+                "peak_source": "in-run DMMA (mma.sync m8n8k4 f64) microbenchmark, htn_fp64_tensor_peak_tflops; "
+                               "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs=%s)" % measured.get("hbm_gbs"),
+                "kernel_ms": gemm_avg,
+                "step_phases_ms": {k_: sum(p[k_] for p in phases) / len(phases) for k_ in phases[0]}}
+        traffic_path = os.path.join(ROOT, "profiles", "gemm_traffic_bytes.json")
+        if os.path.exists(traffic_path):
+            roof["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"hyperplane-truncated MVN k={K}, k2={K2} (G=1^T, r=0; README example "
+                                       "shape), well-conditioned SPD cov, PCG64 per-sample seeds, one "
+                                       "factorisation + batch per step",
+                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "output (524 MB per step at the default batch) and Z~ exceed the 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "gpu_launches": launches, "roofline": roof, "clocks": clk,
+                "max_abs_constraint_residual": resid}
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as ex:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "unavailable",
+                                        "sample": repr(ex)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,8 @@ PUBLIC_SYMBOLS = [
     "rng_free", "rng_pcg64_new", "rng_pcg64_new_seeded", "rng_xrs128p_new", "rng_xrs128p_new_seeded",
     "htn_batch_init", "htn_hyperplane_truncated_mvn_batch", "htn_structured_precision_mvn_batch",
     "htn_rng_raw_fill", "htn_std_normal_fill", "htn_device_count", "htn_last_error", "htn_launch_count",
-    "htn_version", "htn_fp64_tensor_peak_tflops", "htn_fp64_fma_peak_tflops",
+    "htn_version", "htn_fp64_tensor_peak_tflops", "htn_fp64_fma_peak_tflops", "htn_phase_timing_enable",
+    "htn_phase_timing_get",
 ]
 
 HTNORM_ALLOC_ERROR = -100

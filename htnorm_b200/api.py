@@ -300,3 +300,14 @@ def fp64_tensor_peak_tflops(device=-1, ms=50.0):
 
 def fp64_fma_peak_tflops(device=-1, ms=50.0):
     return float(lib.htn_fp64_fma_peak_tflops(device, ms))
+
+
+def phase_timing(enable=None):
+    """enable/disable the CUDA-event phase marks, or (enable=None) read the last call's phases in ms:
+    dict(setup, normals, coeff, gemm)."""
+    if enable is not None:
+        lib.htn_phase_timing_enable(int(bool(enable)))
+        return None
+    ms = (C.c_double * 8)()
+    lib.htn_phase_timing_get(ms, 8)
+    return dict(setup=ms[0], normals=ms[1], coeff=ms[2], gemm=ms[3])

@@ -7,11 +7,10 @@
 // Pivot rule: fail on `ajj <= 0` only - NaN passes and propagates with info = 0, as the reference +
 // OpenBLAS do (reference tests/test_pyhtnorm.py:46-48, 91-95).
 //
-// One CTA of 512 threads.  Phase 1 (right-looking, block in smem, rows padded to 129 doubles so both
-// row and column walks are bank-conflict free): per column one rsqrt-free pivot, a column scale and a
-// rank-1 update of the trailing triangle.  Phase 2: inv(L) by forward elimination on the identity with
-// the 128 x 128 right-hand side held in REGISTERS (32 doubles per thread); row t of the inverse is
-// final after step t and is written straight to global memory (and transposed to dinvt).
+// One CTA of 512 threads, the block in REGISTERS (32 per thread, one owner per element): a column costs
+// one barrier + one fast rsqrt + the owner-local rank-1 update.  Phase 2: inv(L) by forward elimination
+// on the identity, also register-resident; row t of the inverse is final after step t and is published
+// by 128 threads (coalesced) while the others update.
 #include <cuda_runtime.h>
 
 #include "launchers.h"
@@ -19,90 +18,131 @@
 namespace {
 
 constexpr int NB = 128;
-constexpr int LDB = NB + 1;
+constexpr int LDB = NB + 4;  // 132
 constexpr int NT = 512;
 
+// 1/sqrt(x): MUFU seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps in FP64 (~1 ulp).  About a third
+// of the latency of the library rsqrt()/sqrt()+div pair, and it sits on the critical path of EVERY column.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double h = 0.5 * y;
+        const double e = fma(-x * y, h, 0.5);  // 0.5 - 0.5 x y^2
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+// Thread (i = tid / 4, cq = tid % 4) OWNS the elements (i, c), c == cq (mod 4), and keeps them in 32
+// REGISTERS for the whole factorisation (the column loop is fully unrolled so every register index is a
+// compile-time constant).  Step j: the owners of column j publish it (unscaled) to a double-buffered
+// shared-memory column, ONE barrier, then every thread computes the pivot's rsqrt redundantly and applies
+// the rank-1 update to its own registers: no shared-memory traffic for the matrix itself.
 __global__ void __launch_bounds__(NT, 1)
 potf2_inv_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ dinv,
                  double* __restrict__ dinvt, int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    double* S = sm;                  // [NB][LDB]
-    double* xrow = sm + NB * LDB;    // [2][NB]
-    double* dg = xrow + 2 * NB;      // [NB] diagonal of L (S keeps the pre-sqrt pivots until write-back)
+    double* S = sm;                  // [NB][LDB]  staging for the coalesced load / store, L for phase 2
+    double* colbuf = sm + NB * LDB;  // [2][NB]    published column (phase 1) / published row (phase 2)
+    double* rdiag = colbuf + 2 * NB; // [NB]       1 / L[j][j]
     const int tid = threadIdx.x;
-
-    // load the lower triangle (upper part of the block is never read)
-    for (int idx = tid; idx < nb * nb; idx += NT) {
-        int i = idx / nb, c = idx - i * nb;
-        S[i * LDB + c] = (c <= i) ? a[(size_t)i * ld + c] : 0.0;
-    }
-    __syncthreads();
-
-    // ---- phase 1: Cholesky ----
-    const int ty = tid >> 5, tx = tid & 31;
-    bool failed = false;
-    int nfact = nb;  // columns factorised before a failure
-    for (int j = 0; j < nb; j++) {
-        const double ajj = S[j * LDB + j];
-        if (ajj <= 0.0) {
-            if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
-            failed = true;
-            nfact = j;
-            break;
-        }
-        const double d = sqrt(ajj);
-        const double rinv = 1.0 / d;
-        for (int i = j + 1 + tid; i < nb; i += NT) S[i * LDB + j] *= rinv;
-        if (tid == 0) dg[j] = d;
-        __syncthreads();
-        for (int i = j + 1 + ty; i < nb; i += NT / 32) {
-            const double lij = S[i * LDB + j];
-            for (int c = j + 1 + tx; c <= i; c += 32) S[i * LDB + c] -= lij * S[c * LDB + j];
-        }
-        __syncthreads();  // the next pivot read S[j+1][j+1] and column scale need these updates
-    }
-    __syncthreads();
-
-    // write L back: lower triangle, zeros above
-    for (int idx = tid; idx < nb * nb; idx += NT) {
-        int i = idx / nb, c = idx - i * nb;
-        a[(size_t)i * ld + c] = (c < i) ? S[i * LDB + c] : (c == i && !(failed && i >= nfact) ? dg[i] : 0.0);
-    }
-    if (dinv == nullptr || failed) return;
-
-    // ---- phase 2: inv(L) ----
-    // thread owns row i = tid / 4 and columns c = cq + 4*j (j = 0..31), cq = tid % 4
     const int i = tid >> 2, cq = tid & 3;
+
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+        int r = idx >> 7, c = idx & (NB - 1);
+        S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
     double R[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) R[j] = (cq + 4 * j == i) ? 1.0 : 0.0;
-    for (int t = 0; t < nb; t++) {
-        double* xr = xrow + (t & 1) * NB;
-        if (i == t) {
-            const double rinv = 1.0 / dg[t];
+    for (int jj = 0; jj < 32; jj++) R[jj] = S[i * LDB + cq + 4 * jj];
+
+    // ---- phase 1 ----
+    int nfact = nb;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int c = cq + 4 * j;
-                const double x = (c <= t) ? R[j] * rinv : 0.0;
-                xr[c] = x;
-                if (c < nb) {
-                    dinv[(size_t)t * NB + c] = x;
-                    if (dinvt) dinvt[(size_t)c * NB + t] = x;
+    for (int jj = 0; jj < 32; jj++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = 4 * jj + q;
+            if (j < nb && nfact == nb) {  // uniform
+                double* col = colbuf + (j & 1) * NB;
+                if (cq == q && i >= j) col[i] = R[jj];
+                __syncthreads();
+                const double ajj = col[j];
+                if (ajj <= 0.0) {  // uniform; NaN passes
+                    if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
+                    nfact = j;
+                } else {
+                    const double rinv = fast_rsqrt(ajj);
+                    if (i > j) {
+                        const double aij = col[i];
+                        const double m = aij * (rinv * rinv);
+#pragma unroll
+                        for (int jj2 = jj; jj2 < 32; jj2++) {
+                            const int c = cq + 4 * jj2;
+                            if ((jj2 > jj || cq > q) && c <= i) R[jj2] = fma(-m, col[c], R[jj2]);
+                        }
+                        if (cq == q) R[jj] = aij * rinv;  // L[i][j]
+                    } else if (i == j && cq == q) {
+                        double d = ajj * rinv;                       // sqrt(ajj), one Heron correction
+                        d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
+                        R[jj] = d;
+                    }
+                    if (tid == 0) rdiag[j] = rinv;
                 }
             }
         }
-        __syncthreads();
-        if (i > t && i < nb) {
-            const double lit = S[i * LDB + t];
+    }
+    const bool failed = nfact < nb;
+    __syncthreads();
+    // L -> smem (lower triangle, zeros above; nothing beyond a failed column is meaningful)
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int c = cq + 4 * j;
-                if (c <= t) R[j] -= lit * xr[c];
+    for (int jj = 0; jj < 32; jj++) {
+        const int c = cq + 4 * jj;
+        S[i * LDB + c] = (c <= i && c < nfact) ? R[jj] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * nb; idx += NT) {
+        int r = idx / nb, c = idx - r * nb;
+        a[(size_t)r * ld + c] = S[r * LDB + c];
+    }
+    if (dinv == nullptr || failed) return;
+
+    // ---- phase 2: inv(L) by forward elimination on the identity held in registers ----
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) R[jj] = (cq + 4 * jj == i) ? 1.0 : 0.0;
+    for (int t = 0; t < nb; t++) {
+        double* xr = colbuf + (t & 1) * NB;
+        if (i == t) {  // raw row t of the right-hand side; scaling by 1/L[t][t] is folded into its readers
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) xr[cq + 4 * jj] = R[jj];
+        }
+        __syncthreads();
+        const double rinv = rdiag[t];
+        if (tid < nb) {  // row t of the inverse is final: publish (coalesced for dinv)
+            const double x = xr[tid] * rinv;
+            dinv[(size_t)t * NB + tid] = x;
+            if (dinvt) dinvt[(size_t)tid * NB + t] = x;
+        }
+        if (i > t && i < nb) {
+            const double lit = S[i * LDB + t] * rinv;
+#pragma unroll
+            for (int g4 = 0; g4 < 8; g4++) {
+                if (16 * g4 <= t) {  // uniform: columns beyond t are still zero
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int jj = 4 * g4 + u;
+                        R[jj] = fma(-lit, xr[cq + 4 * jj], R[jj]);
+                    }
+                }
             }
         }
-        // xrow is double-buffered: the write of step t+1 goes to the other half, and the write of
-        // step t+2 is ordered after this read by the barrier of step t+1
+        // colbuf is double-buffered: step t+1 writes the other half, and the write of step t+2 is
+        // ordered after this step's reads by the barrier of step t+1
     }
 }
 

@@ -9,12 +9,18 @@
 //   * Cholesky   A22 -= L21 * L21^T       (mode C_LOWER: only tiles touching the lower triangle)
 //   * TRSM       X_j = (B_j - X_<j L_j<^T) * inv(L_jj)^T
 //
-// Tiling: CTA tile 128 x BN (BN = 128 / 32 / 8), BK = 16, 8 warps, 3-stage cp.async pipeline.
+// Tiling: CTA tile 128 x BN, BK = 16, 3-stage cp.async pipeline, warp tile 64 x 32 (32 independent DMMAs
+// and 12 LDS.64 per k4 step) for the wide configurations:
+//   BN = 64  : 4 warps (2 x 2), 128 threads, 92 KB smem -> TWO CTAs per SM, so one CTA's barrier /
+//              prologue / epilogue bubbles are filled by the other's DMMAs (the DMMA pipe is the bound)
+//   BN = 128 : 8 warps (2 x 4), 1 CTA per SM (kept for in-place panel updates that need one N tile)
+//   BN = 32/8: 8 warps (8 x 1) of 16 x BN, for skinny N and for small problems that need more CTAs
 // Shared-memory rows are padded to 20 doubles: the DMMA fragment pattern (8 rows x 4 consecutive
 // doubles per half-warp pair) then hits 16 distinct 8-byte bank pairs -> conflict-free LDS.64.
-// BN = 128: warps 2 x 4, warp tile 64 x 32 -> 32 independent DMMAs per k4 step, 12 LDS.64.
-// Tile order: n fastest and descending, so the (few) CTAs that share one 128-row slab of A run
-// together (A streams from HBM once, B stays in L2) and, for B_LOWER, the longest K loops start first.
+// Tile order: n fastest and descending, so the CTAs that share one 128-row slab of A run together
+// (A streams from HBM once, B stays in L2) and, for B_LOWER, the longest K loops start first.
+// Wasted work is trimmed at 8-column granularity: in the diagonal K blocks of a lower-triangular B, in
+// the N tail and in partial K chunks the DMMAs that would only multiply zeros are not issued.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,7 +32,6 @@ constexpr int BM = 128;
 constexpr int BK = 16;
 constexpr int LDS = 20;  // padded row length (doubles) of a smem tile
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 256;
 
 struct GemmParams {
     int M, N, K;
@@ -60,8 +65,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // rows x BK tile (row-major source, leading dimension ld) -> smem [rows][LDS]; elements outside
-// [0, nrows_valid) x [k0, kend) are zero-filled by cp.async's src-size operand.
-template <int ROWS>
+// [0, nrows_total) x [k0, kend) are zero-filled by cp.async's src-size operand.
+template <int ROWS, int NTHREADS>
 __device__ __forceinline__ void load_tile(double* s, const double* g, size_t ld, int row0, int nrows_total,
                                           int k0, int kend, int tid)
 {
@@ -80,10 +85,10 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, size_t ld,
     }
 }
 
-template <int BN, int WARPS_M, int WARPS_N, int WM, int WN>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p)
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(const GemmParams p)
 {
-    static_assert(WARPS_M * WARPS_N == 8, "8 warps");
+    constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
     static_assert(WARPS_M * WM * 8 == BM, "BM");
     static_assert(WARPS_N * WN * 8 == BN, "BN");
     extern __shared__ __align__(16) double smem[];
@@ -106,7 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p
     if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < n0) return;  // tile entirely above the diagonal
 
     // K schedule: chunks of BK from segment 1 [0, kend1) then segment 2 [kext0, K)
-    int kend1 = p.K, kbeg2 = p.K, kend2 = p.K;
+    int kend1 = p.K, kbeg2 = p.K;
+    const int kend2 = p.K;
     if (p.mode == HTNK_GEMM_B_LOWER) {
         int n1 = min(p.N, n0 + BN);
         kend1 = min(n1, p.ktri);
@@ -116,14 +122,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p
     const int nc2 = (kend2 - kbeg2 + BK - 1) / BK;
     const int nchunks = nc1 + nc2;
 
+    auto chunk_range = [&](int c, int& k0, int& kend) {
+        if (c < nc1) { k0 = c * BK; kend = kend1; }
+        else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
+    };
     auto issue = [&](int c) {
         if (c < nchunks) {
             int k0, kend;
-            if (c < nc1) { k0 = c * BK; kend = kend1; }
-            else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
+            chunk_range(c, k0, kend);
             int s = c % STAGES;
-            load_tile<BM>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
-            load_tile<BN>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
+            load_tile<BM, NTHREADS>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
+            load_tile<BN, NTHREADS>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
         }
         cp_async_commit();
     };
@@ -138,23 +147,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p
     for (int s = 0; s < STAGES - 1; s++) issue(s);
 
     const int g = lane >> 2, t4 = lane & 3;
+    const int nw = n0 + wn * WN * 8;                       // first column of this warp
+    const int jhi = min(WN, (p.N - nw + 7) >> 3);          // 8-column sub-tiles that exist (N tail)
     for (int c = 0; c < nchunks; c++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         issue(c + STAGES - 1);
+        int k0, kend;
+        chunk_range(c, k0, kend);
+        const int klim = min(BK, kend - k0);
         const double* a_s = sA + (c % STAGES) * A_STAGE + (wm * WM * 8 + g) * LDS + t4;
         const double* b_s = sB + (c % STAGES) * B_STAGE + (wn * WN * 8 + g) * LDS + t4;
+        // does this chunk need trimming for this warp?  (all conditions are warp-uniform)
+        const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < nc1) && (k0 + BK > nw);
+        if (!diag && jhi == WN && klim == BK) {
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[WM], bf[WN];
+            for (int kk = 0; kk < BK; kk += 4) {
+                double af[WM], bf[WN];
 #pragma unroll
-            for (int i = 0; i < WM; i++) af[i] = a_s[i * 8 * LDS + kk];
+                for (int i = 0; i < WM; i++) af[i] = a_s[i * 8 * LDS + kk];
 #pragma unroll
-            for (int j = 0; j < WN; j++) bf[j] = b_s[j * 8 * LDS + kk];
+                for (int j = 0; j < WN; j++) bf[j] = b_s[j * 8 * LDS + kk];
 #pragma unroll
-            for (int i = 0; i < WM; i++)
+                for (int i = 0; i < WM; i++)
 #pragma unroll
-                for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) {
+                if (kk < klim) {
+                    // sub-tile j (columns nw + 8j .. +7) of a lower-triangular B is non-zero only for
+                    // k <= nw + 8j + 7: the first sub-tile that still needs k = k0 + kk
+                    int jlo = 0;
+                    if (diag) jlo = max(0, (k0 + kk - nw) >> 3);
+                    if (jlo < jhi) {
+                        double af[WM];
+#pragma unroll
+                        for (int i = 0; i < WM; i++) af[i] = a_s[i * 8 * LDS + kk];
+#pragma unroll
+                        for (int j = 0; j < WN; j++) {
+                            if (j >= jlo && j < jhi) {
+                                const double bfj = b_s[j * 8 * LDS + kk];
+#pragma unroll
+                                for (int i = 0; i < WM; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bfj);
+                            }
+                        }
+                    }
+                }
+            }
         }
     }
     cp_async_wait<0>();
@@ -196,16 +237,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(const GemmParams p
     }
 }
 
-template <int BN, int WARPS_M, int WARPS_N, int WM, int WN>
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB>
 int launch(cudaStream_t st, const GemmParams& p)
 {
     constexpr size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
-    auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN>;
+    auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN, MINB>;
     // per-device attribute: set on every launch (cheap) so that any current device is covered
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     unsigned grid = (unsigned)p.tiles_m * (unsigned)p.tiles_n;
-    kern<<<grid, NTHREADS, smem, st>>>(p);
+    kern<<<grid, 32 * WARPS_M * WARPS_N, smem, st>>>(p);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }
@@ -220,20 +261,30 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     if (K < 0) return -202;
     if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return -202;
-    if (bn == 0) bn = N > 32 ? 128 : (N > 8 ? 32 : 8);
+    const int tiles_m = (M + BM - 1) / BM;
+    if (bn == 0) {
+        if (N <= 8) bn = 8;
+        else if (N <= 32) bn = 32;
+        else {
+            // wide N: 128 x 64 tiles, unless that leaves most of the 148 SMs (x2 CTAs) without a tile
+            long long ctas64 = (long long)tiles_m * ((N + 63) / 64);
+            bn = ctas64 < 148 ? 32 : 64;
+        }
+    }
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.alpha = alpha; p.beta = beta;
     p.A = A; p.B = B; p.C = C; p.bias = bias;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
-    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_m = tiles_m;
     p.tiles_n = (N + bn - 1) / bn;
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
     switch (bn) {
-        case 128: return launch<128, 2, 4, 8, 4>(st, p);
-        case 32: return launch<32, 8, 1, 2, 4>(st, p);
-        case 8: return launch<8, 8, 1, 2, 1>(st, p);
+        case 128: return launch<128, 2, 4, 8, 4, 1>(st, p);
+        case 64: return launch<64, 2, 2, 8, 4, 2>(st, p);
+        case 32: return launch<32, 8, 1, 2, 4, 1>(st, p);
+        case 8: return launch<8, 8, 1, 2, 1, 1>(st, p);
         default: return -202;
     }
 }

@@ -105,7 +105,11 @@ __device__ __forceinline__ bool zig_fast(uint64_t r, const uint64_t* __restrict_
     r >>= 8;
     uint64_t sign = r & 1;
     d.rabs = (r >> 1) & 0x000fffffffffffffULL;
-    double x = __dmul_rn((double)(long long)d.rabs, s_wi[d.idx]);
+    // rabs < 2^52: (2^52 + rabs) is exactly representable, so the integer -> double conversion is one
+    // OR + one subtraction instead of the multi-instruction I2F.F64.U64
+    const double rd = __dadd_rn(__longlong_as_double((long long)(d.rabs | 0x4330000000000000ULL)),
+                                -4503599627370496.0);
+    double x = __dmul_rn(rd, s_wi[d.idx]);
     d.x = sign ? -x : x;
     return d.rabs < s_ki[d.idx];
 }

@@ -109,3 +109,46 @@ void htn_dfree(htn_ctx_t* ctx, void* p)
 {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
+
+/* ---- optional phase timing (CUDA events on the caller's stream; off by default) ---- */
+#define HTN_PROF_SLOTS 8
+static int g_prof_on = 0;
+static cudaEvent_t g_prof_ev[HTN_PROF_SLOTS];
+static int g_prof_set[HTN_PROF_SLOTS];
+static int g_prof_dev = -1;
+
+void htn_phase_timing_enable(int on)
+{
+    g_prof_on = on;
+    if (!on) memset(g_prof_set, 0, sizeof(g_prof_set));
+}
+
+void htn_prof_mark(htn_ctx_t* ctx, int slot)
+{
+    if (!g_prof_on || slot < 0 || slot >= HTN_PROF_SLOTS) return;
+    if (g_prof_dev != ctx->device) { /* events belong to a device: (re)create them here */
+        for (int i = 0; i < HTN_PROF_SLOTS; i++) {
+            cudaEventCreate(&g_prof_ev[i]);
+            g_prof_set[i] = 0;
+        }
+        g_prof_dev = ctx->device;
+    }
+    if (cudaEventRecord(g_prof_ev[slot], ctx->stream) == cudaSuccess) g_prof_set[slot] = 1;
+}
+
+/* ms[i] = time between mark i and mark i+1 of the last call (after synchronising on the later event);
+ * -1 where a mark is missing.  Returns the number of intervals written (nslots - 1). */
+int htn_phase_timing_get(double* ms, int n)
+{
+    int w = 0;
+    for (int i = 0; i + 1 < HTN_PROF_SLOTS && i < n; i++, w++) {
+        ms[i] = -1.0;
+        if (g_prof_set[i] && g_prof_set[i + 1]) {
+            float t = 0;
+            if (cudaEventSynchronize(g_prof_ev[i + 1]) == cudaSuccess &&
+                cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]) == cudaSuccess)
+                ms[i] = t;
+        }
+    }
+    return w;
+}

@@ -32,6 +32,9 @@ int htn_ctx_end(htn_ctx_t* ctx, int sync);
 int htn_dalloc(htn_ctx_t* ctx, void** p, size_t bytes);
 void htn_dfree(htn_ctx_t* ctx, void* p);
 
+/* phase marks for the optional timing facility (context.c) */
+void htn_prof_mark(htn_ctx_t* ctx, int slot);
+
 #define HTN_TRY(expr)                 \
     do {                              \
         rc = (expr);                  \
@@ -62,6 +65,7 @@ typedef struct {
     double* dinv;   /* nblk x 128 x 128: inverse of each diagonal block of L */
     double* dinvt;  /* transposes of the above */
     int nblk;
+    int solves;     /* the factor will be used by the blocked triangular solves (needs every inverse) */
 } htn_factor_t;
 
 /* allocate dinv/dinvt (+u if want_u) for an n x n factor living in f (caller-owned, n x ld) */

@@ -78,6 +78,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_CUDA(cudaMemsetAsync(Sm, 0, (size_t)k2 * k2p * 8, st));
 
     /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
+    htn_prof_mark(ctx, 0);
     /* symmetric copy of cov (as the reference's uplo='L' calls see it) and its lower triangle in F */
     HTN_TRY(htnk_sym_expand(st, cov, (size_t)k, k, lower_src, Sfull, kp, F, ldz));
     HTN_TRY(htn_factor_init(ctx, &fa, F, ldz, k, 0));
@@ -111,6 +112,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         goto done;
     }
     *first_info = h_info[1]; /* G cov G^T not PD: the unprojected y is returned (src/htnorm.c:169-177) */
+    htn_prof_mark(ctx, 1);
 
     /* ---- per chunk of samples ---- */
     size_t chunk = nsamples;
@@ -126,6 +128,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         HTN_CUDA(cudaMemset2DAsync(Z + k, ldz * 8, 0, (ldz - (size_t)k) * 8, nb, st));
         htnk_segment_t seg = {(size_t)k, Z, ldz, NULL, NULL, NULL};
         HTN_TRY(htnk_normal_fill(st, &sv, nb, 1, &seg, NULL));
+        htn_prof_mark(ctx, 2);
         if (!h_info[1]) {
             /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
             HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Z, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
@@ -136,9 +139,11 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
                 HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Z + kp, ldz, NULL));
             }
         }
+        htn_prof_mark(ctx, 3);
         /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
         HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Z, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
-                             (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 128));
+                             (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 0));
+        htn_prof_mark(ctx, 4);
     }
 done:
     htn_factor_free(ctx, &fa);

@@ -19,6 +19,7 @@ int htn_factor_init(htn_ctx_t* ctx, htn_factor_t* fa, double* f, size_t ld, int 
     fa->ld = ld;
     fa->f = f;
     fa->nblk = (n + HTN_NB - 1) / HTN_NB;
+    fa->solves = want_u;
     size_t blk = (size_t)HTN_NB * HTN_NB * sizeof(double);
     HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinv, blk * fa->nblk));
     HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinvt, blk * fa->nblk));
@@ -54,26 +55,32 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
     int rc = 0;
     const int n = fa->n;
     const size_t ld = fa->ld;
+    double* panel = NULL; /* L21 of the current step, rows x 128 (out of place: many small N tiles may run) */
+    if (fa->nblk > 1) HTN_TRY(htn_dalloc(ctx, (void**)&panel, (size_t)n * HTN_NB * sizeof(double)));
     for (int jb = 0; jb < fa->nblk; jb++) {
         const int j0 = jb * HTN_NB;
         const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
+        const int rows = n - j0 - nb;
         double* ajj = fa->f + (size_t)j0 * ld + j0;
         double* dinv = fa->dinv + (size_t)jb * HTN_NB * HTN_NB;
         double* dinvt = fa->dinvt + (size_t)jb * HTN_NB * HTN_NB;
-        HTN_TRY(htnk_potf2_inv(ctx->stream, ajj, ld, nb, j0, dinv, dinvt, d_info));
-        const int rows = n - j0 - nb;
+        /* the inverse of the last diagonal block is only needed by later triangular solves */
+        const int want_inv = rows > 0 || fa->solves;
+        HTN_TRY(htnk_potf2_inv(ctx->stream, ajj, ld, nb, j0, want_inv ? dinv : NULL, want_inv ? dinvt : NULL,
+                               d_info));
         if (rows <= 0) break;
         double* a21 = fa->f + (size_t)(j0 + nb) * ld + j0;
-        /* panel: L21 = A21 * inv(L11)^T  (in place: one N tile spans the panel, K loop ends before the
-         * epilogue writes) */
-        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, nb, nb, 1.0, a21, ld, dinv, HTN_NB, 0.0, a21, ld, NULL,
-                             HTNK_GEMM_FULL, 0, 0, 128));
+        /* panel: L21 = A21 * inv(L11)^T */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, nb, nb, 1.0, a21, ld, dinv, HTN_NB, 0.0, panel, HTN_NB, NULL,
+                             HTNK_GEMM_FULL, 0, 0, 0));
         /* trailing update: A22 -= L21 * L21^T on the lower-triangle tiles */
         double* a22 = fa->f + (size_t)(j0 + nb) * ld + (j0 + nb);
-        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, a21, ld, a21, ld, 1.0, a22, ld, NULL,
-                             HTNK_GEMM_C_LOWER, 0, 0, 128));
+        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, panel, HTN_NB, panel, HTN_NB, 1.0, a22, ld, NULL,
+                             HTNK_GEMM_C_LOWER, 0, 0, 0));
+        HTN_TRY(htnk_copy2d(ctx->stream, panel, HTN_NB, rows, nb, a21, ld, NULL));
     }
 done:
+    htn_dfree(ctx, panel);
     return rc;
 }
 
@@ -87,8 +94,9 @@ int htn_trsm_right_lt(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t 
         double* xj = x + j0;
         if (j0 > 0) /* X_j -= X_{<j} * L[j, <j]^T */
             HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, j0, -1.0, x, ldx, fa->f + (size_t)j0 * fa->ld, fa->ld, 1.0,
-                                 xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
-        /* X_j = X_j * inv(L_jj)^T : B[n][kk] = dinv[n][kk] */
+                                 xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        /* X_j = X_j * inv(L_jj)^T : B[n][kk] = dinv[n][kk].  In place (C == A): one 128-wide N tile per
+         * row slab, whose K loop has consumed every input before its epilogue writes */
         HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, nb, 1.0, xj, ldx, fa->dinv + (size_t)jb * HTN_NB * HTN_NB, HTN_NB,
                              0.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
     }
@@ -112,7 +120,7 @@ int htn_trsm_right_l(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t l
         if (j1 < fa->n)
             HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, fa->n - j1, -1.0, x + j1, ldx,
                                  fa->u + (size_t)j0 * fa->ld + j1, fa->ld, 1.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0,
-                                 0, 128));
+                                 0, 0));
         /* X_j = X_j * inv(L_jj) : B[n][kk] = dinv[kk][n] = dinvt[n][kk] */
         HTN_TRY(htnk_gemm_tn(ctx->stream, m, nb, nb, 1.0, xj, ldx, fa->dinvt + (size_t)jb * HTN_NB * HTN_NB,
                              HTN_NB, 0.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));

@@ -86,6 +86,13 @@ const char* htn_last_error(void);       /* thread-local description of the last 
 unsigned long long htn_launch_count(void); /* kernels this library has launched in this process */
 const char* htn_version(void);
 
+/* Optional phase timing of the shared-covariance hyperplane path: when enabled, CUDA events are recorded
+ * on the call's stream at the phase boundaries; htn_phase_timing_get writes the milliseconds of
+ * [0] setup (factorisation etc.), [1] normal generation, [2] W z + coefficient solve, [3] the sampling
+ * GEMM of the LAST chunk of the last call (-1 where unavailable) and returns the count written. */
+void htn_phase_timing_enable(int on);
+int htn_phase_timing_get(double* ms, int n);
+
 /* Measured FP64 tensor-core (DMMA, mma.sync m8n8k4.f64) throughput of `device` in TFLOP/s, register
  * operands only, all SMs, timed with CUDA events over roughly `ms` milliseconds; <0 on error.  This is
  * the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 entry). */

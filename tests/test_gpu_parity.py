@@ -206,9 +206,11 @@ def test_error_codes_and_nan(h):
     assert info.tolist() == [1, 1] and (out == 7.0).all()
     with pytest.raises(ValueError, match="leading minor"):
         h.hyperplane_truncated_mvnorm_batch(2, np.zeros(k), np.zeros((k, k)), np.ones((2, k)), np.zeros(2))
-    x, info = h.hyperplane_truncated_mvnorm_batch(2, np.zeros(k), cov, np.ones((2, k)), np.zeros(2),
-                                                  raise_on_error=False)
-    assert info.tolist() == [2, 2] and np.isfinite(x).all()
+    # two equal rows of G with an exactly representable G cov G^T = [[64, 64], [64, 64]]: the second
+    # pivot is exactly 0 in any arithmetic -> info 2, out holds the unprojected y
+    x, info = h.hyperplane_truncated_mvnorm_batch(2, np.zeros(16), 4.0 * np.eye(16), np.ones((2, 16)),
+                                                  np.zeros(2), raise_on_error=False)
+    assert info.tolist() == [2, 2] and np.isfinite(x).all() and np.abs(x.sum(axis=1)).max() > 1e-3
     mu = np.zeros(k)
     mu[0] = np.nan
     x, info = h.hyperplane_truncated_mvnorm_batch(1, mu, cov, np.ones((1, k)), np.zeros(1))
