@@ -1,16 +1,15 @@
-// Diagonal-block kernel of the blocked Cholesky: factor one nb x nb (nb <= 128) block held in shared
-// memory and produce inv(L) as well, so that every triangular solve around it (the panel solve of the
-// factorisation, the blocked TRSMs of the samplers) becomes a DMMA GEMM with inv(L_jj).
-//
-// Replaces dpotrf's unblocked base case (reference call sites src/htnorm_distributions.c:77,115 via
-// src/htnorm_blas.h:111-112) and dposv / dpotri's triangular kernels (src/htnorm.c:169,210,330).
+// Shared-memory / register kernels of the blocked Cholesky and of the blocked triangular solves:
+//   potf2_kernel         factor one nb x nb (nb <= 128) diagonal block (dpotrf's unblocked base case;
+//                        reference call sites src/htnorm_distributions.c:77,115 via src/htnorm_blas.h:111)
+//   trsm_rows_kernel     panel solve L21 = A21 L11^-T, rows independent (no inverse needed)
+//   trtri_batched_kernel inverse of every diagonal block at once, so that the many-right-hand-side
+//                        solves of the samplers (dtrsv / dposv / dpotri's solve phases,
+//                        src/htnorm_distributions.c:120, src/htnorm.c:169,210,330) become DMMA GEMMs
 // Pivot rule: fail on `ajj <= 0` only - NaN passes and propagates with info = 0, as the reference +
 // OpenBLAS do (reference tests/test_pyhtnorm.py:46-48, 91-95).
 //
 // One CTA of 512 threads, the block in REGISTERS (32 per thread, one owner per element): a column costs
-// one barrier + one fast rsqrt + the owner-local rank-1 update.  Phase 2: inv(L) by forward elimination
-// on the identity, also register-resident; row t of the inverse is final after step t and is published
-// by 128 threads (coalesced) while the others update.
+// one barrier + one fast rsqrt + the owner-local rank-1 update.
 #include <cuda_runtime.h>
 
 #include "launchers.h"
@@ -42,8 +41,8 @@ __device__ __forceinline__ double fast_rsqrt(double x)
 // shared-memory column, ONE barrier, then every thread computes the pivot's rsqrt redundantly and applies
 // the rank-1 update to its own registers: no shared-memory traffic for the matrix itself.
 __global__ void __launch_bounds__(NT, 1)
-potf2_inv_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ dinv,
-                 double* __restrict__ dinvt, int* __restrict__ info)
+potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ rdiag_out,
+             int* __restrict__ info)
 {
     extern __shared__ double sm[];
     double* S = sm;                  // [NB][LDB]  staging for the coalesced load / store, L for phase 2
@@ -62,15 +61,20 @@ potf2_inv_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __
     for (int jj = 0; jj < 32; jj++) R[jj] = S[i * LDB + cq + 4 * jj];
 
     // ---- phase 1 ----
+    // The register file is used as a ROTATING window: during column group jj (columns 4jj .. 4jj+3),
+    // R[u] holds the element of column cq + 4 (jj + u).  After the group, R[0] is final (it goes to
+    // shared memory) and the window shifts by one.  The loop body is therefore identical for every
+    // group and stays a few KB (a fully unrolled 128-column version measured I-cache bound).
     int nfact = nb;
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
+    const int ngroups = (nb + 3) >> 2;
+    for (int jj = 0; jj < ngroups; jj++) {
+        const int c0 = cq + 4 * jj;  // the column this thread retires in this group
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int j = 4 * jj + q;
             if (j < nb && nfact == nb) {  // uniform
-                double* col = colbuf + (j & 1) * NB;
-                if (cq == q && i >= j) col[i] = R[jj];
+                double* col = colbuf + (q & 1) * NB;
+                if (cq == q && i >= j) col[i] = R[0];
                 __syncthreads();
                 const double ajj = col[j];
                 if (ajj <= 0.0) {  // uniform; NaN passes
@@ -81,83 +85,194 @@ potf2_inv_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __
                     if (i > j) {
                         const double aij = col[i];
                         const double m = aij * (rinv * rinv);
+                        if (cq > q && c0 <= i) R[0] = fma(-m, col[c0], R[0]);
 #pragma unroll
-                        for (int jj2 = jj; jj2 < 32; jj2++) {
-                            const int c = cq + 4 * jj2;
-                            if ((jj2 > jj || cq > q) && c <= i) R[jj2] = fma(-m, col[c], R[jj2]);
+                        for (int ub = 0; ub < 4; ub++) {
+                            if (jj + 8 * ub < 32) {  // uniform: later columns do not exist
+#pragma unroll
+                                for (int u = (ub == 0 ? 1 : 8 * ub); u < 8 * ub + 8; u++) {
+                                    const int c = c0 + 4 * u;
+                                    if (c <= i) R[u] = fma(-m, col[c], R[u]);
+                                }
+                            }
                         }
-                        if (cq == q) R[jj] = aij * rinv;  // L[i][j]
+                        if (cq == q) R[0] = aij * rinv;  // L[i][j]
                     } else if (i == j && cq == q) {
                         double d = ajj * rinv;                       // sqrt(ajj), one Heron correction
                         d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
-                        R[jj] = d;
+                        R[0] = d;
                     }
                     if (tid == 0) rdiag[j] = rinv;
                 }
             }
         }
+        // retire column c0: L[i][c0] (zeros above the diagonal / beyond a failed column)
+        S[i * LDB + c0] = (c0 <= i && c0 < nfact) ? R[0] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 31; u++) R[u] = R[u + 1];
+        R[31] = 0.0;
     }
     const bool failed = nfact < nb;
-    __syncthreads();
-    // L -> smem (lower triangle, zeros above; nothing beyond a failed column is meaningful)
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-        const int c = cq + 4 * jj;
-        S[i * LDB + c] = (c <= i && c < nfact) ? R[jj] : 0.0;
-    }
+    for (int c = cq + 4 * ngroups; c < NB; c += 4) S[i * LDB + c] = 0.0;
     __syncthreads();
     for (int idx = tid; idx < nb * nb; idx += NT) {
         int r = idx / nb, c = idx - r * nb;
         a[(size_t)r * ld + c] = S[r * LDB + c];
     }
-    if (dinv == nullptr || failed) return;
+    if (rdiag_out != nullptr && !failed)
+        for (int c = tid; c < nb; c += NT) rdiag_out[c] = rdiag[c];
+}
 
-    // ---- phase 2: inv(L) by forward elimination on the identity held in registers ----
+// ---- inverse of diagonal blocks, batched: one CTA per block, all blocks in parallel ----
+// inv(L) by forward elimination on the identity held in registers (thread (i, cq) owns columns
+// c == cq mod 4 of row i); row t of the inverse is final after step t and is published by 128 threads
+// (coalesced) while the others update.  Only launched for factors that feed the blocked TRSMs.
+__global__ void __launch_bounds__(NT, 1)
+trtri_batched_kernel(const double* __restrict__ f, size_t ld, int n, double* __restrict__ dinv_all,
+                     double* __restrict__ dinvt_all)
+{
+    extern __shared__ double sm[];
+    double* S = sm;                  // [NB][LDB]
+    double* xrow = sm + NB * LDB;    // [2][NB]
+    double* rdiag = xrow + 2 * NB;   // [NB]
+    const int tid = threadIdx.x;
+    const int i = tid >> 2, cq = tid & 3;
+    const int j0 = blockIdx.x * NB;
+    const int nb = min(NB, n - j0);
+    const double* a = f + (size_t)j0 * ld + j0;
+    double* dinv = dinv_all + (size_t)blockIdx.x * NB * NB;
+    double* dinvt = dinvt_all + (size_t)blockIdx.x * NB * NB;
+
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+        int r = idx >> 7, c = idx & (NB - 1);
+        S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    if (tid < nb) rdiag[tid] = 1.0 / S[tid * LDB + tid];
+    double R[32];
 #pragma unroll
     for (int jj = 0; jj < 32; jj++) R[jj] = (cq + 4 * jj == i) ? 1.0 : 0.0;
+    __syncthreads();
     for (int t = 0; t < nb; t++) {
-        double* xr = colbuf + (t & 1) * NB;
+        double* xr = xrow + (t & 1) * NB;
         if (i == t) {  // raw row t of the right-hand side; scaling by 1/L[t][t] is folded into its readers
 #pragma unroll
             for (int jj = 0; jj < 32; jj++) xr[cq + 4 * jj] = R[jj];
         }
         __syncthreads();
         const double rinv = rdiag[t];
-        if (tid < nb) {  // row t of the inverse is final: publish (coalesced for dinv)
+        if (tid < nb) {
             const double x = xr[tid] * rinv;
             dinv[(size_t)t * NB + tid] = x;
-            if (dinvt) dinvt[(size_t)tid * NB + t] = x;
+            dinvt[(size_t)tid * NB + t] = x;
         }
         if (i > t && i < nb) {
             const double lit = S[i * LDB + t] * rinv;
+            if (t < 64) {  // uniform: columns beyond t are still zero
 #pragma unroll
-            for (int g4 = 0; g4 < 8; g4++) {
-                if (16 * g4 <= t) {  // uniform: columns beyond t are still zero
+                for (int jj = 0; jj < 16; jj++) R[jj] = fma(-lit, xr[cq + 4 * jj], R[jj]);
+            } else {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int jj = 4 * g4 + u;
-                        R[jj] = fma(-lit, xr[cq + 4 * jj], R[jj]);
-                    }
-                }
+                for (int jj = 0; jj < 32; jj++) R[jj] = fma(-lit, xr[cq + 4 * jj], R[jj]);
             }
         }
-        // colbuf is double-buffered: step t+1 writes the other half, and the write of step t+2 is
+        // xrow is double-buffered: step t+1 writes the other half, and the write of step t+2 is
         // ordered after this step's reads by the barrier of step t+1
+    }
+}
+
+// ---- panel solve of the blocked Cholesky: X := X * L^-T for rows of a panel, rows independent ----
+// SIXTEEN threads per row: thread (row i, cq) keeps the residuals of columns c == cq (mod 16) in a rotating
+// window of 8 registers (R[0] = the 16-column group being solved); the solved entry travels to the other
+// 15 threads of the row by shuffle; L (the freshly factored diagonal block) sits in shared memory with an
+// odd row stride, so the 16 different rows a half-warp reads per step hit 16 different banks.
+// No block-level synchronisation after the load: rows never interact.  32 rows per CTA.
+constexpr int TR_ROWS = NT / 16;
+constexpr int LDT = NB + 1;
+__global__ void __launch_bounds__(NT, 1)
+trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __restrict__ l, size_t ldl,
+                 int nb, const double* __restrict__ rdiag_g)
+{
+    extern __shared__ double sm[];
+    double* S = sm;                  // [NB][LDT] : L
+    double* rdiag = sm + NB * LDT;   // [NB]
+    const int tid = threadIdx.x;
+    const int i = tid >> 4, cq = tid & 15;
+    const int lane = tid & 31;
+    const size_t row = (size_t)blockIdx.x * TR_ROWS + i;
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+        int r = idx >> 7, c = idx & (NB - 1);
+        S[r * LDT + c] = (r < nb && c <= r) ? l[(size_t)r * ldl + c] : 0.0;
+    }
+    if (tid < NB) rdiag[tid] = tid < nb ? rdiag_g[tid] : 0.0;
+    __syncthreads();
+    const bool live = row < (size_t)nrows;
+    double* xr = x + (live ? row : 0) * ldx;
+    double R[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int c = cq + 16 * u;
+        R[u] = (live && c < nb) ? xr[c] : 0.0;
+    }
+    const int ngroups = (nb + 15) >> 4;
+    for (int jj = 0; jj < ngroups; jj++) {
+        const int c0 = cq + 16 * jj;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int t = 16 * jj + q;  // column being solved (uniform)
+            // x_t = residual_t / L[t][t], owned by the row's thread cq == q.  Columns t >= nb have
+            // rdiag = 0 and zero rows of L: they solve to 0 and change nothing.
+            double xt = R[0] * rdiag[t];
+            xt = __shfl_sync(0xffffffffu, xt, (lane & 16) | q);
+            if (cq == q) R[0] = xt;
+            else if (cq > q) R[0] = fma(-xt, S[c0 * LDT + t], R[0]);
+#pragma unroll
+            for (int u = 1; u < 8; u++) {
+                if (jj + u < 8) R[u] = fma(-xt, S[(c0 + 16 * u) * LDT + t], R[u]);  // uniform guard
+            }
+        }
+        if (live && c0 < nb) xr[c0] = R[0];
+#pragma unroll
+        for (int u = 0; u < 7; u++) R[u] = R[u + 1];
+        R[7] = 0.0;
     }
 }
 
 }  // namespace
 
-extern "C" int htnk_potf2_inv(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* dinv,
-                              double* dinvt, int* info)
+extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info)
 {
     if (nb <= 0) return 0;
     if (nb > NB) return -202;
     const size_t smem = (size_t)(NB * LDB + 3 * NB) * sizeof(double);
-    if (cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -201;
+    potf2_kernel<<<1, NT, smem, st>>>(a, ld, nb, col0, rdiag, info);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_trtri_batched(cudaStream_t st, const double* f, size_t ld, int n, double* dinv, double* dinvt)
+{
+    if (n <= 0) return 0;
+    const size_t smem = (size_t)(NB * LDB + 3 * NB) * sizeof(double);
+    if (cudaFuncSetAttribute(trtri_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
         return -201;
-    potf2_inv_kernel<<<1, NT, smem, st>>>(a, ld, nb, col0, dinv, dinvt, info);
+    trtri_batched_kernel<<<(n + NB - 1) / NB, NT, smem, st>>>(f, ld, n, dinv, dinvt);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows, const double* l, size_t ldl, int nb,
+                              const double* rdiag)
+{
+    if (nrows <= 0 || nb <= 0) return 0;
+    if (nb > NB) return -202;
+    const size_t smem = (size_t)(NB * LDT + NB) * sizeof(double);
+    if (cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -201;
+    trsm_rows_kernel<<<(nrows + TR_ROWS - 1) / TR_ROWS, NT, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }

@@ -23,6 +23,7 @@
 // the N tail and in partial K chunks the DMMAs that would only multiply zeros are not issued.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "launchers.h"
 
@@ -253,6 +254,18 @@ int launch(cudaStream_t st, const GemmParams& p)
 
 }  // namespace
 
+// wide-N configuration: 64 (default) or an experimental one selected with HTN_GEMM_WIDE
+static int wide_config()
+{
+    static int cfg = 0;
+    if (cfg == 0) {
+        const char* e = getenv("HTN_GEMM_WIDE");
+        cfg = e ? atoi(e) : 64;
+        if (cfg != 64 && cfg != 65 && cfg != 128 && cfg != 129) cfg = 64;
+    }
+    return cfg;
+}
+
 extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
                             const double* B, size_t ldb, double beta, double* C, size_t ldc,
                             const double* bias, int mode, int ktri, int kext0, int bn)
@@ -268,7 +281,7 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
         else {
             // wide N: 128 x 64 tiles, unless that leaves most of the 148 SMs (x2 CTAs) without a tile
             long long ctas64 = (long long)tiles_m * ((N + 63) / 64);
-            bn = ctas64 < 148 ? 32 : 64;
+            bn = ctas64 < 148 ? 32 : wide_config();
         }
     }
     GemmParams p;
@@ -278,11 +291,13 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
     p.tiles_m = tiles_m;
-    p.tiles_n = (N + bn - 1) / bn;
+    p.tiles_n = (N + (bn & ~1) - 1) / (bn & ~1);
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
     switch (bn) {
         case 128: return launch<128, 2, 4, 8, 4, 1>(st, p);
         case 64: return launch<64, 2, 2, 8, 4, 2>(st, p);
+        case 65: return launch<64, 4, 2, 4, 4, 2>(st, p);    // 16 warps / SM, warp tile 32 x 32
+        case 129: return launch<128, 4, 4, 4, 4, 1>(st, p);  // 16 warps / SM in one CTA
         case 32: return launch<32, 8, 1, 2, 4, 1>(st, p);
         case 8: return launch<8, 8, 1, 2, 1, 1>(st, p);
         default: return -202;

@@ -60,11 +60,15 @@ int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const doubl
 
 /* ---- factorisation building blocks (chol.cu) ---- */
 /* Factor the nb x nb (nb <= 128) diagonal block at a (row-major, ld) in place: lower triangle := L,
- * strictly-upper := 0.  Also writes inv(L) to dinv (128 x 128 row-major, zero padded, lower) and its
- * transpose to dinvt.  *info (device int) receives col0 + j + 1 at the first pivot <= 0 (only if it
- * still holds 0). dinv/dinvt may be NULL. */
-int htnk_potf2_inv(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* dinv,
-                   double* dinvt, int* info);
+ * strictly-upper := 0.  rdiag (device, nb doubles, may be NULL) receives 1 / L[j][j].  *info (device int)
+ * receives col0 + j + 1 at the first pivot <= 0 (only if it still holds 0). */
+int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info);
+/* x (nrows x nb, leading dimension ldx) := x * L^-T with the nb x nb lower block l; rdiag = 1 / diag(l) */
+int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows, const double* l, size_t ldl, int nb,
+                   const double* rdiag);
+/* inverse of every 128 x 128 diagonal block of the n x n lower factor f: block b -> dinv + b * 128 * 128
+ * (row-major, leading dimension 128) and its transpose -> dinvt + b * 128 * 128 */
+int htnk_trtri_batched(cudaStream_t st, const double* f, size_t ld, int n, double* dinv, double* dinvt);
 
 /* ---- layout / elementwise helpers (elementwise.cu) ---- */
 /* src: n x n row-major (ld lds), symmetric, read through its UPPER triangle (lower_src = 0) or LOWER

@@ -96,3 +96,83 @@ extern "C" double htnk_dfma_peak_tflops(cudaStream_t st, double ms)
     // per warp per iteration: 32 lanes * 8 FMA * 2 flops
     return time_kernel(st, dfma_peak_kernel, 32.0 * 8.0 * 2.0, ms);
 }
+
+// ---- latency probes (one warp / one CTA): calibrates the cycle models in DESIGN.md ----
+namespace {
+__global__ void latency_kernel(double* out, double seed)
+{
+    __shared__ double sh[64];
+    const int n = 512;
+    double x = seed + threadIdx.x * 1e-9, y = 1.0 - 1e-9;
+    long long t0, t1;
+    // dependent DFMA chain
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; i++) x = fma(x, y, 1e-9);
+    t1 = clock64();
+    double r_dfma = double(t1 - t0) / n;
+    // dependent DMMA chain (accumulator dependency)
+    double c0 = x, c1 = y;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; i++)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0), "+d"(c1) : "d"(y), "d"(y));
+    t1 = clock64();
+    double r_dmma = double(t1 - t0) / n;
+    // dependent library rsqrt chain
+    double z = 2.0 + x * 1e-30;
+    t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < 64; i++) z = rsqrt(z) + 1.5;
+    t1 = clock64();
+    double r_rsqrt = double(t1 - t0) / 64;
+    // dependent sqrt + divide chain
+    double w = 2.0 + x * 1e-30;
+    t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < 64; i++) w = 1.0 / sqrt(w) + 1.5;
+    t1 = clock64();
+    double r_sqrtdiv = double(t1 - t0) / 64;
+    // dependent LDS chain (pointer chasing through shared memory)
+    if (threadIdx.x < 64) sh[threadIdx.x] = (double)((threadIdx.x * 7 + 1) & 63);
+    __syncthreads();
+    int idx = threadIdx.x & 63;
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < 256; i++) idx = (int)sh[idx];
+    t1 = clock64();
+    double r_lds = double(t1 - t0) / 256;
+    // back-to-back barriers with the whole CTA
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < 256; i++) __syncthreads();
+    t1 = clock64();
+    double r_bar = double(t1 - t0) / 256;
+    // shuffle chain
+    double sv = x;
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < 256; i++) sv = __shfl_sync(0xffffffffu, sv, (threadIdx.x + 1) & 31) + 1.0;
+    t1 = clock64();
+    double r_shfl = double(t1 - t0) / 256;
+    if (threadIdx.x == 0) {
+        out[0] = r_dfma; out[1] = r_dmma; out[2] = r_rsqrt; out[3] = r_sqrtdiv; out[4] = r_lds;
+        out[5] = r_bar; out[6] = r_shfl; out[7] = x + c0 + c1 + z + w + idx + sv;
+    }
+}
+}  // namespace
+
+// out[0..6] = cycles per dependent DFMA, DMMA, rsqrt(), 1/sqrt(), LDS (incl. I2F), __syncthreads (nthreads),
+// shuffle+DADD
+extern "C" int htnk_latency_probe(cudaStream_t st, int nthreads, double* host_out)
+{
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8 * sizeof(double)) != cudaSuccess) return -201;
+    latency_kernel<<<1, nthreads, 0, st>>>(d, 1.0);
+    htnk_count_launch();
+    cudaError_t e = cudaMemcpyAsync(host_out, d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : -201;
+}

@@ -21,7 +21,8 @@ namespace {
 
 using namespace htn;
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 16;   // 512 threads: one CTA per SM (135 KB of staging tiles)
+constexpr int kMaxBlocks = 128;      // leave SMs free: the generator overlaps the factorisation kernels
 constexpr int kTile = 32;
 
 template <int GEN>
@@ -47,20 +48,24 @@ struct Seg {
 };
 
 template <int GEN>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size_t nstreams, int nseg,
                    Seg seg0, Seg seg1, uint32_t* ndraws)
 {
-    __shared__ uint64_t s_ki[256];
-    __shared__ double s_wi[256];
-    __shared__ double s_tile[kWarpsPerBlock][kTile][kTile + 1];
+    extern __shared__ double s_dyn[];
+    uint64_t* s_ki = reinterpret_cast<uint64_t*>(s_dyn);
+    double* s_wi = s_dyn + 256;
+    double(*s_tile)[kTile][kTile + 1] = reinterpret_cast<double(*)[kTile][kTile + 1]>(s_dyn + 512);
     zig_stage_tables(s_ki, s_wi);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const size_t warp_base = ((size_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
-    if (warp_base >= nstreams) return;  // whole warp idle
+    // persistent: warp-sized groups of 32 streams are dealt round-robin to the resident warps
+    const size_t ngroups = (nstreams + 31) / 32;
+    for (size_t grp = (size_t)blockIdx.x * kWarpsPerBlock + warp; grp < ngroups;
+         grp += (size_t)gridDim.x * kWarpsPerBlock) {
+    const size_t warp_base = grp * 32;
     const size_t b = warp_base + lane;
     const bool live = b < nstreams;
     double(*tile)[kTile + 1] = s_tile[warp];
@@ -115,6 +120,8 @@ normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size
         stream_end<GEN>(g, states, b);
         if (ndraws) ndraws[b] = ncalls;
     }
+    __syncwarp();
+    }  // groups
 }
 
 }  // namespace
@@ -149,12 +156,11 @@ extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t
     for (int i = 0; i < nseg && i < 2; i++)
         a[i] = Seg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};
     const size_t per_block = (size_t)kWarpsPerBlock * 32;
-    unsigned grid = (unsigned)((nstreams + per_block - 1) / per_block);
-    if (s->gen == 0)
-        normal_fill_kernel<0><<<grid, kWarpsPerBlock * 32, 0, st>>>(s->seeds, s->seed0, s->states, nstreams,
-                                                                    nseg, a[0], a[1], ndraws);
-    else
-        normal_fill_kernel<1><<<grid, kWarpsPerBlock * 32, 0, st>>>(s->seeds, s->seed0, s->states, nstreams,
-                                                                    nseg, a[0], a[1], ndraws);
+    size_t nblocks = (nstreams + per_block - 1) / per_block;
+    unsigned grid = (unsigned)(nblocks < (size_t)kMaxBlocks ? nblocks : (size_t)kMaxBlocks);
+    const size_t smem = (512 + (size_t)kWarpsPerBlock * kTile * (kTile + 1)) * sizeof(double);
+    auto kern = s->gen == 0 ? normal_fill_kernel<0> : normal_fill_kernel<1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(s->seeds, s->seed0, s->states, nstreams, nseg, a[0], a[1], ndraws);
     return launch_status();
 }

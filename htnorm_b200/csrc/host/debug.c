@@ -88,3 +88,15 @@ done:
     }
     return rc ? rc : h_info;
 }
+
+int htnk_latency_probe(cudaStream_t st, int nthreads, double* host_out);
+/* cycles per dependent op, see dev/peak.cu */
+int htn_dbg_latency(int nthreads, double* out8)
+{
+    htn_ctx_t ctx;
+    int rc = htn_ctx_begin(&ctx, -1, NULL, 1);
+    if (rc) return rc;
+    rc = htnk_latency_probe(ctx.stream, nthreads, out8);
+    htn_ctx_end(&ctx, 1);
+    return rc;
+}

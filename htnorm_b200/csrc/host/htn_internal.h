@@ -64,6 +64,7 @@ typedef struct {
     double* u;      /* n x ld: L^T (upper), zeros below; NULL until htn_factor_make_u */
     double* dinv;   /* nblk x 128 x 128: inverse of each diagonal block of L */
     double* dinvt;  /* transposes of the above */
+    double* rdiag;  /* 1 / L[j][j] */
     int nblk;
     int solves;     /* the factor will be used by the blocked triangular solves (needs every inverse) */
 } htn_factor_t;

@@ -45,6 +45,21 @@ done:
     return rc;
 }
 
+/* zero the pad / coefficient columns of Z~, then z_b into columns [0, k) back to front
+ * (std_normal_rand_fill, src/htnorm_distributions.c:12-13, 79) */
+static int ht_draw_chunk(cudaStream_t st, const htn_streams_t* s, size_t b0, size_t nb, int k, size_t ldz,
+                         double* Z)
+{
+    int rc = 0;
+    htnk_streams_t sv;
+    streams_view(s, b0, &sv);
+    HTN_CUDA(cudaMemset2DAsync(Z + k, ldz * 8, 0, (ldz - (size_t)k) * 8, nb, st));
+    htnk_segment_t seg = {(size_t)k, Z, ldz, NULL, NULL, NULL};
+    HTN_TRY(htnk_normal_fill(st, &sv, nb, 1, &seg, NULL));
+done:
+    return rc;
+}
+
 static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, int k2, int k,
                            const double* mean, const double* cov, const double* g, const double* r, double* out,
                            int* first_info)
@@ -53,8 +68,13 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     const int lower_src = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
     const size_t kp = htn_round_up((size_t)k, 16), k2p = htn_round_up((size_t)k2, 16), ldz = kp + k2p;
     double *F = NULL, *Sfull = NULL, *Gp = NULL, *CG = NULL, *Sm = NULL, *WT = NULL, *W = NULL, *c0 = NULL;
-    double *Z = NULL, *D = NULL;
+    double *Z[2] = {NULL, NULL}, *D = NULL;
     int* d_info = NULL;
+    /* the generator runs on a side stream: it needs nothing from the factorisation, so chunk 0's normals
+     * are drawn WHILE cov is being factorised, and chunk c+1's while chunk c is in the sampling GEMM */
+    cudaStream_t side = NULL;
+    cudaEvent_t ev_fork = NULL, ev_rng[2] = {NULL, NULL}, ev_gemm[2] = {NULL, NULL};
+    int rng_pending = -1; /* buffer whose generator launch the main stream has not yet waited for */
     htn_factor_t fa, fs;
     memset(&fa, 0, sizeof(fa));
     memset(&fs, 0, sizeof(fs));
@@ -77,8 +97,27 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_CUDA(cudaMemsetAsync(W, 0, (size_t)k2 * kp * 8, st));
     HTN_CUDA(cudaMemsetAsync(Sm, 0, (size_t)k2 * k2p * 8, st));
 
-    /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
+    size_t chunk = nsamples;
+    const size_t budget = (size_t)3 << 30; /* bytes of Z~ per chunk (two chunks are in flight) */
+    if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
+    const size_t nchunks = (nsamples + chunk - 1) / chunk;
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z[0], chunk * ldz * 8));
+    if (nchunks > 1) HTN_TRY(htn_dalloc(ctx, (void**)&Z[1], chunk * ldz * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
+    HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int e = 0; e < 2; e++) {
+        HTN_CUDA(cudaEventCreateWithFlags(&ev_rng[e], cudaEventDisableTiming));
+        HTN_CUDA(cudaEventCreateWithFlags(&ev_gemm[e], cudaEventDisableTiming));
+    }
     htn_prof_mark(ctx, 0);
+    HTN_CUDA(cudaEventRecord(ev_fork, st));
+    HTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    HTN_TRY(ht_draw_chunk(side, s, 0, nsamples < chunk ? nsamples : chunk, k, ldz, Z[0]));
+    HTN_CUDA(cudaEventRecord(ev_rng[0], side));
+    rng_pending = 0;
+
+    /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
     /* symmetric copy of cov (as the reference's uplo='L' calls see it) and its lower triangle in F */
     HTN_TRY(htnk_sym_expand(st, cov, (size_t)k, k, lower_src, Sfull, kp, F, ldz));
     HTN_TRY(htn_factor_init(ctx, &fa, F, ldz, k, 0));
@@ -115,41 +154,52 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     htn_prof_mark(ctx, 1);
 
     /* ---- per chunk of samples ---- */
-    size_t chunk = nsamples;
-    const size_t budget = (size_t)6 << 30; /* bytes of Z~ per chunk */
-    if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
-    HTN_TRY(htn_dalloc(ctx, (void**)&Z, chunk * ldz * 8));
-    HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
-    for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t b0 = c * chunk;
         const size_t nb = nsamples - b0 < chunk ? nsamples - b0 : chunk;
-        htnk_streams_t sv;
-        streams_view(s, b0, &sv);
-        /* zero the pad / alpha columns, then z_b into columns [0, k) back to front */
-        HTN_CUDA(cudaMemset2DAsync(Z + k, ldz * 8, 0, (ldz - (size_t)k) * 8, nb, st));
-        htnk_segment_t seg = {(size_t)k, Z, ldz, NULL, NULL, NULL};
-        HTN_TRY(htnk_normal_fill(st, &sv, nb, 1, &seg, NULL));
+        const int buf = (int)(c & 1);
+        double* Zc = Z[buf];
+        if (c + 1 < nchunks) { /* draw the next chunk on the side stream, into the other buffer */
+            const size_t b1 = b0 + chunk;
+            const int nbuf = buf ^ 1;
+            if (c >= 1) HTN_CUDA(cudaStreamWaitEvent(side, ev_gemm[nbuf], 0)); /* its previous user is done */
+            HTN_TRY(ht_draw_chunk(side, s, b1, nsamples - b1 < chunk ? nsamples - b1 : chunk, k, ldz, Z[nbuf]));
+            HTN_CUDA(cudaEventRecord(ev_rng[nbuf], side));
+        }
+        HTN_CUDA(cudaStreamWaitEvent(st, ev_rng[buf], 0));
+        rng_pending = (c + 1 < nchunks) ? (buf ^ 1) : -1;
         htn_prof_mark(ctx, 2);
         if (!h_info[1]) {
             /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
-            HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Z, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+            HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Zc, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
             if (k2 <= ALPHA_K2_MAX) {
-                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, NULL, Z, ldz, kp));
+                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, NULL, Zc, ldz, kp));
             } else {
                 HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
-                HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Z + kp, ldz, NULL));
+                HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Zc + kp, ldz, NULL));
             }
         }
         htn_prof_mark(ctx, 3);
         /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
-        HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Z, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
+        HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Zc, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
                              (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 0));
+        HTN_CUDA(cudaEventRecord(ev_gemm[buf], st));
         htn_prof_mark(ctx, 4);
     }
 done:
+    /* never free a buffer the side stream may still be writing */
+    if (rng_pending >= 0 && ev_rng[rng_pending]) cudaStreamWaitEvent(st, ev_rng[rng_pending], 0);
     htn_factor_free(ctx, &fa);
     htn_factor_free(ctx, &fs);
-    htn_dfree(ctx, Z);
+    htn_dfree(ctx, Z[0]);
+    htn_dfree(ctx, Z[1]);
     htn_dfree(ctx, D);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int e = 0; e < 2; e++) {
+        if (ev_rng[e]) cudaEventDestroy(ev_rng[e]);
+        if (ev_gemm[e]) cudaEventDestroy(ev_gemm[e]);
+    }
+    if (side) cudaStreamDestroy(side); /* asynchronous: resources are released once its work has drained */
     htn_dfree(ctx, c0);
     htn_dfree(ctx, Sm);
     htn_dfree(ctx, WT);

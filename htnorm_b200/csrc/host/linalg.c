@@ -21,10 +21,11 @@ int htn_factor_init(htn_ctx_t* ctx, htn_factor_t* fa, double* f, size_t ld, int 
     fa->nblk = (n + HTN_NB - 1) / HTN_NB;
     fa->solves = want_u;
     size_t blk = (size_t)HTN_NB * HTN_NB * sizeof(double);
-    HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinv, blk * fa->nblk));
-    HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinvt, blk * fa->nblk));
-    HTN_CUDA(cudaMemsetAsync(fa->dinv, 0, blk * fa->nblk, ctx->stream));
-    HTN_CUDA(cudaMemsetAsync(fa->dinvt, 0, blk * fa->nblk, ctx->stream));
+    HTN_TRY(htn_dalloc(ctx, (void**)&fa->rdiag, (size_t)fa->nblk * HTN_NB * sizeof(double)));
+    if (fa->solves) {
+        HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinv, blk * fa->nblk));
+        HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinvt, blk * fa->nblk));
+    }
     if (want_u) {
         HTN_TRY(htn_dalloc(ctx, (void**)&fa->u, (size_t)n * ld * sizeof(double)));
     }
@@ -37,7 +38,8 @@ void htn_factor_free(htn_ctx_t* ctx, htn_factor_t* fa)
     htn_dfree(ctx, fa->dinv);
     htn_dfree(ctx, fa->dinvt);
     htn_dfree(ctx, fa->u);
-    fa->dinv = fa->dinvt = fa->u = NULL;
+    htn_dfree(ctx, fa->rdiag);
+    fa->dinv = fa->dinvt = fa->u = fa->rdiag = NULL;
 }
 
 int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa)
@@ -55,32 +57,24 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
     int rc = 0;
     const int n = fa->n;
     const size_t ld = fa->ld;
-    double* panel = NULL; /* L21 of the current step, rows x 128 (out of place: many small N tiles may run) */
-    if (fa->nblk > 1) HTN_TRY(htn_dalloc(ctx, (void**)&panel, (size_t)n * HTN_NB * sizeof(double)));
     for (int jb = 0; jb < fa->nblk; jb++) {
         const int j0 = jb * HTN_NB;
         const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
         const int rows = n - j0 - nb;
         double* ajj = fa->f + (size_t)j0 * ld + j0;
-        double* dinv = fa->dinv + (size_t)jb * HTN_NB * HTN_NB;
-        double* dinvt = fa->dinvt + (size_t)jb * HTN_NB * HTN_NB;
-        /* the inverse of the last diagonal block is only needed by later triangular solves */
-        const int want_inv = rows > 0 || fa->solves;
-        HTN_TRY(htnk_potf2_inv(ctx->stream, ajj, ld, nb, j0, want_inv ? dinv : NULL, want_inv ? dinvt : NULL,
-                               d_info));
+        HTN_TRY(htnk_potf2(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info));
         if (rows <= 0) break;
         double* a21 = fa->f + (size_t)(j0 + nb) * ld + j0;
-        /* panel: L21 = A21 * inv(L11)^T */
-        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, nb, nb, 1.0, a21, ld, dinv, HTN_NB, 0.0, panel, HTN_NB, NULL,
-                             HTNK_GEMM_FULL, 0, 0, 0));
-        /* trailing update: A22 -= L21 * L21^T on the lower-triangle tiles */
+        /* panel: L21 = A21 * L11^-T, rows independent, in place */
+        HTN_TRY(htnk_trsm_rows(ctx->stream, a21, ld, rows, ajj, ld, nb, fa->rdiag + j0));
+        /* trailing update: A22 -= L21 * L21^T on the lower-triangle tiles (DMMA) */
         double* a22 = fa->f + (size_t)(j0 + nb) * ld + (j0 + nb);
-        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, panel, HTN_NB, panel, HTN_NB, 1.0, a22, ld, NULL,
+        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, a21, ld, a21, ld, 1.0, a22, ld, NULL,
                              HTNK_GEMM_C_LOWER, 0, 0, 0));
-        HTN_TRY(htnk_copy2d(ctx->stream, panel, HTN_NB, rows, nb, a21, ld, NULL));
     }
+    /* inverses of the diagonal blocks, all at once, only when blocked solves will follow */
+    if (fa->solves) HTN_TRY(htnk_trtri_batched(ctx->stream, fa->f, ld, n, fa->dinv, fa->dinvt));
 done:
-    htn_dfree(ctx, panel);
     return rc;
 }
 
