@@ -43,14 +43,25 @@ def gather_rows(local, nsamples, group=None, dst=None):
         raise ValueError("local shard has the wrong number of rows")
     if world == 1:
         return local
-    full = torch.empty((nsamples, k), dtype=local.dtype, device=local.device)
     offs = np.concatenate([[0], np.cumsum(sizes)])
-    parts = [full[offs[q]:offs[q + 1]] for q in range(world)]
+    mx = max(sizes)
+    # shards differ by at most one row: pad to the common size so that one equal-sized collective works
+    # on both backends, then drop the padding rows
+    if local.shape[0] < mx:
+        local = torch.cat([local, local.new_zeros((mx - local.shape[0], k))])
+    local = local.contiguous()
     if dst is None:
-        if len(set(sizes)) == 1:
-            dist.all_gather_into_tensor(full, local.contiguous(), group=group)
-        else:
-            dist.all_gather(parts, local.contiguous(), group=group)
-        return full
-    dist.gather(local.contiguous(), parts if rank == dst else None, dst=dst, group=group)
-    return full if rank == dst else None
+        flat = torch.empty((world * mx, k), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(flat, local, group=group)
+        buf = flat.view(world, mx, k)
+    else:
+        buf = torch.empty((world, mx, k), dtype=local.dtype, device=local.device) if rank == dst else None
+        dist.gather(local, list(buf.unbind(0)) if rank == dst else None, dst=dst, group=group)
+        if rank != dst:
+            return None
+    if len(set(sizes)) == 1:
+        return buf.reshape(nsamples, k)
+    full = torch.empty((nsamples, k), dtype=local.dtype, device=local.device)
+    for q in range(world):
+        full[offs[q]:offs[q + 1]] = buf[q, :sizes[q]]
+    return full
