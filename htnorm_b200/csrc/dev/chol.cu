@@ -36,18 +36,26 @@ __device__ __forceinline__ double fast_rsqrt(double x)
 }
 
 // Thread (i = tid / 4, cq = tid % 4) OWNS the elements (i, c), c == cq (mod 4), and keeps them in 32
-// REGISTERS for the whole factorisation (the column loop is fully unrolled so every register index is a
-// compile-time constant).  Step j: the owners of column j publish it (unscaled) to a double-buffered
-// shared-memory column, ONE barrier, then every thread computes the pivot's rsqrt redundantly and applies
-// the rank-1 update to its own registers: no shared-memory traffic for the matrix itself.
+// REGISTERS used as a ROTATING window: during column group jj (columns 4jj .. 4jj+3) R[u] holds the
+// element of column cq + 4 (jj + u); after the group R[0] is final and the window shifts by one, so the
+// loop body is identical for every group (a fully unrolled 128-column version measured I-cache bound).
+//
+// Step j is software-pipelined around ONE barrier:
+//   urgent : pivot rsqrt (redundantly in every thread), then the owners of column j+1 apply step j to
+//            that column only and publish it (unscaled) to shared memory        -> barrier
+//   lazy   : the rest of the rank-1 update of step j runs after the barrier, i.e. in the shadow of the
+//            other warps' next urgent part.
+// The published columns rotate through three buffers (a warp still in lazy(j) reads column j while
+// column j+2 is being published).  No per-element predicates: updates that fall above the diagonal or
+// beyond the block land in registers / zero padding that are never read.
 __global__ void __launch_bounds__(NT, 1)
 potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ rdiag_out,
              int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    double* S = sm;                  // [NB][LDB]  staging for the coalesced load / store, L for phase 2
-    double* colbuf = sm + NB * LDB;  // [2][NB]    published column (phase 1) / published row (phase 2)
-    double* rdiag = colbuf + 2 * NB; // [NB]       1 / L[j][j]
+    double* S = sm;                  // [NB][LDB]  staging for the coalesced load / store
+    double* colbuf = sm + NB * LDB;  // [3][2 * NB] published columns, second half stays zero
+    double* rdiag = colbuf + 6 * NB; // [NB]       1 / L[j][j]
     const int tid = threadIdx.x;
     const int i = tid >> 2, cq = tid & 3;
 
@@ -55,17 +63,16 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
         int r = idx >> 7, c = idx & (NB - 1);
         S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : 0.0;
     }
+    for (int idx = tid; idx < 6 * NB; idx += NT) colbuf[idx] = 0.0;
     __syncthreads();
     double R[32];
 #pragma unroll
     for (int jj = 0; jj < 32; jj++) R[jj] = S[i * LDB + cq + 4 * jj];
+    if (cq == 0) colbuf[i] = R[0];  // column 0
+    __syncthreads();
 
-    // ---- phase 1 ----
-    // The register file is used as a ROTATING window: during column group jj (columns 4jj .. 4jj+3),
-    // R[u] holds the element of column cq + 4 (jj + u).  After the group, R[0] is final (it goes to
-    // shared memory) and the window shifts by one.  The loop body is therefore identical for every
-    // group and stays a few KB (a fully unrolled 128-column version measured I-cache bound).
     int nfact = nb;
+    int bj = 0;  // buffer that holds column j
     const int ngroups = (nb + 3) >> 2;
     for (int jj = 0; jj < ngroups; jj++) {
         const int c0 = cq + 4 * jj;  // the column this thread retires in this group
@@ -73,37 +80,52 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
         for (int q = 0; q < 4; q++) {
             const int j = 4 * jj + q;
             if (j < nb && nfact == nb) {  // uniform
-                double* col = colbuf + (q & 1) * NB;
-                if (cq == q && i >= j) col[i] = R[0];
-                __syncthreads();
+                const double* col = colbuf + bj * 2 * NB;
+                const int bn = bj == 2 ? 0 : bj + 1;
+                double* coln = colbuf + bn * 2 * NB;
                 const double ajj = col[j];
-                if (ajj <= 0.0) {  // uniform; NaN passes
+                double m = 0.0, aij = 0.0, rinv = 0.0;
+                const bool ok = !(ajj <= 0.0);  // uniform; NaN passes
+                if (ok) {
+                    rinv = fast_rsqrt(ajj);
+                    if (i > j) {
+                        aij = col[i];
+                        m = aij * (rinv * rinv);
+                        // urgent: column j+1 (register R[0] of the thread cq == q+1, or R[1] of cq == 0)
+                        if (q < 3) {
+                            if (cq == q + 1) { R[0] = fma(-m, col[j + 1], R[0]); coln[i] = R[0]; }
+                        } else {
+                            if (cq == 0) { R[1] = fma(-m, col[j + 1], R[1]); coln[i] = R[1]; }
+                        }
+                    }
+                } else {
                     if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
                     nfact = j;
-                } else {
-                    const double rinv = fast_rsqrt(ajj);
+                }
+                __syncthreads();
+                if (ok) {
                     if (i > j) {
-                        const double aij = col[i];
-                        const double m = aij * (rinv * rinv);
-                        if (cq > q && c0 <= i) R[0] = fma(-m, col[c0], R[0]);
+                        // lazy: every other owned column > j+1
+                        if (cq > q + 1) R[0] = fma(-m, col[c0], R[0]);
+                        if (!(q == 3 && cq == 0)) R[1] = fma(-m, col[c0 + 4], R[1]);
 #pragma unroll
-                        for (int ub = 0; ub < 4; ub++) {
+                        for (int u = 2; u < 8; u++) R[u] = fma(-m, col[c0 + 4 * u], R[u]);
+#pragma unroll
+                        for (int ub = 1; ub < 4; ub++) {
                             if (jj + 8 * ub < 32) {  // uniform: later columns do not exist
 #pragma unroll
-                                for (int u = (ub == 0 ? 1 : 8 * ub); u < 8 * ub + 8; u++) {
-                                    const int c = c0 + 4 * u;
-                                    if (c <= i) R[u] = fma(-m, col[c], R[u]);
-                                }
+                                for (int u = 8 * ub; u < 8 * ub + 8; u++) R[u] = fma(-m, col[c0 + 4 * u], R[u]);
                             }
                         }
                         if (cq == q) R[0] = aij * rinv;  // L[i][j]
                     } else if (i == j && cq == q) {
-                        double d = ajj * rinv;                       // sqrt(ajj), one Heron correction
+                        double d = ajj * rinv;  // sqrt(ajj), one Heron correction
                         d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
                         R[0] = d;
                     }
                     if (tid == 0) rdiag[j] = rinv;
                 }
+                bj = bn;
             }
         }
         // retire column c0: L[i][c0] (zeros above the diagonal / beyond a failed column)
@@ -244,7 +266,7 @@ extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col
 {
     if (nb <= 0) return 0;
     if (nb > NB) return -202;
-    const size_t smem = (size_t)(NB * LDB + 3 * NB) * sizeof(double);
+    const size_t smem = (size_t)(NB * LDB + 7 * NB) * sizeof(double);
     if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     potf2_kernel<<<1, NT, smem, st>>>(a, ld, nb, col0, rdiag, info);

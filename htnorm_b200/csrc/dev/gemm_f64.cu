@@ -30,9 +30,6 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 16;
-constexpr int LDS = 20;  // padded row length (doubles) of a smem tile
-constexpr int STAGES = 3;
 
 struct GemmParams {
     int M, N, K;
@@ -67,16 +64,18 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // rows x BK tile (row-major source, leading dimension ld) -> smem [rows][LDS]; elements outside
 // [0, nrows_total) x [k0, kend) are zero-filled by cp.async's src-size operand.
-template <int ROWS, int NTHREADS>
+template <int ROWS, int NTHREADS, int BK>
 __device__ __forceinline__ void load_tile(double* s, const double* g, size_t ld, int row0, int nrows_total,
                                           int k0, int kend, int tid)
 {
-    constexpr int CHUNKS = ROWS * (BK / 2);  // 16-byte chunks
+    constexpr int LDS = BK + 4;
+    constexpr int CPR = BK / 2;              // 16-byte chunks per row
+    constexpr int CHUNKS = ROWS * CPR;
 #pragma unroll
     for (int it = 0; it < (CHUNKS + NTHREADS - 1) / NTHREADS; it++) {
         int id = tid + it * NTHREADS;
         if (CHUNKS % NTHREADS != 0 && id >= CHUNKS) break;
-        int r = id >> 3, ch = id & 7;
+        int r = id / CPR, ch = id % CPR;
         int grow = row0 + r;
         int kk = k0 + ch * 2;
         int rem = kend - kk;
@@ -86,10 +85,11 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, size_t ld,
     }
 }
 
-template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB>
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB, int BK, int STAGES>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(const GemmParams p)
 {
     constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
+    constexpr int LDS = BK + 4;  // padded row (doubles): 4 mod 16 -> the DMMA fragment pattern is conflict-free
     static_assert(WARPS_M * WM * 8 == BM, "BM");
     static_assert(WARPS_N * WN * 8 == BN, "BN");
     extern __shared__ __align__(16) double smem[];
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
             int k0, kend;
             chunk_range(c, k0, kend);
             int s = c % STAGES;
-            load_tile<BM, NTHREADS>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
-            load_tile<BN, NTHREADS>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
+            load_tile<BM, NTHREADS, BK>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
+            load_tile<BN, NTHREADS, BK>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
         }
         cp_async_commit();
     };
@@ -238,11 +238,11 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
     }
 }
 
-template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB>
+template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB, int BK = 16, int STAGES = 3>
 int launch(cudaStream_t st, const GemmParams& p)
 {
-    constexpr size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
-    auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN, MINB>;
+    constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
+    auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN, MINB, BK, STAGES>;
     // per-device attribute: set on every launch (cheap) so that any current device is covered
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
@@ -260,8 +260,8 @@ static int wide_config()
     static int cfg = 0;
     if (cfg == 0) {
         const char* e = getenv("HTN_GEMM_WIDE");
-        cfg = e ? atoi(e) : 64;
-        if (cfg != 64 && cfg != 65 && cfg != 128 && cfg != 129) cfg = 64;
+        cfg = e ? atoi(e) : 70;
+        if (cfg < 64 || cfg > 129) cfg = 64;
     }
     return cfg;
 }
@@ -291,12 +291,20 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
     p.tiles_m = tiles_m;
-    p.tiles_n = (N + (bn & ~1) - 1) / (bn & ~1);
+    const int bn_cols = bn >= 128 ? 128 : (bn >= 64 ? 64 : bn);
+    p.tiles_n = (N + bn_cols - 1) / bn_cols;
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
     switch (bn) {
         case 128: return launch<128, 2, 4, 8, 4, 1>(st, p);
+        case 70: {  // TMA + mbarrier ring (gemm_tma.cu); falls back if a tensor map cannot be built
+            int r = htnk_gemm_tn_tma(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, mode, ktri, kext0);
+            if (r != 1) return r;
+            return launch<64, 2, 2, 8, 4, 2>(st, p);
+        }
         case 64: return launch<64, 2, 2, 8, 4, 2>(st, p);
         case 65: return launch<64, 4, 2, 4, 4, 2>(st, p);    // 16 warps / SM, warp tile 32 x 32
+        case 66: return launch<64, 2, 2, 8, 4, 2, 32, 2>(st, p);  // BK = 32, two stages: half the barriers
+        case 67: return launch<64, 2, 2, 8, 4, 2, 16, 4>(st, p);  // four stages (1 CTA/SM fits only: smem)
         case 129: return launch<128, 4, 4, 4, 4, 1>(st, p);  // 16 warps / SM in one CTA
         case 32: return launch<32, 8, 1, 2, 4, 1>(st, p);
         case 8: return launch<8, 8, 1, 2, 1, 1>(st, p);

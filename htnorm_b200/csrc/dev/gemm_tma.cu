@@ -1,0 +1,299 @@
+// TMA-fed variant of the FP64 tensor-core GEMM (same contract as gemm_f64.cu: C = alpha A B^T + beta C + bias,
+// "TN", modes FULL / B_LOWER / C_LOWER), used for the wide-N sampling GEMM and trailing updates.
+//
+// What changes against the cp.async kernel:
+//   * operand tiles arrive by TMA (cp.async.bulk.tensor.2d, one elected thread, 2 instructions per K chunk)
+//     instead of ~100 integer/address instructions per warp per chunk; out-of-range rows / columns are
+//     zero-filled by the TMA unit (no predicates);
+//   * a 4-deep ring of stages guarded by mbarrier full/empty pairs replaces __syncthreads(): warps of a
+//     CTA are never forced to the same point, a warp only ever waits for DATA;
+//   * tiles are dense 128-byte rows with the hardware 128B swizzle.  The DMMA m8n8k4 fragment pattern would
+//     bank-conflict on such rows, so the K order INSIDE a 16-wide chunk is permuted identically for A and B:
+//     k4 step s uses k = {2s, 2s+1, 8+2s, 9+2s}; a half-warp then touches 16 distinct 8-byte bank pairs.
+// CTA tile 128 x 64, 4 warps of 64 x 32, two CTAs per SM (2 x 98 KB of smem).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "launchers.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4, NT = 128;
+constexpr int WM = 8, WN = 4;  // warp tile 64 x 32 in m8n8 units
+constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
+constexpr int AHEAD = 2;  // chunks issued ahead of the one being consumed
+
+struct TmaGemmParams {
+    int M, N, K;
+    double alpha, beta;
+    double* C;
+    const double* bias;
+    size_t ldc;
+    int mode, ktri, kext0;
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
+            "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(NT, 2)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TmaGemmParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the 128B swizzle pattern (the swizzle XORs address bits [4:6] with [7:9])
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = base;
+    unsigned char* sB = base + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int bid = blockIdx.x;
+    const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
+    const int tm = bid / p.tiles_n;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < n0) return;
+
+    int kend1 = p.K, kbeg2 = p.K;
+    const int kend2 = p.K;
+    if (p.mode == HTNK_GEMM_B_LOWER) {
+        int n1 = min(p.N, n0 + BN);
+        kend1 = min(n1, p.ktri);
+        kbeg2 = min(p.kext0, p.K);
+    }
+    const int nc1 = (kend1 + BK - 1) / BK;
+    const int nc2 = (kend2 - kbeg2 + BK - 1) / BK;
+    const int nchunks = nc1 + nc2;
+    auto chunk_range = [&](int c, int& k0, int& kend) {
+        if (c < nc1) { k0 = c * BK; kend = kend1; }
+        else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NT / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // one elected thread feeds the ring; chunk c lands in stage c % STAGES
+    auto issue = [&](int c) {
+        if (c >= nchunks) return;
+        const int s = c % STAGES, round = c / STAGES;
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        int k0, kend;
+        chunk_range(c, k0, kend);
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        tma_load_2d(sA + s * A_BYTES, &tmA, k0, m0, &full[s]);
+        tma_load_2d(sB + s * B_BYTES, &tmB, k0, n0, &full[s]);
+    };
+    if (tid == 0) {
+        for (int c = 0; c < AHEAD; c++) issue(c);
+    }
+
+    double acc[WM][WN][2];
+#pragma unroll
+    for (int i = 0; i < WM; i++)
+#pragma unroll
+        for (int j = 0; j < WN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int g = lane >> 2, t4 = lane & 3;
+    const int nw = n0 + wn * WN * 8;
+    const int jhi = min(WN, (p.N - nw + 7) >> 3);
+    // swizzled fragment addressing: row r (r & 7 == g), 16-byte chunk ((t4 >> 1) * 4 + s) ^ g, half t4 & 1
+    const int a_off = (wm * WM * 8 + g) * 128 + (t4 & 1) * 8;
+    const int b_off = (wn * WN * 8 + g) * 128 + (t4 & 1) * 8;
+    int xs[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) xs[s] = ((((t4 >> 1) * 4 + s) ^ g) << 4);
+
+    for (int c = 0; c < nchunks; c++) {
+        if (tid == 0) issue(c + AHEAD);
+        const int st = c % STAGES;
+        mbar_wait(&full[st], (c / STAGES) & 1);
+        int k0, kend;
+        chunk_range(c, k0, kend);
+        const unsigned char* a_s = sA + st * A_BYTES + a_off;
+        const unsigned char* b_s = sB + st * B_BYTES + b_off;
+        const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < nc1) && (k0 + BK > nw);
+        if (!diag && jhi == WN && kend - k0 >= BK) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                double af[WM], bf[WN];
+#pragma unroll
+                for (int i = 0; i < WM; i++) af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
+#pragma unroll
+                for (int j = 0; j < WN; j++) bf[j] = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
+#pragma unroll
+                for (int i = 0; i < WM; i++)
+#pragma unroll
+                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                // step s multiplies k = k0 + {2s, 2s+1, 8+2s, 9+2s}; its smallest k decides whether any
+                // non-zero element can be involved
+                const int kmin = k0 + 2 * s;
+                if (kmin < kend) {
+                    int jlo = 0;
+                    if (diag) jlo = max(0, (kmin - nw) >> 3);
+                    if (jlo < jhi) {
+                        double af[WM];
+#pragma unroll
+                        for (int i = 0; i < WM; i++) af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
+#pragma unroll
+                        for (int j = 0; j < WN; j++) {
+                            if (j >= jlo && j < jhi) {
+                                const double bfj = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
+#pragma unroll
+                                for (int i = 0; i < WM; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bfj);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
+    }
+
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < WM; i++) {
+        const int m = m0 + wm * WM * 8 + i * 8 + g;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < WN; j++) {
+            const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
+            if (n >= p.N) continue;
+            double v0 = p.alpha * acc[i][j][0];
+            double v1 = p.alpha * acc[i][j][1];
+            double* cp = p.C + (size_t)m * p.ldc + n;
+            const bool two = (n + 1 < p.N);
+            if (p.bias) {
+                v0 += p.bias[n];
+                if (two) v1 += p.bias[n + 1];
+            }
+            if (vec_ok && two) {
+                if (p.beta != 0.0) {
+                    double2 o = *reinterpret_cast<const double2*>(cp);
+                    v0 += p.beta * o.x;
+                    v1 += p.beta * o.y;
+                }
+                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+            } else {
+                if (p.beta != 0.0) {
+                    v0 += p.beta * cp[0];
+                    if (two) v1 += p.beta * cp[1];
+                }
+                cp[0] = v0;
+                if (two) cp[1] = v1;
+            }
+        }
+    }
+}
+
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t get_encode()
+{
+    static encode_fn_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_fn_t>(ptr);
+    }
+    return fn;
+}
+
+// rows x cols row-major matrix (leading dimension ld doubles), box = 16 columns x box_rows rows, 128B swizzle
+bool make_map(CUtensorMap* map, const double* ptr, size_t ld, int rows, int cols, int box_rows)
+{
+    encode_fn_t enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// returns 1 if the TMA path cannot be used for these operands (caller falls back to the cp.async kernel)
+extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
+                                const double* B, size_t ldb, double beta, double* C, size_t ldc,
+                                const double* bias, int mode, int ktri, int kext0)
+{
+    if (M <= 0 || N <= 0) return 0;
+    if (K <= 0 || (lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+        (reinterpret_cast<uintptr_t>(B) & 15))
+        return 1;
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, A, lda, M, K, BM) || !make_map(&tmB, B, ldb, N, K, BN)) return 1;
+    TmaGemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.alpha = alpha; p.beta = beta;
+    p.C = C; p.bias = bias; p.ldc = ldc;
+    p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
+    const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
+    if (cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -201;
+    gemm_tma_kernel<<<(unsigned)p.tiles_m * (unsigned)p.tiles_n, NT, smem, st>>>(tmA, tmB, p);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}

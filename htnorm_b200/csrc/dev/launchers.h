@@ -58,6 +58,11 @@ int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const doubl
                  const double* B, size_t ldb, double beta, double* C, size_t ldc, const double* bias,
                  int mode, int ktri, int kext0, int bn);
 
+/* TMA-fed variant for wide N (gemm_tma.cu); returns 1 when the operands do not admit a tensor map */
+int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
+                     const double* B, size_t ldb, double beta, double* C, size_t ldc, const double* bias,
+                     int mode, int ktri, int kext0);
+
 /* ---- factorisation building blocks (chol.cu) ---- */
 /* Factor the nb x nb (nb <= 128) diagonal block at a (row-major, ld) in place: lower triangle := L,
  * strictly-upper := 0.  rdiag (device, nb doubles, may be NULL) receives 1 / L[j][j].  *info (device int)

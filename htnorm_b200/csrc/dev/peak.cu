@@ -176,3 +176,131 @@ extern "C" int htnk_latency_probe(cudaStream_t st, int nthreads, double* host_ou
     cudaFree(d);
     return e == cudaSuccess ? 0 : -201;
 }
+
+// ---- DMMA issue sweep: throughput vs resident warps and independent accumulators per warp ----
+namespace {
+template <int ILP>
+__global__ void dmma_sweep_kernel(double* sink, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - 1e-12 * threadIdx.x;
+    double c[2 * ILP];
+#pragma unroll
+    for (int i = 0; i < 2 * ILP; i++) c[i] = i * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[2 * i]), "+d"(c[2 * i + 1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * ILP; i++) s += c[i];
+    if (s == 123.456) sink[0] = s;
+}
+}  // namespace
+
+// TFLOP/s with `warps_per_sm` resident warps (one CTA per SM) and ilp in {8, 32} accumulators per warp
+extern "C" double htnk_dmma_sweep(cudaStream_t st, int warps_per_sm, int ilp)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 20000;
+    double best = -1;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0, st);
+        if (ilp == 32) dmma_sweep_kernel<32><<<sms, warps_per_sm * 32, 0, st>>>(sink, iters / 4, 1.0);
+        else dmma_sweep_kernel<8><<<sms, warps_per_sm * 32, 0, st>>>(sink, iters, 1.0);
+        htnk_count_launch();
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = (double)sms * warps_per_sm * (double)iters * 8.0 * 512.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+// ---- synthetic inner loop of the GEMM: fragments from shared memory + 32 DMMAs per k4 step, no global
+// loads, no barriers.  Isolates "operand delivery" from "pipeline / synchronisation" losses. ----
+namespace {
+__global__ void __launch_bounds__(128, 2) dmma_tile_kernel(double* sink, int iters)
+{
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < (128 + 64) * 20; i += 128) sm[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    const int g = lane >> 2, t4 = lane & 3;
+    const double* a_s = sm + ((warp >> 1) * 64 + g) * 20 + t4;
+    const double* b_s = sm + 128 * 20 + ((warp & 1) * 32 + g) * 20 + t4;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int kk = 0; kk < 16; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) af[i] = a_s[i * 8 * 20 + kk];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[j] = b_s[j * 8 * 20 + kk];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(af[i]), "d"(bf[j]));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 123.456) sink[0] = s;
+}
+}  // namespace
+
+extern "C" double htnk_dmma_tile_probe(cudaStream_t st, int ctas_per_sm)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    const size_t smem = ctas_per_sm >= 2 ? 92160 : 180000;  // forces the requested residency
+    cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4000;
+    double best = -1;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0, st);
+        dmma_tile_kernel<<<sms * ctas_per_sm, 128, smem, st>>>(sink, iters);
+        htnk_count_launch();
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = (double)sms * ctas_per_sm * 4.0 * iters * 128.0 * 512.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}

@@ -100,3 +100,23 @@ int htn_dbg_latency(int nthreads, double* out8)
     htn_ctx_end(&ctx, 1);
     return rc;
 }
+
+double htnk_dmma_sweep(cudaStream_t st, int warps_per_sm, int ilp);
+double htn_dbg_dmma_sweep(int warps_per_sm, int ilp)
+{
+    htn_ctx_t ctx;
+    if (htn_ctx_begin(&ctx, -1, NULL, 1)) return -1.0;
+    double v = htnk_dmma_sweep(ctx.stream, warps_per_sm, ilp);
+    htn_ctx_end(&ctx, 1);
+    return v;
+}
+
+double htnk_dmma_tile_probe(cudaStream_t st, int ctas_per_sm);
+double htn_dbg_dmma_tile_probe(int ctas_per_sm)
+{
+    htn_ctx_t ctx;
+    if (htn_ctx_begin(&ctx, -1, NULL, 1)) return -1.0;
+    double v = htnk_dmma_tile_probe(ctx.stream, ctas_per_sm);
+    htn_ctx_end(&ctx, 1);
+    return v;
+}
