@@ -112,10 +112,44 @@ class HTNGenerator:
         return out
 
 
-def _generator(random_state, gen="pcg64"):
+class _NumpyGenerator(HTNGenerator):
+    """A NumPy bit generator behind the C `rng_t` vtable, exactly what the reference's wrapper builds
+    (pyhtnorm/_htnorm.pyx:116-122: base = bitgen.state, next_uint64 / next_double = NumPy's functions).
+    Such a FOREIGN generator cannot run on the device: its normals are drawn on the host through the
+    callbacks (csrc/host/foreign_rng.c), the algebra runs on the GPU."""
+
+    def __init__(self, random_state):
+        gen = np.random.default_rng(random_state)   # same rule as the reference (_htnorm.pyx:201)
+        self.gen = "numpy"
+        self._np = gen
+        self._bitgen = gen.bit_generator
+        iface = self._bitgen.ctypes
+        self._rng_struct = _lib.RngT(C.c_void_p(iface.state_address).value,
+                                     C.cast(iface.next_uint64, C.c_void_p).value,
+                                     C.cast(iface.next_double, C.c_void_p).value)
+        self._rng = C.pointer(self._rng_struct)
+
+    def __del__(self):
+        self._rng = None
+
+    def _locked(self, fn, *a, **kw):
+        with self._bitgen.lock:                     # the reference holds the same lock (_htnorm.pyx:205)
+            return fn(*a, **kw)
+
+    def hyperplane_truncated_mvnorm(self, *a, **kw):
+        return self._locked(HTNGenerator.hyperplane_truncated_mvnorm, self, *a, **kw)
+
+    def structured_precision_mvnorm(self, *a, **kw):
+        return self._locked(HTNGenerator.structured_precision_mvnorm, self, *a, **kw)
+
+
+def _generator(random_state):
+    """random_state as in the reference: anything numpy.random.default_rng accepts (None, int, SeedSequence,
+    BitGenerator, Generator) -> NumPy's generator driven through the rng_t callbacks; an HTNGenerator -> one
+    of the library's own generators, advanced on the GPU."""
     if isinstance(random_state, HTNGenerator):
         return random_state
-    return HTNGenerator(random_state, gen)
+    return _NumpyGenerator(random_state)
 
 
 def hyperplane_truncated_mvnorm(mean, cov, g, r, diag=False, out=None, random_state=None):

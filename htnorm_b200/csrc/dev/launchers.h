@@ -28,6 +28,8 @@ typedef struct {
     uint64_t seed0;         /* seed_b = seed0 + b when seeds == NULL */
     uint64_t* states;       /* device, 4 words per stream, or NULL.  If non-NULL the streams START
                                from these states (seeds ignored) and the advanced states are written back */
+    const double* zpre;     /* device or NULL: normals already drawn (draw order, all segments of stream b
+                               back to back); the generator is not run, they are only scattered */
 } htnk_streams_t;
 
 /* one run of normals per stream: element j (draw order) goes to out[b*ld + (n-1-j)] after
@@ -118,10 +120,11 @@ int htnk_rows_dot(cudaStream_t st, size_t nsamples, int k, int k2, const double*
 
 /* ---- small independent problems (small_batched.cu) ---- */
 /* One CTA per problem, k <= 128, k2 <= 16: the whole of src/htnorm.c:85-187 for problem b with its own
- * mean/cov/g/r (back to back) and its own stream; info[b] as the reference's return code. */
-int htnk_ht_small_batched(cudaStream_t st, const htnk_streams_t* s, size_t nproblems, int k, int k2,
-                          const double* mean, const double* cov, const double* g, const double* r,
-                          int diag, int lower_src, double* out, int* info);
+ * mean/cov/g/r (back to back); zs holds the problem's k normals (already drawn, reverse-fill order);
+ * info[b] as the reference's return code. */
+int htnk_ht_small_batched(cudaStream_t st, size_t nproblems, int k, int k2, const double* mean,
+                          const double* cov, const double* g, const double* r, const double* zs, int diag,
+                          int lower_src, double* out, int* info);
 
 /* ---- peak microbenchmarks (peak.cu) ---- */
 double htnk_dmma_peak_tflops(cudaStream_t st, double ms);

@@ -124,6 +124,24 @@ normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size
     }  // groups
 }
 
+// normals drawn elsewhere (foreign generator, host side): zpre[b * total + off + j] is the j-th draw of
+// stream b; same placement and transforms as normal_fill_kernel's write-out
+__global__ void __launch_bounds__(256)
+prefilled_kernel(const double* __restrict__ zpre, size_t nstreams, size_t total, size_t off, Seg sg)
+{
+    const size_t n = sg.n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nstreams * n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / n, j = idx - b * n;
+        const size_t i = n - 1 - j;
+        double v = zpre[b * total + off + j];
+        if (sg.div) v = __ddiv_rn(v, sg.div[i]);
+        if (sg.mul) v = __dmul_rn(v, sg.mul[i]);
+        if (sg.add) v = __dadd_rn(sg.add[i], v);
+        sg.out[b * sg.ld + i] = v;
+    }
+}
+
 }  // namespace
 
 static unsigned long long g_launches = 0;
@@ -152,6 +170,20 @@ extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t
                                 const htnk_segment_t* seg, uint32_t* ndraws)
 {
     if (nstreams == 0 || nseg <= 0) return 0;
+    if (s->zpre) {  // pre-drawn normals: scatter only
+        size_t total = 0, off = 0;
+        for (int i = 0; i < nseg; i++) total += seg[i].n;
+        for (int i = 0; i < nseg; i++) {
+            if (seg[i].n == 0) continue;
+            Seg sg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};
+            size_t work = nstreams * seg[i].n;
+            unsigned grid = (unsigned)((work + 255) / 256 < 4096 ? (work + 255) / 256 : 4096);
+            prefilled_kernel<<<grid, 256, 0, st>>>(s->zpre, nstreams, total, off, sg);
+            if (launch_status()) return -201;
+            off += seg[i].n;
+        }
+        return 0;
+    }
     Seg a[2] = {{0, nullptr, 0, nullptr, nullptr, nullptr}, {0, nullptr, 0, nullptr, nullptr, nullptr}};
     for (int i = 0; i < nseg && i < 2; i++)
         a[i] = Seg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};

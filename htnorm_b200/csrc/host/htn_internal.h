@@ -94,12 +94,15 @@ typedef struct {
     const uint64_t* seeds; /* device or NULL */
     uint64_t seed0;
     uint64_t* states;      /* device or NULL */
+    const double* zpre;    /* device or NULL: pre-drawn normals of a foreign generator */
 } htn_streams_t;
+void htn_foreign_draw(rng_t* rng, size_t n, double* z);
 
 int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int independent, unsigned flags,
                   size_t k2, size_t k, const double* mean, const double* cov, const double* g,
                   const double* r, int diag, double* out, int* d_info_out, int* first_info);
 int htn_ht_last_cov_failed(void);
+int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info);
 int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, size_t n, size_t p,
                   const double* mean, const double* a, const double* phi, const double* omega,
                   int struct_mean, int a_id, int o_id, double* out, int* d_info_out, int* first_info);

@@ -32,6 +32,7 @@ static void streams_view(const htn_streams_t* s, size_t offset, htnk_streams_t* 
     v->seeds = s->seeds ? s->seeds + offset : NULL;
     v->seed0 = s->seed0 + (uint64_t)offset;
     v->states = s->states ? s->states + 4 * offset : NULL;
+    v->zpre = s->zpre; /* single-draw use only (offset 0) */
 }
 
 /* k2 x k2 system (G cov G^T) for k2 > 16: D := (c0 - D) (L_s L_s^T)^-1 through the blocked TRSMs */
@@ -298,14 +299,24 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
         if (k <= SMALL_K_MAX && k2 <= SMALL_K2_MAX) {
             int* info_dev = d_info_out;
             int* tmp = NULL;
+            double* zs = NULL;
             if (!info_dev) {
                 HTN_TRY(htn_dalloc(ctx, (void**)&tmp, nsamples * sizeof(int)));
                 info_dev = tmp;
             }
-            htnk_streams_t sv;
-            streams_view(s, 0, &sv);
-            rc = htnk_ht_small_batched(ctx->stream, &sv, nsamples, (int)k, (int)k2, mean, cov, g, r, diag,
-                                       (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
+            /* every problem's normals first, one stream per thread (fully parallel), then one CTA per
+             * problem for the algebra */
+            rc = htn_dalloc(ctx, (void**)&zs, nsamples * k * sizeof(double));
+            if (!rc) {
+                htnk_streams_t sv;
+                streams_view(s, 0, &sv);
+                htnk_segment_t seg = {k, zs, k, NULL, NULL, NULL};
+                rc = htnk_normal_fill(ctx->stream, &sv, nsamples, 1, &seg, NULL);
+            }
+            if (!rc)
+                rc = htnk_ht_small_batched(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, diag,
+                                           (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
+            htn_dfree(ctx, zs);
             htn_dfree(ctx, tmp);
             *first_info = 0; /* per-problem codes live in the device array */
             return rc;
@@ -316,6 +327,7 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
             si.seeds = s->seeds ? s->seeds + i : NULL;
             si.seed0 = s->seed0 + i;
             si.states = s->states ? s->states + 4 * i : NULL;
+            si.zpre = NULL;
             int fi = 0;
             rc = htn_ht_device(ctx, &si, 1, 0, flags, k2, k, mean + i * k, cov + i * k * k, g + i * k2 * k,
                                r + i * k2, diag, out + i * k, NULL, &fi);
@@ -330,6 +342,31 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
         rc = ht_shared_dense(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
     if (!rc && d_info_out) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
 done:
+    return rc;
+}
+
+/* LAPACK status of chol(cov) alone (used to decide whether a foreign generator may be advanced) */
+int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info)
+{
+    int rc = 0;
+    const size_t kp = htn_round_up((size_t)k, 16);
+    double* F = NULL;
+    int* d_info = NULL;
+    htn_factor_t fa;
+    memset(&fa, 0, sizeof(fa));
+    HTN_TRY(htn_dalloc(ctx, (void**)&F, (size_t)k * kp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&d_info, sizeof(int)));
+    HTN_CUDA(cudaMemsetAsync(F, 0, (size_t)k * kp * 8, ctx->stream));
+    HTN_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+    HTN_TRY(htnk_sym_expand(ctx->stream, cov, (size_t)k, k, 0, NULL, 0, F, kp));
+    HTN_TRY(htn_factor_init(ctx, &fa, F, kp, k, 0));
+    HTN_TRY(htn_potrf(ctx, &fa, d_info));
+    HTN_CUDA(cudaMemcpyAsync(info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HTN_CUDA(cudaStreamSynchronize(ctx->stream));
+done:
+    htn_factor_free(ctx, &fa);
+    htn_dfree(ctx, d_info);
+    htn_dfree(ctx, F);
     return rc;
 }
 
@@ -356,7 +393,7 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, b->mem == HTN_MEM_HOST);
     if (rc) return rc;
     int first = 0;
-    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL};
+    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL, NULL};
     if (b->mem == HTN_MEM_DEVICE) {
         rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
                            conf->diag, out, info, &first);
@@ -423,35 +460,49 @@ int htn_hyperplane_truncated_mvn(rng_t* rng, const ht_config_t* conf, double* HT
         return HTN_E_ARG;
     }
     const int kind = htn_rng_kind(rng);
-    if (kind < 0) {
-        htn_set_error("rng_t was not created by rng_pcg64_new*/rng_xrs128p_new*: foreign generators "
-                      "cannot run on the device");
-        return HTN_E_FOREIGN_RNG;
-    }
     const size_t k = conf->gncol, k2 = conf->gnrow;
     htn_ctx_t ctx;
     int rc = htn_ctx_begin(&ctx, -1, NULL, 1);
     if (rc) return rc;
     int first = 0;
-    void *d_mean = NULL, *d_cov = NULL, *d_g = NULL, *d_r = NULL, *d_out = NULL, *d_state = NULL;
+    void *d_mean = NULL, *d_cov = NULL, *d_g = NULL, *d_r = NULL, *d_out = NULL, *d_state = NULL, *d_z = NULL;
+    double* h_z = NULL;
     uint64_t h_state[4] = {0, 0, 0, 0};
-    memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
+    if (kind >= 0) memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
     if (k == 0 || k2 == 0) { rc = HTN_E_ARG; goto done; }
     HTN_TRY(upload(&ctx, &d_mean, conf->mean, k * 8));
     HTN_TRY(upload(&ctx, &d_cov, conf->cov, k * k * 8));
     HTN_TRY(upload(&ctx, &d_g, conf->g, k2 * k * 8));
     HTN_TRY(upload(&ctx, &d_r, conf->r, k2 * 8));
-    HTN_TRY(upload(&ctx, &d_state, h_state, sizeof(h_state)));
     HTN_TRY(upload(&ctx, &d_out, out, k * 8)); /* a failed factorisation must leave out as it was */
-    {
-        htn_streams_t s = {kind, NULL, 0, (uint64_t*)d_state};
+    if (kind >= 0) {
+        HTN_TRY(upload(&ctx, &d_state, h_state, sizeof(h_state)));
+        htn_streams_t s = {kind, NULL, 0, (uint64_t*)d_state, NULL};
         HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, 0, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL, &first));
+    } else {
+        /* foreign generator: its callbacks run on the host.  The reference draws only after a
+         * successful factorisation (src/htnorm_distributions.c:78), so factorise first with no draw ... */
+        if (!conf->diag) {
+            HTN_TRY(htn_ht_cov_info(&ctx, (int)k, d_cov, &first));
+        }
+        if (first == 0) { /* ... then draw k normals through the callbacks and run the device path on them */
+            h_z = malloc(k * sizeof(double));
+            if (!h_z) { rc = HTNORM_ALLOC_ERROR; goto done; }
+            htn_foreign_draw(rng, k, h_z);
+            HTN_TRY(upload(&ctx, &d_z, h_z, k * 8));
+            htn_streams_t s = {0, NULL, 0, NULL, (const double*)d_z};
+            HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, 0, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL,
+                                  &first));
+        }
     }
     HTN_CUDA(cudaMemcpyAsync(out, d_out, k * 8, cudaMemcpyDeviceToHost, ctx.stream));
-    HTN_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(h_state), cudaMemcpyDeviceToHost, ctx.stream));
+    if (kind >= 0)
+        HTN_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(h_state), cudaMemcpyDeviceToHost, ctx.stream));
     HTN_CUDA(cudaStreamSynchronize(ctx.stream));
-    memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
+    if (kind >= 0) memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
 done:
+    free(h_z);
+    htn_dfree(&ctx, d_z);
     htn_dfree(&ctx, d_state);
     htn_dfree(&ctx, d_out);
     htn_dfree(&ctx, d_r);

@@ -14,6 +14,7 @@
  */
 #include "htn_internal.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 /* value of every double of the reference's IDENTITY "factor": memset(factor, 1, n * sizeof(double))
@@ -144,7 +145,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
         const int nb = (int)(nsamples - b0 < chunk ? nsamples - b0 : chunk);
         htnk_streams_t sv = {s->gen, s->seeds ? s->seeds + b0 : NULL, s->seed0 + (uint64_t)b0,
-                             s->states ? s->states + 4 * b0 : NULL};
+                             s->states ? s->states + 4 * b0 : NULL, s->zpre};
         htnk_segment_t seg[2] = {{(size_t)p, Z1, pp, a_id == DIAGONAL ? sda : NULL, NULL, NULL},
                                  {(size_t)n, Z2, np, o_id == DIAGONAL ? sdo : NULL, NULL, NULL}};
         if (h_info[1]) { /* Omega not PD: y1 was drawn (stream advanced), then the call fails (:246) */
@@ -204,7 +205,7 @@ done:
 
 /* host arrays -> device, run, -> host.  states_host (4 words) non-NULL: single draw continuing a generator */
 static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint64_t seed0, uint64_t* states_host,
-                   size_t B, unsigned flags, int device, double* out, int* info)
+                   size_t B, unsigned flags, int device, double* out, int* info, rng_t* foreign)
 {
     const size_t n = conf->pnrow, p = conf->pncol;
     htn_ctx_t ctx;
@@ -212,7 +213,8 @@ static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint
     if (rc) return rc;
     int first = 0;
     void *d_mean = NULL, *d_a = NULL, *d_phi = NULL, *d_om = NULL, *d_seeds = NULL, *d_out = NULL, *d_info = NULL,
-         *d_state = NULL;
+         *d_state = NULL, *d_z = NULL;
+    double* h_z = NULL;
     if (B == 0) goto done;
     if (n == 0 || p == 0 || !conf->mean || !conf->phi || !out) {
         htn_set_error("structured precision: empty or NULL input");
@@ -229,8 +231,24 @@ static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint
     if (states_host) HTN_TRY(upload(&ctx, &d_state, states_host, 32));
     HTN_TRY(upload(&ctx, &d_out, out, B * p * 8)); /* failed factorisations leave `out` as it was */
     HTN_TRY(htn_dalloc(&ctx, &d_info, B * sizeof(int)));
-    {
-        htn_streams_t s = {gen, (const uint64_t*)d_seeds, seed0, (uint64_t*)d_state};
+    if (foreign) {
+        /* foreign generator: the reference draws y1's normals only after chol(A) succeeded and
+         * y2's only after chol(omega) did (src/htnorm.c:245-246): check both, then draw on the host */
+        int ia = 0, io = 0;
+        if (conf->a_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)p, d_a, &ia));
+        if (ia) { first = ia; goto done; }
+        h_z = malloc((p + n) * sizeof(double));
+        if (!h_z) { rc = HTNORM_ALLOC_ERROR; goto done; }
+        htn_foreign_draw(foreign, p, h_z);
+        if (conf->o_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)n, d_om, &io));
+        if (io) { first = io; goto done; }
+        htn_foreign_draw(foreign, n, h_z + p);
+        HTN_TRY(upload(&ctx, &d_z, h_z, (p + n) * 8));
+        htn_streams_t s = {0, NULL, 0, NULL, (const double*)d_z};
+        HTN_TRY(htn_sp_device(&ctx, &s, 1, flags, n, p, d_mean, d_a, d_phi, d_om, conf->struct_mean, conf->a_id,
+                              conf->o_id, d_out, d_info, &first));
+    } else {
+        htn_streams_t s = {gen, (const uint64_t*)d_seeds, seed0, (uint64_t*)d_state, NULL};
         HTN_TRY(htn_sp_device(&ctx, &s, B, flags, n, p, d_mean, d_a, d_phi, d_om, conf->struct_mean, conf->a_id,
                               conf->o_id, d_out, d_info, &first));
     }
@@ -238,6 +256,8 @@ static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint
     HTN_CUDA(cudaMemcpyAsync(out, d_out, B * p * 8, cudaMemcpyDeviceToHost, ctx.stream));
     if (states_host) HTN_CUDA(cudaMemcpyAsync(states_host, d_state, 32, cudaMemcpyDeviceToHost, ctx.stream));
 done:
+    free(h_z);
+    htn_dfree(&ctx, d_z);
     htn_dfree(&ctx, d_state);
     htn_dfree(&ctx, d_info);
     htn_dfree(&ctx, d_out);
@@ -264,12 +284,12 @@ int htn_structured_precision_mvn_batch(const htn_batch_t* b, const sp_config_t* 
         return HTN_E_ARG;
     }
     if (b->mem == HTN_MEM_HOST)
-        return sp_host(conf, (int)b->gen, b->seeds, b->seed0, NULL, b->nsamples, b->flags, b->device, out, info);
+        return sp_host(conf, (int)b->gen, b->seeds, b->seed0, NULL, b->nsamples, b->flags, b->device, out, info, NULL);
     htn_ctx_t ctx;
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, 0);
     if (rc) return rc;
     int first = 0;
-    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL};
+    htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL, NULL};
     rc = htn_sp_device(&ctx, &s, b->nsamples, b->flags, conf->pnrow, conf->pncol, conf->mean, conf->a, conf->phi,
                        conf->omega, conf->struct_mean, conf->a_id, conf->o_id, out, info, &first);
     int rc2 = htn_ctx_end(&ctx, 0);
@@ -283,14 +303,11 @@ int htn_structured_precision_mvn(rng_t* rng, const sp_config_t* conf, double* HT
         return HTN_E_ARG;
     }
     const int kind = htn_rng_kind(rng);
-    if (kind < 0) {
-        htn_set_error("rng_t was not created by rng_pcg64_new*/rng_xrs128p_new*: foreign generators "
-                      "cannot run on the device");
-        return HTN_E_FOREIGN_RNG;
-    }
+    if (kind < 0) /* foreign generator: host draws through its callbacks, device algebra */
+        return sp_host(conf, 0, NULL, 0, NULL, 1, 0, -1, out, NULL, rng);
     uint64_t h_state[4] = {0, 0, 0, 0};
     memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
-    int rc = sp_host(conf, kind, NULL, 0, h_state, 1, 0, -1, out, NULL);
+    int rc = sp_host(conf, kind, NULL, 0, h_state, 1, 0, -1, out, NULL, NULL);
     if (rc >= 0 || rc == HTNORM_ALLOC_ERROR) memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
     return rc;
 }

@@ -234,9 +234,45 @@ def test_single_sample_api_advances_generator(h, oracle):
     d = h.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"], random_state=6)
     assert np.array_equal(a, b) and not np.allclose(a, d)
     s = cases.sp_case("nn_plain")
-    y = h.structured_precision_mvnorm(s["mean"], s["a"], s["phi"], s["omega"], random_state=9)
+    y = h.structured_precision_mvnorm(s["mean"], s["a"], s["phi"], s["omega"], random_state=h.HTNGenerator(9))
     yo = oracle.structured("pcg64", 1, s["mean"], s["a"], s["phi"], s["omega"], seed0=9)[0]
     assert rel_err(y[None], yo) < REL_TOL
+
+
+def test_numpy_generator_through_rng_t_callbacks(h):
+    """A foreign rng_t (NumPy's bit generator, as the reference's Cython wrapper passes it,
+    pyhtnorm/_htnorm.pyx:116-122).  SURVEY 8c secondary oracle: with mean 0 and a unit diagonal covariance
+    the reference's normals are Generator.standard_normal(n)[::-1] bit for bit - NumPy's ziggurat IS the
+    reference's; the projection with G = 1^T then gives z - mean(z)."""
+    n = 257
+    z = np.random.default_rng(2024).standard_normal(n)[::-1]
+    x = h.hyperplane_truncated_mvnorm(np.zeros(n), np.eye(n), np.ones((1, n)), np.zeros(1), diag=True,
+                                      random_state=2024)
+    assert np.abs(x - (z - z.mean())).max() < 1e-13
+    xd = h.hyperplane_truncated_mvnorm(np.zeros(n), np.eye(n), np.ones((1, n)), np.zeros(1), diag=False,
+                                       random_state=2024)
+    assert np.abs(xd - x).max() < 1e-12
+    # the generator object is advanced exactly by the draws made: two calls == one stream of 2n normals
+    g = np.random.default_rng(7)
+    a = h.hyperplane_truncated_mvnorm(np.zeros(n), np.eye(n), np.ones((1, n)), np.ones(1) * n, diag=True,
+                                      random_state=g)
+    b = h.hyperplane_truncated_mvnorm(np.zeros(n), np.eye(n), np.ones((1, n)), np.ones(1) * n, diag=True,
+                                      random_state=g)
+    zz = np.random.default_rng(7).standard_normal(2 * n)
+    za, zb = zz[:n][::-1], zz[n:][::-1]
+    assert np.abs(a - (za - za.mean() + 1)).max() < 1e-12 and np.abs(b - (zb - zb.mean() + 1)).max() < 1e-12
+    # structured precision with identity A, identity-like Omega quirk aside: A = I, Omega diagonal
+    p_, n_ = 40, 6
+    rng = np.random.default_rng(1)
+    phi = rng.standard_normal((n_, p_)) / np.sqrt(p_)
+    om = np.diag(rng.random(n_) + 0.5)
+    mu = rng.standard_normal(p_)
+    y = h.structured_precision_mvnorm(mu, np.eye(p_), phi, om, a_type=2, o_type=1, random_state=5)
+    zz = np.random.default_rng(5).standard_normal(p_ + n_)
+    y1, y2 = zz[:p_][::-1], zz[p_:][::-1] / np.sqrt(np.diag(om))
+    m = np.diag(1 / np.diag(om)) + phi @ phi.T
+    want = mu + y1 + phi.T @ np.linalg.solve(m, phi @ y1 + y2)     # reference sign (SURVEY Q1)
+    assert np.abs(y - want).max() < 1e-11
 
 
 def test_reference_properties_on_device(h):
