@@ -39,7 +39,8 @@ def make_inputs(np):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), time-stamped by arrival so that the
+    samples that fall inside the timed region can be picked out."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -50,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -58,23 +59,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count_since(self, t0):
+        return sum(1 for t, _ in self.rows if t >= t0)
+
+    def stop(self, t0, t1, note=None):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) > 8]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[1]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[2]) for r in rows) if v is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        load = [s for s in sm if s > 0.5 * (mx[0] if mx else 1)] or sm
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_run(nsamples, nthreads, seed0=12345):
@@ -180,7 +191,11 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HTN_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()          # nvidia-smi needs ~1 s to deliver its first sample
 
     B = args.batch                      # per GPU: weak scaling, the batch shards naturally
     mean, cov, g, r = make_inputs(np)
@@ -202,14 +217,12 @@ def main():
     barrier()
     # ---- timed: device-resident inputs ----
     h.phase_timing(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gemm_ms = []
     phases = []
     barrier()
+    t_wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
@@ -217,9 +230,27 @@ def main():
     e1.record()
     barrier()
     launches = h.launch_count() - launches0
+    t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     h.phase_timing(False)
+    clk = None
+    if rank == 0:
+        note = None
+        if clocks.count_since(t_wall0) < 3 and clocks.proc is not None:
+            # the timed region is shorter than the sampler's period: keep the SAME steps running (untimed)
+            # until a few samples have arrived, and report those
+            note = ("timed region (%.0f ms) shorter than the nvidia-smi sampling period; clocks sampled over an "
+                    "identical untimed continuation of the same steps" % ms_total)
+            t_probe = time.perf_counter()
+            i = 0
+            while clocks.count_since(t_probe) < 6 and time.perf_counter() - t_probe < 4.0:
+                step(args.warmup + args.steps + i)
+                i += 1
+                if i % 8 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            t_wall0, t_wall1 = t_probe, time.perf_counter()
+        clk = clocks.stop(t_wall0, t_wall1, note)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

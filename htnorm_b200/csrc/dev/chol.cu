@@ -8,8 +8,6 @@
 // Pivot rule: fail on `ajj <= 0` only - NaN passes and propagates with info = 0, as the reference +
 // OpenBLAS do (reference tests/test_pyhtnorm.py:46-48, 91-95).
 //
-// One CTA of 512 threads, the block in REGISTERS (32 per thread, one owner per element): a column costs
-// one barrier + one fast rsqrt + the owner-local rank-1 update.
 #include <cuda_runtime.h>
 
 #include "launchers.h"
@@ -35,111 +33,141 @@ __device__ __forceinline__ double fast_rsqrt(double x)
     return y;
 }
 
-// Thread (i = tid / 4, cq = tid % 4) OWNS the elements (i, c), c == cq (mod 4), and keeps them in 32
-// REGISTERS used as a ROTATING window: during column group jj (columns 4jj .. 4jj+3) R[u] holds the
-// element of column cq + 4 (jj + u); after the group R[0] is final and the window shifts by one, so the
-// loop body is identical for every group (a fully unrolled 128-column version measured I-cache bound).
-//
-// Step j is software-pipelined around ONE barrier:
-//   urgent : pivot rsqrt (redundantly in every thread), then the owners of column j+1 apply step j to
-//            that column only and publish it (unscaled) to shared memory        -> barrier
-//   lazy   : the rest of the rank-1 update of step j runs after the barrier, i.e. in the shadow of the
-//            other warps' next urgent part.
-// The published columns rotate through three buffers (a warp still in lazy(j) reads column j while
-// column j+2 is being published).  No per-element predicates: updates that fall above the diagonal or
-// beyond the block land in registers / zero padding that are never read.
+// potf2: the 128 x 128 block is factorised in 16 column panels of width 8.
+//   panel   : threads 0..127 (thread = row) each read the 8 x 8 diagonal sub-block and factor it LOCALLY in
+//             registers (redundantly - no communication on the 8-pivot chain), then solve their own row of
+//             the panel against it (28 FMAs) and publish the row (final L) to shared memory;
+//   update  : the trailing lower triangle gets its rank-8 update on the tensor cores: every 8 x 8 tile is
+//             two DMMAs (m8n8k4) on fragments read straight from the published panel; warp w owns tile row
+//             b + 1 + w.
+// Two barriers per panel, i.e. 32 per block instead of one per column; the pivot chain (128 dependent
+// rsqrt + a few FMAs each) is all that remains serial.
+__device__ __forceinline__ void dmma_sub(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int LDP = 12;  // panel row stride (doubles): 8 + 4 keeps the DMMA fragment reads conflict-free
+
 __global__ void __launch_bounds__(NT, 1)
 potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ rdiag_out,
              int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    double* S = sm;                  // [NB][LDB]  staging for the coalesced load / store
-    double* colbuf = sm + NB * LDB;  // [3][2 * NB] published columns, second half stays zero
-    double* rdiag = colbuf + 6 * NB; // [NB]       1 / L[j][j]
-    const int tid = threadIdx.x;
-    const int i = tid >> 2, cq = tid & 3;
+    double* S = sm;                  // [NB][LDB]  the block (lower triangle meaningful)
+    double* P = sm + NB * LDB;       // [NB][LDP]  current panel: L[:, 8b .. 8b+7]
+    double* rdiag = P + NB * LDP;    // [NB]       1 / L[j][j]
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int idx = tid; idx < NB * NB; idx += NT) {
         int r = idx >> 7, c = idx & (NB - 1);
         S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : 0.0;
     }
-    for (int idx = tid; idx < 6 * NB; idx += NT) colbuf[idx] = 0.0;
-    __syncthreads();
-    double R[32];
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) R[jj] = S[i * LDB + cq + 4 * jj];
-    if (cq == 0) colbuf[i] = R[0];  // column 0
+    for (int idx = tid; idx < NB * LDP; idx += NT) P[idx] = 0.0;
+    if (tid == 0) s_fail = 0;
     __syncthreads();
 
+    const int npanels = (nb + 7) >> 3;
     int nfact = nb;
-    int bj = 0;  // buffer that holds column j
-    const int ngroups = (nb + 3) >> 2;
-    for (int jj = 0; jj < ngroups; jj++) {
-        const int c0 = cq + 4 * jj;  // the column this thread retires in this group
+    for (int b = 0; b < npanels; b++) {
+        const int j0 = 8 * b;
+        if (tid < NB) {
+            // ---- local Cholesky of the 8 x 8 diagonal sub-block (identical in every thread) ----
+            double l[8][8];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = 4 * jj + q;
-            if (j < nb && nfact == nb) {  // uniform
-                const double* col = colbuf + bj * 2 * NB;
-                const int bn = bj == 2 ? 0 : bj + 1;
-                double* coln = colbuf + bn * 2 * NB;
-                const double ajj = col[j];
-                double m = 0.0, aij = 0.0, rinv = 0.0;
-                const bool ok = !(ajj <= 0.0);  // uniform; NaN passes
-                if (ok) {
-                    rinv = fast_rsqrt(ajj);
-                    if (i > j) {
-                        aij = col[i];
-                        m = aij * (rinv * rinv);
-                        // urgent: column j+1 (register R[0] of the thread cq == q+1, or R[1] of cq == 0)
-                        if (q < 3) {
-                            if (cq == q + 1) { R[0] = fma(-m, col[j + 1], R[0]); coln[i] = R[0]; }
-                        } else {
-                            if (cq == 0) { R[1] = fma(-m, col[j + 1], R[1]); coln[i] = R[1]; }
-                        }
-                    }
-                } else {
-                    if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
-                    nfact = j;
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) l[r][c] = (c <= r) ? S[(j0 + r) * LDB + j0 + c] : 0.0;
+            double ri[8];
+            int bad = -1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double ajj = l[j][j];
+                // columns beyond nb (partial last panel) are padding: treat them as the identity
+                if (j0 + j >= nb) ajj = 1.0;
+                if (ajj <= 0.0 && bad < 0) bad = j;  // NaN passes
+                const double rinv = fast_rsqrt(ajj);
+                ri[j] = rinv;
+                double d = ajj * rinv;
+                d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
+                l[j][j] = d;
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (r > j) l[r][j] *= rinv;
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int c = 0; c < 8; c++)
+                        if (r > j && c > j && c <= r) l[r][c] = fma(-l[r][j], l[c][j], l[r][c]);
+            }
+            if (bad >= 0) {  // uniform over the 128 threads: every one factored the same block
+                if (tid == 0) {
+                    atomicCAS(info, 0, col0 + j0 + bad + 1);
+                    s_fail = j0 + bad + 1;
                 }
-                __syncthreads();
-                if (ok) {
-                    if (i > j) {
-                        // lazy: every other owned column > j+1
-                        if (cq > q + 1) R[0] = fma(-m, col[c0], R[0]);
-                        if (!(q == 3 && cq == 0)) R[1] = fma(-m, col[c0 + 4], R[1]);
+            } else {
+                // ---- my row of the panel: x = a L11^-T (rows below), or L11's own row (diagonal rows) ----
+                const int r = tid;
+                if (r >= j0 && r < nb) {
+                    double x[8];
 #pragma unroll
-                        for (int u = 2; u < 8; u++) R[u] = fma(-m, col[c0 + 4 * u], R[u]);
+                    for (int c = 0; c < 8; c++) x[c] = S[r * LDB + j0 + c];
 #pragma unroll
-                        for (int ub = 1; ub < 4; ub++) {
-                            if (jj + 8 * ub < 32) {  // uniform: later columns do not exist
+                    for (int c = 0; c < 8; c++) {
+                        double v = x[c];
 #pragma unroll
-                                for (int u = 8 * ub; u < 8 * ub + 8; u++) R[u] = fma(-m, col[c0 + 4 * u], R[u]);
-                            }
-                        }
-                        if (cq == q) R[0] = aij * rinv;  // L[i][j]
-                    } else if (i == j && cq == q) {
-                        double d = ajj * rinv;  // sqrt(ajj), one Heron correction
-                        d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
-                        R[0] = d;
+                        for (int t = 0; t < 8; t++)
+                            if (t < c) v = fma(-x[t], l[c][t], v);
+                        const double vraw = v, ric = ri[c];
+                        v *= ric;
+                        // a diagonal row's own entry is the pivot (sqrt with one Heron step); nothing above it
+                        const double piv = fma(fma(-v, v, vraw), 0.5 * ric, v);
+                        const int dr = r - j0;
+                        v = (dr == c) ? piv : ((dr < c) ? 0.0 : v);
+                        if (j0 + c >= nb) v = 0.0;
+                        x[c] = v;
                     }
-                    if (tid == 0) rdiag[j] = rinv;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        S[r * LDB + j0 + c] = x[c];
+                        P[r * LDP + c] = x[c];
+                    }
                 }
-                bj = bn;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (tid == j && j0 + j < nb) rdiag[j0 + j] = ri[j];
             }
         }
-        // retire column c0: L[i][c0] (zeros above the diagonal / beyond a failed column)
-        S[i * LDB + c0] = (c0 <= i && c0 < nfact) ? R[0] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 31; u++) R[u] = R[u + 1];
-        R[31] = 0.0;
+        __syncthreads();
+        if (s_fail) { nfact = s_fail - 1; break; }
+        // ---- rank-8 update of the trailing lower triangle on the tensor cores ----
+        {
+            const int tr = b + 1 + warp;  // this warp's tile row
+            if (tr < npanels) {
+                const int g = lane >> 2, t4 = lane & 3;
+                const double a0 = -P[(tr * 8 + g) * LDP + t4];
+                const double a1 = -P[(tr * 8 + g) * LDP + 4 + t4];
+                for (int tc = b + 1; tc <= tr; tc++) {
+                    const double b0 = P[(tc * 8 + g) * LDP + t4];
+                    const double b1 = P[(tc * 8 + g) * LDP + 4 + t4];
+                    double2* cp = reinterpret_cast<double2*>(&S[(tr * 8 + g) * LDB + tc * 8 + 2 * t4]);
+                    double2 c = *cp;
+                    dmma_sub(c.x, c.y, a0, b0);
+                    dmma_sub(c.x, c.y, a1, b1);
+                    *cp = c;
+                }
+            }
+        }
+        __syncthreads();
     }
     const bool failed = nfact < nb;
-    for (int c = cq + 4 * ngroups; c < NB; c += 4) S[i * LDB + c] = 0.0;
-    __syncthreads();
+    // write L back: lower triangle, zeros above; nothing beyond a failed column is meaningful
     for (int idx = tid; idx < nb * nb; idx += NT) {
         int r = idx / nb, c = idx - r * nb;
-        a[(size_t)r * ld + c] = S[r * LDB + c];
+        a[(size_t)r * ld + c] = (c <= r && c < ((nfact + 7) & ~7)) ? S[r * LDB + c] : 0.0;
     }
     if (rdiag_out != nullptr && !failed)
         for (int c = tid; c < nb; c += NT) rdiag_out[c] = rdiag[c];
@@ -266,7 +294,7 @@ extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col
 {
     if (nb <= 0) return 0;
     if (nb > NB) return -202;
-    const size_t smem = (size_t)(NB * LDB + 7 * NB) * sizeof(double);
+    const size_t smem = (size_t)(NB * LDB + NB * LDP + NB) * sizeof(double);
     if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     potf2_kernel<<<1, NT, smem, st>>>(a, ld, nb, col0, rdiag, info);

@@ -73,7 +73,8 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     int* d_info = NULL;
     /* the generator runs on a side stream: it needs nothing from the factorisation, so chunk 0's normals
      * are drawn WHILE cov is being factorised, and chunk c+1's while chunk c is in the sampling GEMM */
-    cudaStream_t side = NULL;
+    cudaStream_t side = NULL, side2 = NULL; /* side2: the G cov G^T branch, independent of chol(cov) */
+    cudaEvent_t ev_sym = NULL, ev_sbranch = NULL;
     cudaEvent_t ev_fork = NULL, ev_rng[2] = {NULL, NULL}, ev_gemm[2] = {NULL, NULL};
     int rng_pending = -1; /* buffer whose generator launch the main stream has not yet waited for */
     htn_factor_t fa, fs;
@@ -106,7 +107,10 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     if (nchunks > 1) HTN_TRY(htn_dalloc(ctx, (void**)&Z[1], chunk * ldz * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
     HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    HTN_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_sym, cudaEventDisableTiming));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_sbranch, cudaEventDisableTiming));
     for (int e = 0; e < 2; e++) {
         HTN_CUDA(cudaEventCreateWithFlags(&ev_rng[e], cudaEventDisableTiming));
         HTN_CUDA(cudaEventCreateWithFlags(&ev_gemm[e], cudaEventDisableTiming));
@@ -121,27 +125,39 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
     /* symmetric copy of cov (as the reference's uplo='L' calls see it) and its lower triangle in F */
     HTN_TRY(htnk_sym_expand(st, cov, (size_t)k, k, lower_src, Sfull, kp, F, ldz));
-    HTN_TRY(htn_factor_init(ctx, &fa, F, ldz, k, 0));
-    HTN_TRY(htn_potrf(ctx, &fa, d_info)); /* dpotrf: src/htnorm_distributions.c:77 */
     if (flags & HTN_FLAG_COLMAJOR) /* g is k2 x k column-major = k x k2 row-major */
         HTN_TRY(htnk_transpose(st, g, (size_t)k2, k, k2, Gp, kp));
     else
         HTN_TRY(htnk_copy2d(st, g, (size_t)k, k2, k, Gp, kp, NULL));
-    /* cov G^T -> F[:, kp : kp+k2]   (dsymm, src/htnorm.c:154; dsymv :73) */
-    HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, F + kp, ldz, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-    HTN_TRY(htnk_transpose(st, F + kp, ldz, k, k2, CG, kp));
+    HTN_CUDA(cudaEventRecord(ev_sym, st));
+    /* ---- branch on side2 (needs cov and G only, runs under the factorisation): cov G^T, G cov G^T and
+     * its Cholesky, r - G mean ---- */
+    HTN_CUDA(cudaStreamWaitEvent(side2, ev_sym, 0));
+    /* cov G^T -> F[:, kp : kp+k2]   (dsymm, src/htnorm.c:154; dsymv :73).  Disjoint from L's columns. */
+    HTN_TRY(htnk_gemm_tn(side2, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, F + kp, ldz, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    HTN_TRY(htnk_transpose(side2, F + kp, ldz, k, k2, CG, kp));
     /* G cov G^T   (dgemm TN, src/htnorm.c:164; ddot :77) */
-    HTN_TRY(htnk_gemm_tn(st, k2, k2, k, 1.0, Gp, kp, CG, kp, 0.0, Sm, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-    if (k2 > 1) { /* dposv's factorisation, src/htnorm.c:169; k2 == 1 divides by the scalar (:77) */
-        HTN_TRY(htn_factor_init(ctx, &fs, Sm, k2p, k2, k2 > ALPHA_K2_MAX));
-        HTN_TRY(htn_potrf(ctx, &fs, d_info + 1));
-        if (k2 > ALPHA_K2_MAX) HTN_TRY(htn_factor_make_u(ctx, &fs));
+    HTN_TRY(htnk_gemm_tn(side2, k2, k2, k, 1.0, Gp, kp, CG, kp, 0.0, Sm, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    HTN_TRY(htnk_r_minus_gmean(side2, Gp, kp, k2, k, mean, r, c0));
+    {
+        htn_ctx_t c2 = *ctx; /* same device, the branch's stream */
+        c2.stream = side2;
+        if (k2 > 1) { /* dposv's factorisation, src/htnorm.c:169; k2 == 1 divides by the scalar (:77) */
+            HTN_TRY(htn_factor_init(&c2, &fs, Sm, k2p, k2, k2 > ALPHA_K2_MAX));
+            HTN_TRY(htn_potrf(&c2, &fs, d_info + 1));
+            if (k2 > ALPHA_K2_MAX) HTN_TRY(htn_factor_make_u(&c2, &fs));
+        }
     }
+    HTN_CUDA(cudaEventRecord(ev_sbranch, side2));
+    /* ---- main stream: chol(cov)  (dpotrf, src/htnorm_distributions.c:77) ---- */
+    HTN_TRY(htn_factor_init(ctx, &fa, F, ldz, k, 0));
+    HTN_TRY(htn_potrf(ctx, &fa, d_info));
+    /* join the G cov G^T branch (it reads Sfull, which is recycled next) */
+    HTN_CUDA(cudaStreamWaitEvent(st, ev_sbranch, 0));
     /* W = G L  via  W^T = L^T G^T  (L^T parked in the Sfull buffer, free from here on) */
     HTN_TRY(htnk_transpose(st, F, ldz, k, k, Sfull, kp));
     HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, WT, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
     HTN_TRY(htnk_transpose(st, WT, k2p, k, k2, W, kp));
-    HTN_TRY(htnk_r_minus_gmean(st, Gp, kp, k2, k, mean, r, c0));
 
     int h_info[2] = {0, 0};
     HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
@@ -195,7 +211,13 @@ done:
     htn_dfree(ctx, Z[0]);
     htn_dfree(ctx, Z[1]);
     htn_dfree(ctx, D);
+    if (ev_sbranch) { /* the branch may still be running if we bailed out early */
+        cudaStreamWaitEvent(st, ev_sbranch, 0);
+    }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_sym) cudaEventDestroy(ev_sym);
+    if (ev_sbranch) cudaEventDestroy(ev_sbranch);
+    if (side2) cudaStreamDestroy(side2);
     for (int e = 0; e < 2; e++) {
         if (ev_rng[e]) cudaEventDestroy(ev_rng[e]);
         if (ev_gemm[e]) cudaEventDestroy(ev_gemm[e]);
