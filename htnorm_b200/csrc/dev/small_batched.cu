@@ -12,8 +12,9 @@
 // parallel - a per-problem stream drawn inside this kernel would leave 127 threads waiting for one).
 //
 //   load cov (coalesced) and symmetrise it through the triangle the reference reads
-//   cov * G^T                               dsymm,  src/htnorm.c:154   (before the factor overwrites cov)
-//   Cholesky in smem, one owner thread per element, one barrier per column   dpotrf, distributions.c:77
+//   cov * G^T on the tensor cores (DMMA)    dsymm,  src/htnorm.c:154   (before the factor overwrites cov)
+//   Cholesky in 8-wide panels: local 8 x 8 factor + row solve per thread, DMMA rank-8 trailing update
+//                                           dpotrf, distributions.c:77
 //   y = mean + L z                          dtrmv + daxpy, distributions.c:81-83
 //   r - G y, G cov G^T, k2 x k2 solve       dgemm :132, :164, dposv :169
 //   x = y + cov G^T alpha                   dgemv :176
@@ -29,6 +30,21 @@ namespace {
 
 constexpr int NT = 128;
 constexpr int MAXK2 = 16;
+
+constexpr int LDP = 12;
+
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
 
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
@@ -49,124 +65,196 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
                 int diag, int lower_src, double* __restrict__ out, int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    const int ld = k + 2;                 // even pad: row-owner accesses (i, cq + 2u) are conflict-free
-    double* A = sm;                       // [k][ld]   cov, then its factor in the lower triangle
-    double* G = A + (size_t)k * ld;       // [k2][k]
-    double* CG = G + (size_t)k2 * k;      // [k2][k]   row c = cov * g[c]^T
-    double* z = CG + (size_t)k2 * k;      // [k]
-    double* y = z + k;                    // [k]
-    double* mu = y + k;                   // [k]
-    double* S2 = mu + k;                  // [MAXK2][MAXK2]
+    const int kpad = (k + 7) & ~7, ntiles = kpad >> 3;
+    const int ld = kpad + 4;              // 4 mod 16: DMMA A-fragment reads of the rows are conflict-free
+    const int ldg = kpad + 4;
+    const int k2p = (k2 + 7) & ~7;        // G rows / CG row stride, padded to the 8-wide DMMA tile
+    double* A = sm;                       // [kpad][ld]   cov, then its factor in the lower triangle
+    double* G = A + (size_t)kpad * ld;    // [k2p][ldg] zero-padded rows / columns
+    double* CG = G + (size_t)k2p * ldg;   // [kpad][k2p] row i = (cov * G^T)[i][:]
+    double* P = CG + (size_t)kpad * k2p;  // [kpad][LDP]  current panel of L
+    double* z = P + (size_t)kpad * LDP;   // [kpad]
+    double* y = z + kpad;                 // [kpad]
+    double* mu = y + kpad;                // [kpad]
+    double* S2 = mu + kpad;               // [MAXK2][MAXK2]
     double* gy = S2 + MAXK2 * MAXK2;      // [MAXK2]
     __shared__ int s_fail, s_info2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tpr = NT / k >= 2 ? 2 : 1;  // threads per row in the factorisation (2 for k <= 64)
-    const int row = tid / tpr, cq = tid % tpr;
+    // zero everything once: padding rows / columns must stay zero for the tensor-core tiles
+    for (int idx = tid; idx < kpad * ld + k2p * ldg + kpad * k2p + kpad * LDP + 3 * kpad; idx += NT) sm[idx] = 0.0;
+    __syncthreads();
 
     for (size_t pb = blockIdx.x; pb < nproblems; pb += gridDim.x) {
         const double* covp = cov + pb * (size_t)k * k;
         const double* gp = gm + pb * (size_t)k2 * k;
         // ---- stage inputs (coalesced) ----
-        for (int idx = tid; idx < k * k; idx += NT) {
-            int i = idx / k, j = idx - i * k;
-            A[i * ld + j] = covp[idx];
+        // asynchronous 8-byte copies global -> shared (LDGSTS): every element of the problem is in flight at
+        // once instead of 32 dependent load -> store round trips per thread
+        for (int i = warp; i < k; i += NT / 32) {  // one row per warp: 32 lanes x consecutive doubles
+            const double* src = covp + (size_t)i * k;
+            for (int j = lane; j < k; j += 32) cp_async8(&A[i * ld + j], src + j);
         }
-        for (int idx = tid; idx < k2 * k; idx += NT) G[idx] = gp[idx];
+        for (int c = warp; c < k2; c += NT / 32)
+            for (int j = lane; j < k; j += 32) cp_async8(&G[c * ldg + j], gp + (size_t)c * k + j);
         for (int i = tid; i < k; i += NT) {
-            mu[i] = mean[pb * (size_t)k + i];
-            z[i] = zs[pb * (size_t)k + i];
+            cp_async8(&mu[i], mean + pb * (size_t)k + i);
+            cp_async8(&z[i], zs + pb * (size_t)k + i);
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
         if (tid == 0) { s_fail = 0; s_info2 = 0; }
         __syncthreads();
         if (!diag) {  // symmetrise through the triangle the reference reads
-            for (int idx = tid; idx < k * k; idx += NT) {
-                int i = idx / k, j = idx - i * k;
-                bool keep = lower_src ? (j <= i) : (j >= i);
-                if (!keep) A[i * ld + j] = A[j * ld + i];
-            }
+            for (int i = warp; i < k; i += NT / 32)
+                for (int j = lane; j < k; j += 32) {
+                    const bool keep = lower_src ? (j <= i) : (j >= i);
+                    if (!keep) A[i * ld + j] = A[j * ld + i];
+                }
             __syncthreads();
         }
         // ---- cov * G^T (before the factorisation overwrites the lower triangle) ----
-        for (int idx = tid; idx < k2 * k; idx += NT) {
-            int c = idx / k, i = idx - c * k;
-            double acc = 0.0;
-            if (diag) {
-                acc = A[i * ld + i] * G[c * k + i];
-            } else {
-                const double* ai = A + i * ld;
-                const double* gc = G + c * k;
-#pragma unroll 8
-                for (int j = 0; j < k; j++) acc = fma(ai[j], gc[j], acc);
+        if (diag) {
+            for (int idx = tid; idx < k2 * k; idx += NT) {
+                int c = idx / k, i = idx - c * k;
+                CG[i * k2p + c] = A[i * ld + i] * G[c * ldg + i];
             }
-            CG[idx] = acc;
+        } else {
+            // tensor cores: CG (k x k2) = cov (k x k) * G^T; warp w owns 8-row tiles w, w+4, ...
+            const int g = lane >> 2, t4 = lane & 3;
+            for (int tr = warp; tr < ntiles; tr += NT / 32) {
+                for (int tc = 0; tc < (k2 + 7) / 8; tc++) {
+                    double c0 = 0.0, c1 = 0.0;
+                    const double* ar = A + (tr * 8 + g) * ld + t4;
+                    const double* gr = G + (tc * 8 + g) * ldg + t4;
+                    for (int kk = 0; kk < kpad; kk += 4) dmma_acc(c0, c1, ar[kk], gr[kk]);
+                    CG[(tr * 8 + g) * k2p + tc * 8 + 2 * t4] = c0;
+                    CG[(tr * 8 + g) * k2p + tc * 8 + 2 * t4 + 1] = c1;
+                }
+            }
         }
         __syncthreads();
-        // ---- Cholesky: thread (row, cq) owns A[row][c], c == cq (mod tpr); one barrier per column ----
+        // ---- Cholesky in 8-wide panels: thread = row factors the 8 x 8 diagonal block locally and solves its
+        // own panel row; the trailing lower triangle gets its rank-8 update by DMMA (see chol.cu:potf2) ----
         if (!diag) {
-            for (int j = 0; j < k; j++) {
-                const double ajj = A[j * ld + j];
-                if (ajj <= 0.0) {  // uniform; NaN passes
-                    if (tid == 0) s_fail = j + 1;
-                    break;
+            const int g = lane >> 2, t4 = lane & 3;
+            for (int b = 0; b < ntiles; b++) {
+                const int j0 = 8 * b;
+                if (tid >= j0 && tid < kpad) {
+                    double l[8][8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+#pragma unroll
+                        for (int c = 0; c < 8; c++) l[r][c] = (c <= r) ? A[(j0 + r) * ld + j0 + c] : 0.0;
+                    double ri[8];
+                    int bad = -1;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        double ajj = l[j][j];
+                        if (j0 + j >= k) ajj = 1.0;  // padding columns of the last panel
+                        if (ajj <= 0.0 && bad < 0) bad = j;  // NaN passes
+                        const double rinv = fast_rsqrt(ajj);
+                        ri[j] = rinv;
+#pragma unroll
+                        for (int r = 0; r < 8; r++)
+                            if (r > j) l[r][j] *= rinv;
+#pragma unroll
+                        for (int r = 0; r < 8; r++)
+#pragma unroll
+                            for (int c = 0; c < 8; c++)
+                                if (r > j && c > j && c <= r) l[r][c] = fma(-l[r][j], l[c][j], l[r][c]);
+                    }
+                    if (bad >= 0) {
+                        if (tid == j0) s_fail = j0 + bad + 1;  // every participating thread sees the same block
+                    } else {
+                        const int r = tid;
+                        double x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) x[c] = A[r * ld + j0 + c];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            double v = x[c];
+#pragma unroll
+                            for (int t = 0; t < 8; t++)
+                                if (t < c) v = fma(-x[t], l[c][t], v);
+                            const double vraw = v, ric = ri[c];
+                            v *= ric;
+                            const double piv = fma(fma(-v, v, vraw), 0.5 * ric, v);
+                            const int dr = r - j0;
+                            v = (dr == c) ? piv : ((dr < c) ? 0.0 : v);
+                            if (j0 + c >= k || r >= k) v = 0.0;
+                            x[c] = v;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            A[r * ld + j0 + c] = x[c];
+                            P[r * LDP + c] = x[c];
+                        }
+                    }
                 }
-                const double rinv = fast_rsqrt(ajj);
-                if (row > j && row < k) {
-                    const double aij = A[row * ld + j];
-                    const double m = aij * (rinv * rinv);
-                    int c = cq + tpr * ((j + 1 - cq + tpr - 1) / tpr);  // first owned column > j
-                    double* ar = A + row * ld;
-#pragma unroll 4
-                    for (; c <= row; c += tpr) ar[c] = fma(-m, A[c * ld + j], ar[c]);
-                    if (cq == (j % tpr)) A[j * ld + row] = aij * rinv;  // L[row][j] parked above the diagonal
-                } else if (row == j && cq == (j % tpr)) {
-                    double d = ajj * rinv;
-                    d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
-                    y[j] = d;  // diagonal of L (y is free until the triangular product)
+                __syncthreads();
+                if (s_fail) break;
+                for (int tr = b + 1 + warp; tr < ntiles; tr += NT / 32) {
+                    const double a0 = -P[(tr * 8 + g) * LDP + t4];
+                    const double a1 = -P[(tr * 8 + g) * LDP + 4 + t4];
+#pragma unroll 2
+                    for (int tc = b + 1; tc <= tr; tc++) {
+                        const double b0 = P[(tc * 8 + g) * LDP + t4];
+                        const double b1 = P[(tc * 8 + g) * LDP + 4 + t4];
+                        double2* cp = reinterpret_cast<double2*>(&A[(tr * 8 + g) * ld + tc * 8 + 2 * t4]);
+                        double2 c = *cp;
+                        dmma_acc(c.x, c.y, a0, b0);
+                        dmma_acc(c.x, c.y, a1, b1);
+                        *cp = c;
+                    }
                 }
                 __syncthreads();
             }
-            __syncthreads();
             if (s_fail) {  // reference returns before drawing (src/htnorm_distributions.c:78); out untouched
                 if (tid == 0 && info) info[pb] = s_fail;
                 __syncthreads();
                 continue;
             }
-            // unpark: L[i][j] = A[j][i] for j < i, diagonal from y
-            for (int idx = tid; idx < k * k; idx += NT) {
-                int i = idx / k, j = idx - i * k;
-                if (j < i) A[i * ld + j] = A[j * ld + i];
-            }
-            __syncthreads();
-            if (tid < k) A[tid * ld + tid] = y[tid];
-            __syncthreads();
         }
         // ---- y = mean + L z   /   mean + sqrt(cov_ii) z ----
-        for (int i = tid; i < k; i += NT) {
-            double acc;
-            if (diag) {
-                acc = __dadd_rn(mu[i], __dmul_rn(sqrt(A[i * ld + i]), z[i]));
-            } else {
-                acc = 0.0;
-                const double* ai = A + i * ld;
-                for (int t = 0; t <= i; t++) acc = fma(ai[t], z[t], acc);
-                acc += mu[i];
+        if (diag) {
+            for (int i = tid; i < k; i += NT) y[i] = __dadd_rn(mu[i], __dmul_rn(sqrt(A[i * ld + i]), z[i]));
+        } else {
+            // triangular product on the tensor cores: z is column 0 of an (k x 8) right-hand side; the
+            // diagonal 8 x 8 blocks of A are clean lower triangles, blocks above the diagonal are not read
+            const int g = lane >> 2, t4 = lane & 3;
+            for (int tr = warp; tr < ntiles; tr += NT / 32) {
+                double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                const double* ar = A + (tr * 8 + g) * ld + t4;
+                for (int kk = 0; kk < 8 * (tr + 1); kk += 8) {
+                    dmma_acc(c0, c1, ar[kk], g == 0 ? z[kk + t4] : 0.0);
+                    dmma_acc(d0, d1, ar[kk + 4], g == 0 ? z[kk + 4 + t4] : 0.0);
+                }
+                if (t4 == 0 && tr * 8 + g < k) y[tr * 8 + g] = c0 + d0 + mu[tr * 8 + g];
             }
-            y[i] = acc;
         }
         __syncthreads();
         // ---- gy = r - G y  and  S2 = (cov G^T)^T G^T ----
         for (int c = warp; c < k2; c += NT / 32) {
             double acc = 0.0;
-            for (int i = lane; i < k; i += 32) acc = fma(G[c * k + i], y[i], acc);
+            for (int i = lane; i < k; i += 32) acc = fma(G[c * ldg + i], y[i], acc);
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) gy[c] = rv[pb * (size_t)k2 + c] - acc;
         }
-        for (int idx = tid; idx < k2 * k2; idx += NT) {
-            int a = idx / k2, c = idx - a * k2;
-            double acc = 0.0;
-            for (int i = 0; i < k; i++) acc = fma(CG[a * k + i], G[c * k + i], acc);
-            S2[a * MAXK2 + c] = acc;
+        if (warp == NT / 32 - 1) {  // S2 = G (cov G^T): 8 x 8 tiles on the tensor cores, the last warp's job
+            const int g = lane >> 2, t4 = lane & 3;
+            for (int ta = 0; ta < k2p / 8; ta++)
+                for (int tc = 0; tc < k2p / 8; tc++) {
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // two chains: even / odd k4 steps
+                    const double* ga = G + (ta * 8 + g) * ldg + t4;
+                    const double* cb = CG + t4 * k2p + tc * 8 + g;
+                    for (int kk = 0; kk < kpad; kk += 8) {
+                        dmma_acc(c0, c1, ga[kk], cb[kk * k2p]);
+                        dmma_acc(d0, d1, ga[kk + 4], cb[(kk + 4) * k2p]);
+                    }
+                    S2[(ta * 8 + g) * MAXK2 + tc * 8 + 2 * t4] = c0 + d0;
+                    S2[(ta * 8 + g) * MAXK2 + tc * 8 + 2 * t4 + 1] = c1 + d1;
+                }
         }
         __syncthreads();
         // ---- k2 x k2 solve by one thread (tiny) ----
@@ -210,7 +298,7 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
             double acc = y[i];
             if (!f2) {
                 double p = 0.0;
-                for (int c = 0; c < k2; c++) p = fma(CG[c * k + i], gy[c], p);
+                for (int c = 0; c < k2; c++) p = fma(CG[i * k2p + c], gy[c], p);
                 acc += p;
             }
             out[pb * (size_t)k + i] = acc;
@@ -228,7 +316,9 @@ extern "C" int htnk_ht_small_batched(cudaStream_t st, size_t nproblems, int k, i
 {
     if (nproblems == 0) return 0;
     if (k < 1 || k > 128 || k2 < 1 || k2 > MAXK2) return -202;
-    const size_t smem = ((size_t)k * (k + 2) + 2 * (size_t)k2 * k + 3 * (size_t)k + MAXK2 * MAXK2 + MAXK2) * 8;
+    const size_t kpad = (size_t)((k + 7) & ~7);
+    const size_t k2p = (size_t)((k2 + 7) & ~7);
+    const size_t smem = (kpad * (kpad + 4) + k2p * (kpad + 4) + kpad * k2p + kpad * LDP + 3 * kpad + MAXK2 * MAXK2 + MAXK2) * 8;
     if (cudaFuncSetAttribute(ht_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     int dev = 0, sms = 148, per_sm = 1;
