@@ -26,6 +26,13 @@
 static _Thread_local int g_cov_failed = 0;
 int htn_ht_last_cov_failed(void) { return g_cov_failed; }
 
+/* Host-memory batches: the wrapper points this at the caller's output array; the shared dense path then
+ * draws in chunks and copies each finished chunk device -> host on its own stream WHILE the next chunk is in
+ * the sampling GEMM (the PCIe copy of the samples is the longest leg of a host-to-host call). */
+static _Thread_local double* g_host_sink = NULL;
+static _Thread_local int g_host_sink_used = 0;
+#define SINK_CHUNK 8192
+
 static void streams_view(const htn_streams_t* s, size_t offset, htnk_streams_t* v)
 {
     v->gen = s->gen;
@@ -102,12 +109,16 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     size_t chunk = nsamples;
     const size_t budget = (size_t)3 << 30; /* bytes of Z~ per chunk (two chunks are in flight) */
     if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
+    double* const sink = g_host_sink;
+    cudaStream_t copy_st = NULL;
+    if (sink && chunk > SINK_CHUNK) chunk = SINK_CHUNK;
     const size_t nchunks = (nsamples + chunk - 1) / chunk;
     HTN_TRY(htn_dalloc(ctx, (void**)&Z[0], chunk * ldz * 8));
     if (nchunks > 1) HTN_TRY(htn_dalloc(ctx, (void**)&Z[1], chunk * ldz * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
     HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     HTN_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+    if (sink) HTN_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_sym, cudaEventDisableTiming));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_sbranch, cudaEventDisableTiming));
@@ -202,6 +213,15 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
                              (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 0));
         HTN_CUDA(cudaEventRecord(ev_gemm[buf], st));
         htn_prof_mark(ctx, 4);
+        if (sink) { /* ship this chunk home while the next one is being computed */
+            HTN_CUDA(cudaStreamWaitEvent(copy_st, ev_gemm[buf], 0));
+            HTN_CUDA(cudaMemcpyAsync(sink + b0 * (size_t)k, out + b0 * (size_t)k, nb * (size_t)k * 8,
+                                     cudaMemcpyDeviceToHost, copy_st));
+        }
+    }
+    if (sink) {
+        HTN_CUDA(cudaStreamSynchronize(copy_st));
+        g_host_sink_used = 1;
     }
 done:
     /* never free a buffer the side stream may still be writing */
@@ -218,6 +238,7 @@ done:
     if (ev_sym) cudaEventDestroy(ev_sym);
     if (ev_sbranch) cudaEventDestroy(ev_sbranch);
     if (side2) cudaStreamDestroy(side2);
+    if (copy_st) cudaStreamDestroy(copy_st);
     for (int e = 0; e < 2; e++) {
         if (ev_rng[e]) cudaEventDestroy(ev_rng[e]);
         if (ev_gemm[e]) cudaEventDestroy(ev_gemm[e]);
@@ -443,8 +464,12 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     HTN_CUDA(cudaMemsetAsync(d_info, 0, B * sizeof(int), ctx.stream));
     if (b->independent) /* a problem whose cov is not PD leaves its row of `out` as the caller had it */
         HTN_CUDA(cudaMemcpyAsync(d_out, out, B * k * 8, cudaMemcpyHostToDevice, ctx.stream));
-    HTN_TRY(htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
-                          d_info, &first));
+    g_host_sink = (!b->independent && !conf->diag) ? out : NULL;
+    g_host_sink_used = 0;
+    rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
+                       d_info, &first);
+    g_host_sink = NULL;
+    if (rc) goto done;
     {
         int* h_info = info ? info : malloc(B * sizeof(int));
         if (!h_info) { rc = HTNORM_ALLOC_ERROR; goto done; }
@@ -455,8 +480,8 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
         if (!info) free(h_info);
     }
     /* shared inputs with cov not PD: nothing was drawn, `out` stays untouched (reference behaviour) */
-    if (!(first > 0 && !b->independent && !conf->diag && htn_ht_last_cov_failed()))
-    HTN_CUDA(cudaMemcpyAsync(out, d_out, B * k * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (!g_host_sink_used && !(first > 0 && !b->independent && !conf->diag && htn_ht_last_cov_failed()))
+        HTN_CUDA(cudaMemcpyAsync(out, d_out, B * k * 8, cudaMemcpyDeviceToHost, ctx.stream));
 done:
     htn_dfree(&ctx, d_info);
     htn_dfree(&ctx, d_out);
