@@ -93,18 +93,20 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m0 = tm * BM, n0 = tn * BN;
     if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < n0) return;
 
-    int kend1 = p.K, kbeg2 = p.K;
+    int kbeg1 = 0, kend1 = p.K, kbeg2 = p.K;
     const int kend2 = p.K;
     if (p.mode == HTNK_GEMM_B_LOWER) {
         int n1 = min(p.N, n0 + BN);
         kend1 = min(n1, p.ktri);
         kbeg2 = min(p.kext0, p.K);
+    } else if (p.mode == HTNK_GEMM_B_UPPER) {
+        kbeg1 = min((n0 / BK) * BK, p.K);  // B[n][k] == 0 for k < n: skip the chunks left of the tile
     }
-    const int nc1 = (kend1 + BK - 1) / BK;
+    const int nc1 = (kend1 - kbeg1 + BK - 1) / BK;
     const int nc2 = (kend2 - kbeg2 + BK - 1) / BK;
     const int nchunks = nc1 + nc2;
     auto chunk_range = [&](int c, int& k0, int& kend) {
-        if (c < nc1) { k0 = c * BK; kend = kend1; }
+        if (c < nc1) { k0 = kbeg1 + c * BK; kend = kend1; }
         else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
     };
 

@@ -53,9 +53,10 @@ int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, 
  * A, B: 16-byte aligned, lda/ldb even.  C: any ldc.  bias may be NULL.
  * mode: HTNK_GEMM_FULL; HTNK_GEMM_B_LOWER - B is lower-trapezoidal: B[n][kk] == 0 for
  *       n < kk < ktri, and columns [kext0, K) are dense (K range per tile is clipped accordingly);
- *       HTNK_GEMM_C_LOWER - only tiles that touch the lower triangle (m >= n) are computed.
+ *       HTNK_GEMM_C_LOWER - only tiles that touch the lower triangle (m >= n) are computed;
+ *       HTNK_GEMM_B_UPPER - B[n][kk] == 0 for kk < n: the K loop of a tile starts at its first column.
  * bn: N-tile width, 128 / 32 / 8 (0 = pick from N). */
-enum { HTNK_GEMM_FULL = 0, HTNK_GEMM_B_LOWER = 1, HTNK_GEMM_C_LOWER = 2 };
+enum { HTNK_GEMM_FULL = 0, HTNK_GEMM_B_LOWER = 1, HTNK_GEMM_C_LOWER = 2, HTNK_GEMM_B_UPPER = 3 };
 int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
                  const double* B, size_t ldb, double beta, double* C, size_t ldc, const double* bias,
                  int mode, int ktri, int kext0, int bn);

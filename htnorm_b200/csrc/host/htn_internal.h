@@ -65,6 +65,8 @@ typedef struct {
     double* dinv;   /* nblk x 128 x 128: inverse of each diagonal block of L */
     double* dinvt;  /* transposes of the above */
     double* rdiag;  /* 1 / L[j][j] */
+    double* linv;   /* n x ld: explicit L^-1 (lower), NULL until htn_factor_make_inverse */
+    double* linvt;  /* its transpose */
     int nblk;
     int solves;     /* the factor will be used by the blocked triangular solves (needs every inverse) */
 } htn_factor_t;
@@ -81,6 +83,11 @@ int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa);
 int htn_trsm_right_lt(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m);
 /* X := X * L^-1   (solves X_new L = X); needs fa->u */
 int htn_trsm_right_l(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m);
+int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa);
+int htn_solve_l(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m);
+int htn_solve_lt(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m);
+int htn_solve_spd(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* t, double* y,
+                  size_t ldy, int m);
 /* X := X * (L L^T)^-1  (dpotrs for row vectors) */
 int htn_potrs_rows(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m);
 

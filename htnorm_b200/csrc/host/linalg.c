@@ -39,7 +39,9 @@ void htn_factor_free(htn_ctx_t* ctx, htn_factor_t* fa)
     htn_dfree(ctx, fa->dinvt);
     htn_dfree(ctx, fa->u);
     htn_dfree(ctx, fa->rdiag);
-    fa->dinv = fa->dinvt = fa->u = fa->rdiag = NULL;
+    htn_dfree(ctx, fa->linv);
+    htn_dfree(ctx, fa->linvt);
+    fa->dinv = fa->dinvt = fa->u = fa->rdiag = fa->linv = fa->linvt = NULL;
 }
 
 int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa)
@@ -120,6 +122,47 @@ int htn_trsm_right_l(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t l
                              HTN_NB, 0.0, xj, ldx, NULL, HTNK_GEMM_FULL, 0, 0, 128));
     }
 done:
+    return rc;
+}
+
+/* Explicit inverse of the factor, so that solves with MANY right-hand-side rows become one triangular DMMA
+ * GEMM each (full-width grids) instead of n/128 dependent panel steps: linv = L^-1 (lower) by the blocked
+ * solve X L = I, linvt = its transpose. */
+int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa)
+{
+    int rc = 0;
+    const size_t bytes = (size_t)fa->n * fa->ld * sizeof(double);
+    if (!fa->linv) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linv, bytes));
+    if (!fa->linvt) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linvt, bytes));
+    HTN_CUDA(cudaMemsetAsync(fa->linv, 0, bytes, ctx->stream));
+    HTN_CUDA(cudaMemsetAsync(fa->linvt, 0, bytes, ctx->stream));
+    HTN_TRY(htnk_diag_set(ctx->stream, fa->linv, fa->ld, fa->n, NULL, 1.0));
+    HTN_TRY(htn_trsm_right_l(ctx, fa, fa->linv, fa->ld, fa->n));
+    HTN_TRY(htnk_transpose(ctx->stream, fa->linv, fa->ld, fa->n, fa->n, fa->linvt, fa->ld));
+done:
+    return rc;
+}
+
+/* Y (m x n) = X L^-1      (solves Y L = X; the row form of L^T y = x, dtrsv 'L','T') */
+int htn_solve_l(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
+{
+    return htnk_gemm_tn(ctx->stream, m, fa->n, fa->n, 1.0, x, ldx, fa->linvt, fa->ld, 0.0, y, ldy, NULL,
+                        HTNK_GEMM_B_UPPER, 0, 0, 0);
+}
+
+/* Y = X L^-T     (solves Y L^T = X) */
+int htn_solve_lt(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
+{
+    return htnk_gemm_tn(ctx->stream, m, fa->n, fa->n, 1.0, x, ldx, fa->linv, fa->ld, 0.0, y, ldy, NULL,
+                        HTNK_GEMM_B_LOWER, fa->n, fa->n, 0);
+}
+
+/* Y = X (L L^T)^-1 through a scratch buffer t (m x n, leading dimension ldx) */
+int htn_solve_spd(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* t, double* y,
+                  size_t ldy, int m)
+{
+    int rc = htn_solve_lt(ctx, fa, x, ldx, t, ldx, m);
+    if (!rc) rc = htn_solve_l(ctx, fa, t, ldx, y, ldy, m);
     return rc;
 }
 

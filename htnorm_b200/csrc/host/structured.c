@@ -26,7 +26,8 @@ static double identity_factor_garbage(void)
     return d;
 }
 
-/* stage a dense SPD input: lower triangle into a fresh n x ld buffer, factorise, build L^T */
+/* stage a dense SPD input: lower triangle into a fresh n x ld buffer, factorise, and build the explicit
+ * inverse factor that turns every later many-row solve into one triangular GEMM */
 static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src, double** buf, htn_factor_t* fa,
                         int* d_info)
 {
@@ -38,6 +39,7 @@ static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src,
     HTN_TRY(htn_factor_init(ctx, fa, *buf, ld, n, 1));
     HTN_TRY(htn_potrf(ctx, fa, d_info));
     HTN_TRY(htn_factor_make_u(ctx, fa));
+    HTN_TRY(htn_factor_make_inverse(ctx, fa));
 done:
     return rc;
 }
@@ -59,13 +61,21 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     const int lower_src = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
     const size_t pp = htn_round_up(p_, 16), np = htn_round_up(n_, 16);
     cudaStream_t st = ctx->stream;
-    double *Phip = NULL, *FA = NULL, *FO = NULL, *XT = NULL, *X = NULL, *M = NULL;
-    double *da = NULL, *sda = NULL, *sdo = NULL, *invo = NULL, *Z1 = NULL, *Z2 = NULL;
+    double *Phip = NULL, *FA = NULL, *FO = NULL, *XT = NULL, *X = NULL, *M = NULL, *T1 = NULL;
+    double *da = NULL, *sda = NULL, *sdo = NULL, *invo = NULL;
+    double *Z1 = NULL, *Z2 = NULL, *Y1 = NULL, *Y2 = NULL;
     int* d_info = NULL;
+    cudaStream_t side = NULL;  /* the generator: chunk 0 is drawn while A, Omega and M are being factorised */
+    cudaEvent_t ev_fork = NULL, ev_rng = NULL, ev_done = NULL;
+    int rng_in_flight = 0;
     htn_factor_t fa, fo, fm;
     memset(&fa, 0, sizeof(fa));
     memset(&fo, 0, sizeof(fo));
     memset(&fm, 0, sizeof(fm));
+
+    size_t chunk = nsamples;
+    const size_t budget = (size_t)3 << 30;
+    if (chunk * (pp + np) * 8 > budget) chunk = htn_round_up(budget / ((pp + np) * 8), 128);
 
     HTN_TRY(htn_dalloc(ctx, (void**)&d_info, 3 * sizeof(int)));
     HTN_CUDA(cudaMemsetAsync(d_info, 0, 3 * sizeof(int), st));
@@ -75,26 +85,49 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         HTN_TRY(htnk_transpose(st, phi, (size_t)n, p, n, Phip, pp));
     else
         HTN_TRY(htnk_copy2d(st, phi, (size_t)p, n, p, Phip, pp, NULL));
-
-    /* ---- A: factor (dense) or diagonal (mvn_rand_prec, src/htnorm_distributions.c:96-123) ---- */
-    if (a_id == NORMAL) {
-        HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
-    } else if (a_id == DIAGONAL) {
+    /* diagonal types: the divide by sqrt(d_ii) is folded into the generator's write-out
+     * (mvn_rand_prec, src/htnorm_distributions.c:101-109) */
+    if (a_id == DIAGONAL) {
         HTN_TRY(htn_dalloc(ctx, (void**)&da, pp * 8));
         HTN_TRY(htn_dalloc(ctx, (void**)&sda, pp * 8));
         HTN_TRY(htnk_diag_extract(st, a, (size_t)p, p, 0, da));
         HTN_TRY(htnk_diag_extract(st, a, (size_t)p, p, 1, sda));
     }
-    /* ---- Omega ---- */
-    if (o_id == NORMAL) {
-        HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1));
-    } else if (o_id == DIAGONAL) {
+    if (o_id == DIAGONAL) {
         HTN_TRY(htn_dalloc(ctx, (void**)&sdo, np * 8));
         HTN_TRY(htn_dalloc(ctx, (void**)&invo, np * 8));
         HTN_TRY(htnk_diag_extract(st, omega, (size_t)n, n, 1, sdo));
         HTN_TRY(htnk_diag_extract(st, omega, (size_t)n, n, 2, invo));
     }
-    /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two TRSMs) ---- */
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z1, chunk * pp * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Z2, chunk * np * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&Y2, chunk * np * 8));
+    if (a_id == NORMAL) HTN_TRY(htn_dalloc(ctx, (void**)&Y1, chunk * pp * 8));
+    HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_rng, cudaEventDisableTiming));
+    HTN_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    /* Both runs of normals of chunk 0 are drawn up front (y1's then y2's, from the same stream).  If chol(A)
+     * or chol(omega) fails the reference would have stopped earlier: only the single-draw entry cares (it
+     * writes the generator back), and it re-checks the codes below before touching the caller's state. */
+    {
+        const size_t nb0 = nsamples < chunk ? nsamples : chunk;
+        htnk_streams_t sv = {s->gen, s->seeds, s->seed0, s->states, s->zpre};
+        htnk_segment_t seg[2] = {{(size_t)p, Z1, pp, a_id == DIAGONAL ? sda : NULL, NULL, NULL},
+                                 {(size_t)n, Z2, np, o_id == DIAGONAL ? sdo : NULL, NULL, NULL}};
+        HTN_CUDA(cudaEventRecord(ev_fork, st));
+        if (!s->states) { /* batched (seeded) streams: overlap with the factorisations */
+            HTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            HTN_TRY(htnk_normal_fill(side, &sv, nb0, 2, seg, NULL));
+            HTN_CUDA(cudaEventRecord(ev_rng, side));
+            rng_in_flight = 1;
+        }
+    }
+
+    /* ---- A, Omega: factor (dense) (mvn_rand_prec, src/htnorm_distributions.c:110-123) ---- */
+    if (a_id == NORMAL) HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
+    if (o_id == NORMAL) HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1));
+    /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs) */
     if (a_id == IDENTITY) {
         XT = Phip;
     } else {
@@ -103,25 +136,25 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         if (a_id == DIAGONAL) {
             HTN_TRY(htnk_coldiv(st, Phip, pp, n, p, da, XT, pp));
         } else {
-            HTN_TRY(htnk_copy2d(st, Phip, pp, n, p, XT, pp, NULL));
-            HTN_TRY(htn_potrs_rows(ctx, &fa, XT, pp, n));
+            HTN_TRY(htn_dalloc(ctx, (void**)&T1, (size_t)n * pp * 8));
+            HTN_TRY(htn_solve_spd(ctx, &fa, Phip, pp, T1, XT, pp, n));
         }
     }
     /* ---- M = Omega^-1 + X^T Phi^T  (compute_precision_inverse, src/htnorm.c:190-214; dgemm/dsyrk :267-300) */
     HTN_TRY(htn_dalloc(ctx, (void**)&M, (size_t)n * np * 8));
     HTN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * np * 8, st));
-    if (o_id == NORMAL) {
-        HTN_TRY(htnk_diag_set(st, M, np, n, NULL, 1.0));
-        HTN_TRY(htn_potrs_rows(ctx, &fo, M, np, n));
-    } else if (o_id == DIAGONAL) {
+    if (o_id == NORMAL) /* Omega^-1 = L^-T L^-1 */
+        HTN_TRY(htnk_gemm_tn(st, n, n, n, 1.0, fo.linvt, fo.ld, fo.linvt, fo.ld, 0.0, M, np, NULL, HTNK_GEMM_FULL, 0,
+                             0, 0));
+    else if (o_id == DIAGONAL)
         HTN_TRY(htnk_diag_set(st, M, np, n, invo, 0.0));
-    } else {
+    else
         HTN_TRY(htnk_diag_set(st, M, np, n, NULL, 1 / identity_factor_garbage()));
-    }
     HTN_TRY(htnk_gemm_tn(st, n, n, p, 1.0, XT, pp, Phip, pp, 1.0, M, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
     HTN_TRY(htn_factor_init(ctx, &fm, M, np, n, 1));
     HTN_TRY(htn_potrf(ctx, &fm, d_info + 2)); /* dposv, src/htnorm.c:330 */
     HTN_TRY(htn_factor_make_u(ctx, &fm));
+    HTN_TRY(htn_factor_make_inverse(ctx, &fm));
     /* X = (X^T)^T, p x n: the B operand of the final GEMM */
     HTN_TRY(htn_dalloc(ctx, (void**)&X, (size_t)p * np * 8));
     HTN_CUDA(cudaMemsetAsync(X, 0, (size_t)p * np * 8, st));
@@ -137,47 +170,63 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
 
     double coef = struct_mean ? -1.0 : 1.0;
     if (flags & HTN_FLAG_PAPER_SIGN) coef = -coef;
-    size_t chunk = nsamples;
-    const size_t budget = (size_t)6 << 30;
-    if (chunk * (pp + np) * 8 > budget) chunk = htn_round_up(budget / ((pp + np) * 8), 128);
-    HTN_TRY(htn_dalloc(ctx, (void**)&Z1, chunk * pp * 8));
-    HTN_TRY(htn_dalloc(ctx, (void**)&Z2, chunk * np * 8));
     for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
         const int nb = (int)(nsamples - b0 < chunk ? nsamples - b0 : chunk);
         htnk_streams_t sv = {s->gen, s->seeds ? s->seeds + b0 : NULL, s->seed0 + (uint64_t)b0,
                              s->states ? s->states + 4 * b0 : NULL, s->zpre};
         htnk_segment_t seg[2] = {{(size_t)p, Z1, pp, a_id == DIAGONAL ? sda : NULL, NULL, NULL},
                                  {(size_t)n, Z2, np, o_id == DIAGONAL ? sdo : NULL, NULL, NULL}};
-        if (h_info[1]) { /* Omega not PD: y1 was drawn (stream advanced), then the call fails (:246) */
+        if (b0 == 0 && rng_in_flight) {
+            HTN_CUDA(cudaStreamWaitEvent(st, ev_rng, 0));
+            rng_in_flight = 0;
+            if (h_info[1]) continue; /* Omega not PD: the call fails after y1's draws (:246) */
+        } else if (h_info[1]) { /* single draw continuing a generator: advance it by y1's draws only */
             HTN_TRY(htnk_normal_fill(st, &sv, (size_t)nb, 1, seg, NULL));
             continue;
+        } else {
+            HTN_TRY(htnk_normal_fill(st, &sv, (size_t)nb, 2, seg, NULL));
         }
-        HTN_TRY(htnk_normal_fill(st, &sv, (size_t)nb, 2, seg, NULL));
-        if (a_id == NORMAL) HTN_TRY(htn_trsm_right_l(ctx, &fa, Z1, pp, nb)); /* L^T y1 = z (dtrsv, :120) */
-        if (o_id == NORMAL) HTN_TRY(htn_trsm_right_l(ctx, &fo, Z2, np, nb));
+        /* L^T y1 = z (dtrsv, src/htnorm_distributions.c:120) for the whole chunk: Y1 = Z1 L_A^-1 */
+        const double* y1 = Z1;
+        if (a_id == NORMAL) {
+            HTN_TRY(htn_solve_l(ctx, &fa, Z1, pp, Y1, pp, nb));
+            y1 = Y1;
+        }
+        double* bm = Z2;
+        if (o_id == NORMAL) {
+            HTN_TRY(htn_solve_l(ctx, &fo, Z2, np, Y2, np, nb));
+            bm = Y2;
+        }
+        double* scratch = (bm == Z2) ? Y2 : Z2;
         /* b = Phi y1 + y2 (dgemm, src/htnorm.c:310) */
-        HTN_TRY(htnk_gemm_tn(st, nb, n, p, 1.0, Z1, pp, Phip, pp, 1.0, Z2, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        HTN_TRY(htnk_gemm_tn(st, nb, n, p, 1.0, y1, pp, Phip, pp, 1.0, bm, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
         double* o = out + b0 * p_;
         if (struct_mean) { /* src/htnorm.c:314-321 */
-            HTN_TRY(htnk_rsub_rows(st, Z2, np, nb, n, mean));
-            HTN_TRY(htnk_copy2d(st, Z1, pp, nb, p, o, p_, NULL));
+            HTN_TRY(htnk_rsub_rows(st, bm, np, nb, n, mean));
+            HTN_TRY(htnk_copy2d(st, y1, pp, nb, p, o, p_, NULL));
         } else { /* src/htnorm.c:322-326 */
-            HTN_TRY(htnk_copy2d(st, Z1, pp, nb, p, o, p_, mean));
+            HTN_TRY(htnk_copy2d(st, y1, pp, nb, p, o, p_, mean));
         }
         if (h_info[2]) continue; /* M not PD: out keeps y1 (+ mean), as after a failed dposv (:330-346) */
-        HTN_TRY(htn_potrs_rows(ctx, &fm, Z2, np, nb));
+        /* alpha = b M^-1: two triangular GEMMs, result back in bm */
+        HTN_TRY(htn_solve_lt(ctx, &fm, bm, np, scratch, np, nb));
+        HTN_TRY(htn_solve_l(ctx, &fm, scratch, np, bm, np, nb));
         /* out += coef * alpha X^T  (dgemv / dgemm, src/htnorm.c:332-346) */
-        HTN_TRY(htnk_gemm_tn(st, nb, p, n, coef, Z2, np, X, np, 1.0, o, p_, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        HTN_TRY(htnk_gemm_tn(st, nb, p, n, coef, bm, np, X, np, 1.0, o, p_, NULL, HTNK_GEMM_FULL, 0, 0, 0));
     }
     *first_info = h_info[1] ? h_info[1] : h_info[2];
 finish:
     if (d_info_out) rc = htnk_fill_i32(st, d_info_out, nsamples, *first_info);
 done:
+    if (rng_in_flight && ev_rng) cudaStreamWaitEvent(st, ev_rng, 0); /* never free under the generator */
     htn_factor_free(ctx, &fa);
     htn_factor_free(ctx, &fo);
     htn_factor_free(ctx, &fm);
     htn_dfree(ctx, Z1);
     htn_dfree(ctx, Z2);
+    htn_dfree(ctx, Y1);
+    htn_dfree(ctx, Y2);
+    htn_dfree(ctx, T1);
     htn_dfree(ctx, X);
     htn_dfree(ctx, M);
     if (XT != Phip) htn_dfree(ctx, XT);
@@ -189,6 +238,10 @@ done:
     htn_dfree(ctx, FA);
     htn_dfree(ctx, Phip);
     htn_dfree(ctx, d_info);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_rng) cudaEventDestroy(ev_rng);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (side) cudaStreamDestroy(side);
     return rc;
 }
 
