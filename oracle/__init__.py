@@ -115,8 +115,10 @@ class Oracle:
 class Reference:
     """The unmodified reference library (kind "reference"); raises FileNotFoundError if not built."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libref_harness.so")
+    def __init__(self, colmajor=False):
+        """colmajor=True: the reference compiled with -DHTNORM_COLMAJOR (what its R binding builds,
+        src/Makevars:1): g / phi are column-major, symmetric inputs are read through the lower triangle."""
+        path = os.path.join(HERE, "_ref", "libref_harness_colmajor.so" if colmajor else "libref_harness.so")
         if not os.path.exists(path):
             if os.path.isdir(os.environ.get("HTNORM_REFERENCE", "/root/reference")):
                 build()

@@ -312,3 +312,66 @@ def test_device_pointer_path_and_shard_invariance(h):
         parts.append(o)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts), full)
+
+
+def test_colmajor_flag_matches_reference_colmajor_build(h):
+    """HTN_FLAG_COLMAJOR == the reference compiled with -DHTNORM_COLMAJOR (its R binding, src/Makevars:1):
+    g / phi column-major.  Golden vectors come from that build (tools/make_golden.py)."""
+    import os
+    from conftest import GOLD
+    gold = np.load(os.path.join(GOLD, "colmajor.npz"))
+    F = h._lib.HTN_FLAG_COLMAJOR
+    for name in ("k4_dense_64", "k20_dense_100", "k3_diag_40", "k1_dense_50"):
+        c = cases.ht_case(name)
+        gcm = np.ascontiguousarray(c["g"].T).reshape(c["g"].shape)   # same bytes as column-major g
+        x, info = h.hyperplane_truncated_mvnorm_batch(c["nsamples"], c["mean"], c["cov"], gcm, c["r"],
+                                                      diag=c["diag"], gen=c["gen"], seed0=c["seed0"], flags=F)
+        assert not info.any() and rel_err(x, gold["ht_" + name + "__x"]) < REL_TOL
+    for name in ("nn_plain", "nn_struct", "dn_struct", "nd_plain_mid", "in_plain"):
+        c = cases.sp_case(name)
+        pcm = np.ascontiguousarray(c["phi"].T).reshape(c["phi"].shape)
+        x, info = h.structured_precision_mvnorm_batch(c["nsamples"], c["mean"], c["a"], pcm, c["omega"],
+                                                      c["struct_mean"], c["a_type"], c["o_type"], gen=c["gen"],
+                                                      seed0=c["seed0"], flags=F)
+        assert not info.any() and rel_err(x, gold["sp_" + name + "__x"]) < REL_TOL
+
+
+def test_triangle_read_by_each_layout(h):
+    """the row-major build reads symmetric inputs through the UPPER triangle, the column-major
+    build through the LOWER one: garbage in the other triangle must not change the result."""
+    c = cases.ht_case("k4_dense_64")
+    k = c["cov"].shape[0]
+    rng = np.random.default_rng(0)
+    junk = rng.standard_normal((k, k))
+    up_ok = np.triu(c["cov"]) + np.tril(junk, -1)          # upper intact, lower garbage
+    lo_ok = np.tril(c["cov"]) + np.triu(junk, 1)
+    base, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], c["cov"], c["g"], c["r"], seed0=3)
+    x, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], up_ok, c["g"], c["r"], seed0=3)
+    assert np.array_equal(x, base)
+    gcm = np.ascontiguousarray(c["g"].T).reshape(c["g"].shape)
+    F = h._lib.HTN_FLAG_COLMAJOR
+    basec, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], c["cov"], gcm, c["r"], seed0=3, flags=F)
+    xc, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"], lo_ok, gcm, c["r"], seed0=3, flags=F)
+    assert np.array_equal(xc, basec) and rel_err(basec, base) < REL_TOL
+
+
+def test_paper_sign_option(h, oracle):
+    """HTN_FLAG_PAPER_SIGN flips the coefficient of the Woodbury update to the sign of Cong et al. (2017);
+    the default stays the reference's.  With the paper's sign the samples have covariance
+    (A + Phi^T Omega Phi)^-1 - checked statistically on a small problem."""
+    s = cases.sp_case("nn_plain")
+    F = h._lib.HTN_FLAG_PAPER_SIGN
+    x, _ = h.structured_precision_mvnorm_batch(16, s["mean"], s["a"], s["phi"], s["omega"], False, 0, 0,
+                                               gen="pcg64", seed0=5, flags=F)
+    xo = oracle.structured("pcg64", 16, s["mean"], s["a"], s["phi"], s["omega"], False, 0, 0, paper_sign=True,
+                           seed0=5)[0]
+    assert rel_err(x, xo) < REL_TOL
+    xd, _ = h.structured_precision_mvnorm_batch(16, s["mean"], s["a"], s["phi"], s["omega"], False, 0, 0,
+                                                gen="pcg64", seed0=5)
+    assert not np.allclose(x, xd)
+    B = 200000
+    xs, _ = h.structured_precision_mvnorm_batch(B, np.zeros(20), s["a"], s["phi"], s["omega"], False, 0, 0,
+                                                gen="xrs128p", seed0=123, flags=F)
+    target = np.linalg.inv(s["a"] + s["phi"].T @ s["omega"] @ s["phi"])
+    emp = np.cov(xs.T)
+    assert np.abs(emp - target).max() < 0.02 * np.abs(target).max() + 5e-3

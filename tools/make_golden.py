@@ -66,6 +66,22 @@ def main():
         sp[name + "__info"] = info
         sp[name + "__digest"] = digest(c["mean"], c["a"], c["phi"], c["omega"])
     np.savez_compressed(os.path.join(GOLD, "structured.npz"), **sp)
+    # the -DHTNORM_COLMAJOR build (R binding): g / phi handed over column-major
+    refc = Reference(colmajor=True)
+    cm = {}
+    for name in ("k4_dense_64", "k20_dense_100", "k3_diag_40", "k1_dense_50"):
+        c = cases.ht_case(name)
+        gcm = np.ascontiguousarray(c["g"].T)          # k x k2 row-major == k2 x k column-major
+        x, info, rc = refc.hyperplane(c["gen"], c["nsamples"], c["mean"], c["cov"], gcm.reshape(c["g"].shape),
+                                      c["r"], diag=c["diag"], seed0=c["seed0"])
+        cm["ht_" + name + "__x"] = x
+    for name in ("nn_plain", "nn_struct", "dn_struct", "nd_plain_mid", "in_plain"):
+        c = cases.sp_case(name)
+        pcm = np.ascontiguousarray(c["phi"].T).reshape(c["phi"].shape)
+        x, info, rc = refc.structured(c["gen"], c["nsamples"], c["mean"], c["a"], pcm, c["omega"],
+                                      c["struct_mean"], c["a_type"], c["o_type"], seed0=c["seed0"])
+        cm["sp_" + name + "__x"] = x
+    np.savez_compressed(os.path.join(GOLD, "colmajor.npz"), **cm)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
