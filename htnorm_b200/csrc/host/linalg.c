@@ -59,20 +59,32 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
     int rc = 0;
     const int n = fa->n;
     const size_t ld = fa->ld;
-    for (int jb = 0; jb < fa->nblk; jb++) {
-        const int j0 = jb * HTN_NB;
-        const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
-        const int rows = n - j0 - nb;
-        double* ajj = fa->f + (size_t)j0 * ld + j0;
-        HTN_TRY(htnk_potf2(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info));
-        if (rows <= 0) break;
-        double* a21 = fa->f + (size_t)(j0 + nb) * ld + j0;
-        /* panel: L21 = A21 * L11^-T, rows independent, in place */
-        HTN_TRY(htnk_trsm_rows(ctx->stream, a21, ld, rows, ajj, ld, nb, fa->rdiag + j0));
-        /* trailing update: A22 -= L21 * L21^T on the lower-triangle tiles (DMMA) */
-        double* a22 = fa->f + (size_t)(j0 + nb) * ld + (j0 + nb);
-        HTN_TRY(htnk_gemm_tn(ctx->stream, rows, rows, nb, -1.0, a21, ld, a21, ld, 1.0, a22, ld, NULL,
-                             HTNK_GEMM_C_LOWER, 0, 0, 0));
+    /* Two-level blocking.  Super-panels of W columns are factorised left-looking INSIDE the panel (block
+     * column j gets the updates of the panel's earlier columns in one GEMM, then potf2 + row solve), and the
+     * matrix to the right of the super-panel gets ONE right-looking rank-W update.  W = 128 is the plain
+     * right-looking algorithm (most parallel tiles per launch: best for small n); large n uses wide panels so
+     * that the trailing update has a long K loop (W / 16 chunks instead of 8) and the trailing matrix is
+     * re-read and re-written n / W instead of n / 128 times. */
+    const int W = n >= 8192 ? 1024 : (n >= 2048 ? 512 : HTN_NB);
+    for (int J0 = 0; J0 < n; J0 += W) {
+        const int J1 = J0 + W < n ? J0 + W : n;
+        for (int j0 = J0; j0 < J1; j0 += HTN_NB) {
+            const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
+            const int rows = n - j0 - nb;
+            double* ajj = fa->f + (size_t)j0 * ld + j0;
+            if (j0 > J0) /* A[j0:, j0:j0+nb] -= L[j0:, J0:j0] * L[j0:j0+nb, J0:j0]^T */
+                HTN_TRY(htnk_gemm_tn(ctx->stream, n - j0, nb, j0 - J0, -1.0, fa->f + (size_t)j0 * ld + J0, ld,
+                                     fa->f + (size_t)j0 * ld + J0, ld, 1.0, ajj, ld, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+            HTN_TRY(htnk_potf2(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info));
+            if (rows > 0) /* panel: L21 = A21 * L11^-T, rows independent, in place */
+                HTN_TRY(htnk_trsm_rows(ctx->stream, fa->f + (size_t)(j0 + nb) * ld + j0, ld, rows, ajj, ld, nb,
+                                       fa->rdiag + j0));
+        }
+        const int R = n - J1;
+        if (R > 0) /* trailing update: A[J1:, J1:] -= L[J1:, J0:J1] * L[J1:, J0:J1]^T on the lower tiles (DMMA) */
+            HTN_TRY(htnk_gemm_tn(ctx->stream, R, R, J1 - J0, -1.0, fa->f + (size_t)J1 * ld + J0, ld,
+                                 fa->f + (size_t)J1 * ld + J0, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld, NULL,
+                                 HTNK_GEMM_C_LOWER, 0, 0, 0));
     }
     /* inverses of the diagonal blocks, all at once, only when blocked solves will follow */
     if (fa->solves) HTN_TRY(htnk_trtri_batched(ctx->stream, fa->f, ld, n, fa->dinv, fa->dinvt));

@@ -375,3 +375,19 @@ def test_paper_sign_option(h, oracle):
     target = np.linalg.inv(s["a"] + s["phi"].T @ s["omega"] @ s["phi"])
     emp = np.cov(xs.T)
     assert np.abs(emp - target).max() < 0.02 * np.abs(target).max() + 5e-3
+
+
+@pytest.mark.parametrize("n", [2048 + 77, 8192 + 130])
+def test_potrf_wide_panels(h, n):
+    """n >= 2048 / 8192 take 512- / 1024-column super-panels (htn_potrf): L L^T = A, L lower, solves correct."""
+    lib = _dbg(h)
+    rng = np.random.default_rng(n)
+    a = cases.spd(rng, n)
+    l = np.empty((n, n))
+    x0 = rng.standard_normal((3, n))
+    x = x0.copy()
+    rc = lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 3, 3, x.ctypes.data)
+    assert rc == 0, h._lib.last_error()
+    assert np.abs(l @ l.T - a).max() < 2e-11
+    assert np.abs(np.triu(l, 1)).max() == 0.0
+    assert np.abs(x @ a - x0).max() < 1e-9          # x = x0 A^-1
