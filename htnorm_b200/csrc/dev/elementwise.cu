@@ -328,3 +328,22 @@ extern "C" int htnk_rows_dot(cudaStream_t st, size_t nsamples, int k, int k2, co
     rows_dot_kernel<<<(unsigned)((nsamples + 7) / 8), 256, 0, st>>>(nsamples, k, k2, g, ldg, y, ldy, dcol, ldd);
     return status();
 }
+
+// ---- test matrix for the factorisation benchmark: lower triangle of the SPD Toeplitz matrix
+// a[i][j] = 1 / (1 + |i - j|) + [i == j]   (zeros above the diagonal) ----
+namespace {
+__global__ void fill_test_spd_kernel(double* f, size_t ld, int n)
+{
+    const size_t total = (size_t)n * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t i = idx / n, j = idx - i * n;
+        f[i * ld + j] = j <= i ? 1.0 / (1.0 + (double)(i - j)) + (i == j ? 1.0 : 0.0) : 0.0;
+    }
+}
+}  // namespace
+extern "C" int htnk_fill_test_spd(cudaStream_t st, double* f, size_t ld, int n)
+{
+    fill_test_spd_kernel<<<148 * 8, 256, 0, st>>>(f, ld, n);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}

@@ -120,3 +120,46 @@ double htn_dbg_dmma_tile_probe(int ctas_per_sm)
     htn_ctx_end(&ctx, 1);
     return v;
 }
+
+int htnk_fill_test_spd(cudaStream_t st, double* f, size_t ld, int n);
+/* milliseconds of ONE blocked Cholesky (htn_potrf) of an n x n SPD test matrix generated on the device,
+ * best of `reps`, CUDA events; also returns the LAPACK info in *info_out */
+double htn_dbg_potrf_time(int n, int reps, int* info_out)
+{
+    htn_ctx_t ctx;
+    if (htn_ctx_begin(&ctx, -1, NULL, 1)) return -1.0;
+    int rc = 0;
+    const size_t ld = htn_round_up((size_t)n, 16);
+    double* F = NULL;
+    int* d_info = NULL;
+    double best = -1.0;
+    htn_factor_t fa;
+    memset(&fa, 0, sizeof(fa));
+    cudaEvent_t e0 = NULL, e1 = NULL;
+    HTN_TRY(htn_dalloc(&ctx, (void**)&F, (size_t)n * ld * 8));
+    HTN_TRY(htn_dalloc(&ctx, (void**)&d_info, sizeof(int)));
+    HTN_TRY(htn_factor_init(&ctx, &fa, F, ld, n, 0));
+    HTN_CUDA(cudaEventCreate(&e0));
+    HTN_CUDA(cudaEventCreate(&e1));
+    for (int r = 0; r < reps; r++) {
+        HTN_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx.stream));
+        HTN_CUDA(cudaMemsetAsync(F, 0, (size_t)n * ld * 8, ctx.stream));
+        HTN_TRY(htnk_fill_test_spd(ctx.stream, F, ld, n));
+        HTN_CUDA(cudaEventRecord(e0, ctx.stream));
+        HTN_TRY(htn_potrf(&ctx, &fa, d_info));
+        HTN_CUDA(cudaEventRecord(e1, ctx.stream));
+        HTN_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        HTN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (best < 0 || ms < best) best = ms;
+    }
+    if (info_out) HTN_CUDA(cudaMemcpy(info_out, d_info, sizeof(int), cudaMemcpyDeviceToHost));
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    htn_factor_free(&ctx, &fa);
+    htn_dfree(&ctx, d_info);
+    htn_dfree(&ctx, F);
+    htn_ctx_end(&ctx, 1);
+    return rc ? -1.0 : best;
+}
