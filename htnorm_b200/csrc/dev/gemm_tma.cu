@@ -32,6 +32,7 @@ struct TmaGemmParams {
     size_t ldc;
     int mode, ktri, kext0;
     int tiles_m, tiles_n;
+    int paired;  // B_LOWER: one CTA runs the N tiles (tiles_n-1-q, q) of a row slab back to back
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,6 +74,40 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// per-tile K schedule: chunks of BK from segment 1 [kbeg1, kend1) then segment 2 [kbeg2, K)
+struct TileK {
+    int n0, kbeg1, kend1, kbeg2, nc1, nchunks;
+};
+
+__device__ __forceinline__ TileK make_tile(const TmaGemmParams& p, int tn)
+{
+    TileK t;
+    t.n0 = tn * BN;
+    t.kbeg1 = 0;
+    t.kend1 = p.K;
+    t.kbeg2 = p.K;
+    if (p.mode == HTNK_GEMM_B_LOWER) {
+        int n1 = min(p.N, t.n0 + BN);
+        t.kend1 = min(n1, p.ktri);
+        t.kbeg2 = min(p.kext0, p.K);
+    } else if (p.mode == HTNK_GEMM_B_UPPER) {
+        t.kbeg1 = min((t.n0 / BK) * BK, p.K);  // B[n][k] == 0 for k < n: skip the chunks left of the tile
+    }
+    t.nc1 = (t.kend1 - t.kbeg1 + BK - 1) / BK;
+    t.nchunks = t.nc1 + (p.K - t.kbeg2 + BK - 1) / BK;
+    return t;
+}
+
+__device__ __forceinline__ void tile_chunk(const TmaGemmParams& p, const TileK& t, int c, int& k0, int& kend)
+{
+    if (c < t.nc1) { k0 = t.kbeg1 + c * BK; kend = t.kend1; }
+    else { k0 = t.kbeg2 + (c - t.nc1) * BK; kend = p.K; }
+}
+
+// A CTA owns ONE output tile, or (p.paired: lower-triangular B) the PAIR of N tiles (tiles_n-1-q, q) of one
+// 128-row slab: every CTA then runs the same number of K chunks (the longest and the shortest loop together,
+// as in causal-attention schedulers), and the TMA ring keeps streaming across the tile boundary, so the
+// second tile's first chunks are already in flight while the first tile's epilogue is being written.
 __global__ void __launch_bounds__(NT, 2)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TmaGemmParams p)
@@ -88,27 +123,24 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const int bid = blockIdx.x;
-    const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
-    const int tm = bid / p.tiles_n;
-    const int m0 = tm * BM, n0 = tn * BN;
-    if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < n0) return;
-
-    int kbeg1 = 0, kend1 = p.K, kbeg2 = p.K;
-    const int kend2 = p.K;
-    if (p.mode == HTNK_GEMM_B_LOWER) {
-        int n1 = min(p.N, n0 + BN);
-        kend1 = min(n1, p.ktri);
-        kbeg2 = min(p.kext0, p.K);
-    } else if (p.mode == HTNK_GEMM_B_UPPER) {
-        kbeg1 = min((n0 / BK) * BK, p.K);  // B[n][k] == 0 for k < n: skip the chunks left of the tile
+    int ntl = 1;
+    TileK T[2];
+    int m0;
+    if (p.paired) {
+        const int npairs = (p.tiles_n + 1) >> 1;
+        const int q = bid % npairs;
+        m0 = (bid / npairs) * BM;
+        T[0] = make_tile(p, p.tiles_n - 1 - q);
+        T[1] = make_tile(p, q);
+        ntl = (p.tiles_n - 1 - q != q) ? 2 : 1;
+    } else {
+        const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
+        m0 = (bid / p.tiles_n) * BM;
+        T[0] = make_tile(p, tn);
+        T[1] = T[0];
+        if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < T[0].n0) return;
     }
-    const int nc1 = (kend1 - kbeg1 + BK - 1) / BK;
-    const int nc2 = (kend2 - kbeg2 + BK - 1) / BK;
-    const int nchunks = nc1 + nc2;
-    auto chunk_range = [&](int c, int& k0, int& kend) {
-        if (c < nc1) { k0 = kbeg1 + c * BK; kend = kend1; }
-        else { k0 = kbeg2 + (c - nc1) * BK; kend = kend2; }
-    };
+    const int total_chunks = T[0].nchunks + (ntl == 2 ? T[1].nchunks : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -120,119 +152,127 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     __syncthreads();
 
-    // one elected thread feeds the ring; chunk c lands in stage c % STAGES
-    auto issue = [&](int c) {
-        if (c >= nchunks) return;
-        const int s = c % STAGES, round = c / STAGES;
+    // one elected thread feeds the ring; global chunk cg (over the CTA's tiles) lands in stage cg % STAGES
+    auto issue = [&](int cg) {
+        if (cg >= total_chunks) return;
+        const int s = cg % STAGES, round = cg / STAGES;
         if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        const int t = cg < T[0].nchunks ? 0 : 1;
         int k0, kend;
-        chunk_range(c, k0, kend);
+        tile_chunk(p, T[t], t ? cg - T[0].nchunks : cg, k0, kend);
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
         tma_load_2d(sA + s * A_BYTES, &tmA, k0, m0, &full[s]);
-        tma_load_2d(sB + s * B_BYTES, &tmB, k0, n0, &full[s]);
+        tma_load_2d(sB + s * B_BYTES, &tmB, k0, T[t].n0, &full[s]);
     };
     if (tid == 0) {
         for (int c = 0; c < AHEAD; c++) issue(c);
     }
 
-    double acc[WM][WN][2];
-#pragma unroll
-    for (int i = 0; i < WM; i++)
-#pragma unroll
-        for (int j = 0; j < WN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
     const int g = lane >> 2, t4 = lane & 3;
-    const int nw = n0 + wn * WN * 8;
-    const int jhi = min(WN, (p.N - nw + 7) >> 3);
     // swizzled fragment addressing: row r (r & 7 == g), 16-byte chunk ((t4 >> 1) * 4 + s) ^ g, half t4 & 1
     const int a_off = (wm * WM * 8 + g) * 128 + (t4 & 1) * 8;
     const int b_off = (wn * WN * 8 + g) * 128 + (t4 & 1) * 8;
     int xs[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) xs[s] = ((((t4 >> 1) * 4 + s) ^ g) << 4);
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 
-    for (int c = 0; c < nchunks; c++) {
-        if (tid == 0) issue(c + AHEAD);
-        const int st = c % STAGES;
-        mbar_wait(&full[st], (c / STAGES) & 1);
-        int k0, kend;
-        chunk_range(c, k0, kend);
-        const unsigned char* a_s = sA + st * A_BYTES + a_off;
-        const unsigned char* b_s = sB + st * B_BYTES + b_off;
-        const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < nc1) && (k0 + BK > nw);
-        if (!diag && jhi == WN && kend - k0 >= BK) {
+    int cg = 0;
+    for (int tl = 0; tl < ntl; tl++) {
+        const TileK tk = T[tl];
+        const int n0 = tk.n0;
+        const int nw = n0 + wn * WN * 8;
+        const int jhi = min(WN, (p.N - nw + 7) >> 3);
+        double acc[WM][WN][2];
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                double af[WM], bf[WN];
+        for (int i = 0; i < WM; i++)
 #pragma unroll
-                for (int i = 0; i < WM; i++) af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
+            for (int j = 0; j < WN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int c = 0; c < tk.nchunks; c++, cg++) {
+            if (tid == 0) issue(cg + AHEAD);
+            const int st = cg % STAGES;
+            mbar_wait(&full[st], (cg / STAGES) & 1);
+            int k0, kend;
+            tile_chunk(p, tk, c, k0, kend);
+            const unsigned char* a_s = sA + st * A_BYTES + a_off;
+            const unsigned char* b_s = sB + st * B_BYTES + b_off;
+            const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < tk.nc1) && (k0 + BK > nw);
+            if (!diag && jhi == WN && kend - k0 >= BK) {
 #pragma unroll
-                for (int j = 0; j < WN; j++) bf[j] = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
+                for (int s = 0; s < 4; s++) {
+                    double af[WM], bf[WN];
 #pragma unroll
-                for (int i = 0; i < WM; i++)
+                    for (int i = 0; i < WM; i++) af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
 #pragma unroll
-                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
-        } else {
+                    for (int j = 0; j < WN; j++) bf[j] = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                // step s multiplies k = k0 + {2s, 2s+1, 8+2s, 9+2s}; its smallest k decides whether any
-                // non-zero element can be involved
-                const int kmin = k0 + 2 * s;
-                if (kmin < kend) {
-                    int jlo = 0;
-                    if (diag) jlo = max(0, (kmin - nw) >> 3);
-                    if (jlo < jhi) {
-                        double af[WM];
+                    for (int i = 0; i < WM; i++)
 #pragma unroll
-                        for (int i = 0; i < WM; i++) af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
+                        for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            } else {
 #pragma unroll
-                        for (int j = 0; j < WN; j++) {
-                            if (j >= jlo && j < jhi) {
-                                const double bfj = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
+                for (int s = 0; s < 4; s++) {
+                    // step s multiplies k = k0 + {2s, 2s+1, 8+2s, 9+2s}; its smallest k decides whether any
+                    // non-zero element can be involved
+                    const int kmin = k0 + 2 * s;
+                    if (kmin < kend) {
+                        int jlo = 0;
+                        if (diag) jlo = max(0, (kmin - nw) >> 3);
+                        if (jlo < jhi) {
+                            double af[WM];
 #pragma unroll
-                                for (int i = 0; i < WM; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bfj);
+                            for (int i = 0; i < WM; i++)
+                                af[i] = *reinterpret_cast<const double*>(a_s + i * 1024 + xs[s]);
+#pragma unroll
+                            for (int j = 0; j < WN; j++) {
+                                if (j >= jlo && j < jhi) {
+                                    const double bfj = *reinterpret_cast<const double*>(b_s + j * 1024 + xs[s]);
+#pragma unroll
+                                    for (int i = 0; i < WM; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bfj);
+                                }
                             }
                         }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
-    }
 
-    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        // epilogue of this tile
 #pragma unroll
-    for (int i = 0; i < WM; i++) {
-        const int m = m0 + wm * WM * 8 + i * 8 + g;
-        if (m >= p.M) continue;
+        for (int i = 0; i < WM; i++) {
+            const int m = m0 + wm * WM * 8 + i * 8 + g;
+            if (m >= p.M) continue;
 #pragma unroll
-        for (int j = 0; j < WN; j++) {
-            const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
-            if (n >= p.N) continue;
-            double v0 = p.alpha * acc[i][j][0];
-            double v1 = p.alpha * acc[i][j][1];
-            double* cp = p.C + (size_t)m * p.ldc + n;
-            const bool two = (n + 1 < p.N);
-            if (p.bias) {
-                v0 += p.bias[n];
-                if (two) v1 += p.bias[n + 1];
-            }
-            if (vec_ok && two) {
-                if (p.beta != 0.0) {
-                    double2 o = *reinterpret_cast<const double2*>(cp);
-                    v0 += p.beta * o.x;
-                    v1 += p.beta * o.y;
+            for (int j = 0; j < WN; j++) {
+                const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
+                if (n >= p.N) continue;
+                double v0 = p.alpha * acc[i][j][0];
+                double v1 = p.alpha * acc[i][j][1];
+                double* cp = p.C + (size_t)m * p.ldc + n;
+                const bool two = (n + 1 < p.N);
+                if (p.bias) {
+                    v0 += p.bias[n];
+                    if (two) v1 += p.bias[n + 1];
                 }
-                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
-            } else {
-                if (p.beta != 0.0) {
-                    v0 += p.beta * cp[0];
-                    if (two) v1 += p.beta * cp[1];
+                if (vec_ok && two) {
+                    if (p.beta != 0.0) {
+                        double2 o = *reinterpret_cast<const double2*>(cp);
+                        v0 += p.beta * o.x;
+                        v1 += p.beta * o.y;
+                    }
+                    *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+                } else {
+                    if (p.beta != 0.0) {
+                        v0 += p.beta * cp[0];
+                        if (two) v1 += p.beta * cp[1];
+                    }
+                    cp[0] = v0;
+                    if (two) cp[1] = v1;
                 }
-                cp[0] = v0;
-                if (two) cp[1] = v1;
             }
         }
     }
@@ -292,10 +332,13 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
+    p.paired = (mode == HTNK_GEMM_B_LOWER && p.tiles_n >= 2) ? 1 : 0;
+    const unsigned grid = p.paired ? (unsigned)p.tiles_m * (unsigned)((p.tiles_n + 1) / 2)
+                                   : (unsigned)p.tiles_m * (unsigned)p.tiles_n;
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
     if (cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
-    gemm_tma_kernel<<<(unsigned)p.tiles_m * (unsigned)p.tiles_n, NT, smem, st>>>(tmA, tmB, p);
+    gemm_tma_kernel<<<grid, NT, smem, st>>>(tmA, tmB, p);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }

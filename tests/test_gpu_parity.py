@@ -391,3 +391,42 @@ def test_potrf_wide_panels(h, n):
     assert np.abs(l @ l.T - a).max() < 2e-11
     assert np.abs(np.triu(l, 1)).max() == 0.0
     assert np.abs(x @ a - x0).max() < 1e-9          # x = x0 A^-1
+
+
+def test_edge_cases_empty_ragged_chunked(h, oracle):
+    """empty batch; independent problems too large for the one-CTA kernel (k > 128: one factorisation each);
+    device-resident seed array; a host-memory batch long enough to be drawn in several overlapped chunks
+    must equal the single-chunk device result bit for bit."""
+    import torch
+    c = cases.ht_case("k4_dense_64")
+    x, info = h.hyperplane_truncated_mvnorm_batch(0, c["mean"], c["cov"], c["g"], c["r"])
+    assert x.shape == (0, 64) and info.shape == (0,)
+    # independent, k = 150 > 128
+    rng = np.random.default_rng(8)
+    P, k, k2 = 3, 150, 2
+    cov = np.stack([cases.spd(rng, k) for _ in range(P)])
+    g = rng.standard_normal((P, k2, k))
+    r = rng.standard_normal((P, k2))
+    mu = rng.standard_normal((P, k))
+    x, info = h.hyperplane_truncated_mvnorm_batch(P, mu, cov, g, r, independent=True, seed0=4)
+    xo, io, _ = oracle.hyperplane("pcg64", P, mu, cov, g, r, independent=True, seed0=4)
+    assert np.array_equal(info, io) and rel_err(x, xo) < REL_TOL
+    # seeds on the device
+    dev = "cuda:0"
+    c = cases.ht_case("k7_dense_333")
+    t = [torch.from_numpy(np.ascontiguousarray(c[n_])).to(dev) for n_ in ("mean", "cov", "g", "r")]
+    seeds = rng.integers(0, 2**63, size=50, dtype=np.uint64)
+    xd, _ = h.hyperplane_truncated_mvnorm_batch(50, *t, seeds=torch.from_numpy(seeds.view(np.int64)).to(dev))
+    torch.cuda.synchronize()
+    xo, _, _ = oracle.hyperplane("pcg64", 50, c["mean"], c["cov"], c["g"], c["r"], seeds=seeds)
+    assert rel_err(xd.cpu().numpy(), xo) < REL_TOL
+    # chunked host path (3 chunks of 8192) == one device call
+    B = 20000
+    xh, ih = h.hyperplane_truncated_mvnorm_batch(B, c["mean"], c["cov"], c["g"], c["r"], seed0=77)
+    xdev, _ = h.hyperplane_truncated_mvnorm_batch(B, *t, seed0=77)
+    torch.cuda.synchronize()
+    assert np.array_equal(xh, xdev.cpu().numpy()) and not ih.any()
+    spot = rng.integers(0, B, size=16)
+    xo, _, _ = oracle.hyperplane("pcg64", 16, c["mean"], c["cov"], c["g"], c["r"],
+                                 seeds=(77 + spot).astype(np.uint64))
+    assert rel_err(xh[spot], xo) < REL_TOL
