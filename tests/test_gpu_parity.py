@@ -430,3 +430,72 @@ def test_edge_cases_empty_ragged_chunked(h, oracle):
     xo, _, _ = oracle.hyperplane("pcg64", 16, c["mean"], c["cov"], c["g"], c["r"],
                                  seeds=(77 + spot).astype(np.uint64))
     assert rel_err(xh[spot], xo) < REL_TOL
+
+
+def test_full_size_headline_properties(h, oracle):
+    """BASELINE headline size (k = 1000, k2 = 1, 65 536 samples, device-resident): size-independent properties
+    (constraint residual, sample mean of the projected distribution) plus a spot check of 6 samples against
+    the oracle."""
+    import torch
+    import bench
+    mean, cov, g, r = bench.make_inputs(np)
+    dev = "cuda:0"
+    t = [torch.from_numpy(x).to(dev) for x in (mean, cov, g, r)]
+    B = 1 << 16
+    x, info = h.hyperplane_truncated_mvnorm_batch(B, *t, seed0=12345)
+    torch.cuda.synchronize()
+    assert int((info != 0).sum()) == 0
+    resid = (x @ t[2].T - t[3]).abs().max().item()
+    assert resid < 1e-12 * max(1.0, x.abs().max().item()) * 10          # sum-to-zero constraint
+    # E[x] = mean + cov g^T (g cov g^T)^-1 (r - g mean)
+    cg = cov @ g.T
+    want = mean + (cg @ np.linalg.solve(g @ cg, r - g @ mean))
+    assert np.abs(x.mean(dim=0).cpu().numpy() - want).max() < 6 * np.sqrt(np.diag(cov).max() / B) + 1e-3
+    spot = np.array([0, 1, 31, 32, 40000, B - 1])
+    xo, _, _ = oracle.hyperplane("pcg64", len(spot), mean, cov, g, r, seeds=(12345 + spot).astype(np.uint64))
+    assert rel_err(x[spot].cpu().numpy(), xo) < REL_TOL
+
+
+def test_full_size_small_problems_properties(h, oracle):
+    """BASELINE configs[1] shape (k = 64, k2 = 4) on 2^16 independent problems: every problem satisfies its
+    own constraint, and 8 of them are checked against the oracle."""
+    import torch
+    dev = "cuda:0"
+    B, k, k2 = 1 << 16, 64, 4
+    rng = np.random.default_rng(21)
+    base = np.stack([cases.spd(rng, k) for _ in range(32)])
+    gen = torch.Generator(device=dev).manual_seed(5)
+    cov = torch.from_numpy(base).to(dev).repeat(B // 32, 1, 1).contiguous()
+    scale = 1.0 + torch.rand(B, 1, 1, dtype=torch.float64, device=dev, generator=gen)
+    cov = cov * scale                                             # distinct covariances
+    g = torch.randn(B, k2, k, dtype=torch.float64, device=dev, generator=gen)
+    r = torch.randn(B, k2, dtype=torch.float64, device=dev, generator=gen)
+    mu = torch.randn(B, k, dtype=torch.float64, device=dev, generator=gen)
+    x, info = h.hyperplane_truncated_mvnorm_batch(B, mu, cov, g, r, independent=True, seed0=12345)
+    torch.cuda.synchronize()
+    assert int((info != 0).sum()) == 0
+    resid = (torch.einsum("bck,bk->bc", g, x) - r).abs().max().item()
+    assert resid < 1e-11
+    spot = np.array([0, 1, 127, 128, 4097, 30000, 65534, 65535])
+    sel = torch.from_numpy(spot).to(dev)
+    xo, io, _ = oracle.hyperplane("pcg64", len(spot), mu[sel].cpu().numpy(), cov[sel].cpu().numpy(),
+                                  g[sel].cpu().numpy(), r[sel].cpu().numpy(), independent=True,
+                                  seeds=(12345 + spot).astype(np.uint64))
+    assert rel_err(x[sel].cpu().numpy(), xo) < REL_TOL
+
+
+def test_full_size_structured_spot_check(h, oracle):
+    """BASELINE configs[2] (p = 2000, n = 500, diagonal Omega, 4096 samples sharing A and Phi): 3 samples
+    against the oracle, all samples finite."""
+    rng = np.random.default_rng(2)
+    p, n, B = 2000, 500, 4096
+    a = cases.spd(rng, p)
+    phi = rng.standard_normal((n, p)) / np.sqrt(p)
+    om = np.diag(rng.uniform(0.5, 1.5, n))
+    mu = rng.standard_normal(p)
+    x, info = h.structured_precision_mvnorm_batch(B, mu, a, phi, om, False, 0, 1, seed0=12345)
+    assert not info.any() and np.isfinite(x).all()
+    spot = np.array([0, 2048, B - 1])
+    xo = oracle.structured("pcg64", len(spot), mu, a, phi, om, False, 0, 1,
+                           seeds=(12345 + spot).astype(np.uint64))[0]
+    assert rel_err(x[spot], xo) < REL_TOL
