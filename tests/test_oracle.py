@@ -10,10 +10,13 @@ from conftest import REL_TOL, rel_err
 
 
 def digest(*arrays):
-    h = hashlib.sha256()
+    """Fingerprint of the seeded inputs.  The builders go through BLAS (t @ t.T), whose last bit depends on
+    the CPU, so the fingerprint is a few float statistics compared with a tolerance, not a hash."""
+    out = []
     for a in arrays:
-        h.update(np.ascontiguousarray(a).tobytes())
-    return np.frombuffer(h.digest()[:8], dtype=np.uint64)[0]
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        out += [a.sum(), (a * a).sum(), a[::97].sum(), float(a.size)]
+    return np.array(out)
 
 
 # SURVEY.md section 8(c): known answers extracted from the compiled reference
@@ -60,7 +63,7 @@ def test_rng_golden(oracle, gold, gen):
 def test_hyperplane_golden(oracle, gold, name):
     c = cases.ht_case(name)
     g = gold["hyperplane"]
-    assert digest(c["mean"], c["cov"], c["g"], c["r"]) == g[name + "__digest"], "input builder drifted"
+    assert np.allclose(digest(c["mean"], c["cov"], c["g"], c["r"]), g[name + "__digest"], rtol=1e-10), "input builder drifted"
     x, info, rc = oracle.hyperplane(c["gen"], c["nsamples"], c["mean"], c["cov"], c["g"], c["r"],
                                     diag=c["diag"], seed0=c["seed0"])
     assert np.array_equal(info, g[name + "__info"])
@@ -71,7 +74,7 @@ def test_hyperplane_golden(oracle, gold, name):
 def test_hyperplane_independent_golden(oracle, gold):
     c = cases.ht_independent_case()
     g = gold["hyperplane"]
-    assert digest(c["mean"], c["cov"], c["g"], c["r"]) == g["independent__digest"]
+    assert np.allclose(digest(c["mean"], c["cov"], c["g"], c["r"]), g["independent__digest"], rtol=1e-10)
     x, info, rc = oracle.hyperplane(c["gen"], c["nsamples"], c["mean"], c["cov"], c["g"], c["r"],
                                     independent=True, seed0=c["seed0"])
     assert rc == 0 and not info.any()
@@ -82,7 +85,7 @@ def test_hyperplane_independent_golden(oracle, gold):
 def test_structured_golden(oracle, gold, name):
     c = cases.sp_case(name)
     g = gold["structured"]
-    assert digest(c["mean"], c["a"], c["phi"], c["omega"]) == g[name + "__digest"]
+    assert np.allclose(digest(c["mean"], c["a"], c["phi"], c["omega"]), g[name + "__digest"], rtol=1e-10)
     x, info, rc = oracle.structured(c["gen"], c["nsamples"], c["mean"], c["a"], c["phi"], c["omega"],
                                     c["struct_mean"], c["a_type"], c["o_type"], seed0=c["seed0"])
     assert np.array_equal(info, g[name + "__info"])

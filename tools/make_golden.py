@@ -23,10 +23,13 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def digest(*arrays):
-    h = hashlib.sha256()
+    """Fingerprint of the seeded inputs.  The builders go through BLAS (t @ t.T), whose last bit depends on
+    the CPU, so the fingerprint is a few float statistics compared with a tolerance, not a hash."""
+    out = []
     for a in arrays:
-        h.update(np.ascontiguousarray(a).tobytes())
-    return np.frombuffer(h.digest()[:8], dtype=np.uint64)[0]
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        out += [a.sum(), (a * a).sum(), a[::97].sum(), float(a.size)]
+    return np.array(out)
 
 
 def main():
