@@ -1,7 +1,7 @@
 // Shared-memory / register kernels of the blocked Cholesky and of the blocked triangular solves:
 //   potf2_kernel         factor one nb x nb (nb <= 128) diagonal block (dpotrf's unblocked base case;
 //                        reference call sites src/htnorm_distributions.c:77,115 via src/htnorm_blas.h:111)
-//   trsm_rows_kernel     panel solve L21 = A21 L11^-T, rows independent (no inverse needed)
+//   trsm_rows_kernel     panel solve L21 = A21 L11^-T on the tensor cores, rows independent
 //   trtri_batched_kernel inverse of every diagonal block at once, so that the many-right-hand-side
 //                        solves of the samplers (dtrsv / dposv / dpotri's solve phases,
 //                        src/htnorm_distributions.c:120, src/htnorm.c:169,210,330) become DMMA GEMMs
@@ -9,6 +9,7 @@
 // OpenBLAS do (reference tests/test_pyhtnorm.py:46-48, 91-95).
 //
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include "launchers.h"
 
@@ -31,6 +32,27 @@ __device__ __forceinline__ double fast_rsqrt(double x)
         y = fma(y, e, y);
     }
     return y;
+}
+
+// full 128 x 128 block global -> shared by 16-byte LDGSTS (every element in flight at once); partial blocks
+// (nb < 128) take the masked scalar path so that the padding stays zero
+__device__ __forceinline__ void load_block(double* S, const double* __restrict__ a, size_t ld, int nb, int tid,
+                                           bool mask_upper)
+{
+    if (nb == NB && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        for (int idx = tid; idx < NB * (NB / 2); idx += NT) {
+            const int r = idx >> 6, ch = idx & 63;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * LDB + 2 * ch);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(a + (size_t)r * ld + 2 * ch));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+    } else {
+        for (int idx = tid; idx < NB * NB; idx += NT) {
+            const int r = idx >> 7, c = idx & (NB - 1);
+            S[r * LDB + c] = (r < nb && c < nb && (!mask_upper || c <= r)) ? a[(size_t)r * ld + c] : 0.0;
+        }
+    }
 }
 
 // potf2: the 128 x 128 block is factorised in 16 column panels of width 8.
@@ -62,10 +84,9 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-        int r = idx >> 7, c = idx & (NB - 1);
-        S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : 0.0;
-    }
+    // the strictly upper part of a full block may hold junk (diagonal tiles of earlier trailing updates): it is
+    // never used - sub-block loads read c <= r, diagonal rows mask their result, the write-back masks too
+    load_block(S, a, ld, nb, tid, true);
     for (int idx = tid; idx < NB * LDP; idx += NT) P[idx] = 0.0;
     if (tid == 0) s_fail = 0;
     __syncthreads();
@@ -165,9 +186,9 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     }
     const bool failed = nfact < nb;
     // write L back: lower triangle, zeros above; nothing beyond a failed column is meaningful
-    for (int idx = tid; idx < nb * nb; idx += NT) {
-        int r = idx / nb, c = idx - r * nb;
-        a[(size_t)r * ld + c] = (c <= r && c < ((nfact + 7) & ~7)) ? S[r * LDB + c] : 0.0;
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        if (r < nb && c < nb) a[(size_t)r * ld + c] = (c <= r && c < ((nfact + 7) & ~7)) ? S[r * LDB + c] : 0.0;
     }
     if (rdiag_out != nullptr && !failed)
         for (int c = tid; c < nb; c += NT) rdiag_out[c] = rdiag[c];
@@ -231,60 +252,90 @@ trtri_batched_kernel(const double* __restrict__ f, size_t ld, int n, double* __r
     }
 }
 
-// ---- panel solve of the blocked Cholesky: X := X * L^-T for rows of a panel, rows independent ----
-// SIXTEEN threads per row: thread (row i, cq) keeps the residuals of columns c == cq (mod 16) in a rotating
-// window of 8 registers (R[0] = the 16-column group being solved); the solved entry travels to the other
-// 15 threads of the row by shuffle; L (the freshly factored diagonal block) sits in shared memory with an
-// odd row stride, so the 16 different rows a half-warp reads per step hit 16 different banks.
-// No block-level synchronisation after the load: rows never interact.  32 rows per CTA.
-constexpr int TR_ROWS = NT / 16;
-constexpr int LDT = NB + 1;
+// ---- panel solve of the blocked Cholesky: X := X * L^-T for the rows of a panel, on the tensor cores ----
+// A warp owns 8 rows and keeps their 128 entries as sixteen 8 x 8 DMMA accumulator tiles.  For each 8-column
+// block b: X_b = Acc_b * inv(L_bb)^T (two DMMAs with the 8 x 8 inverse computed once per CTA), X_b is final
+// and stored; then Acc_c -= X_b * L[c-block, b-block]^T for every later block c (two DMMAs each, fragments of
+// L straight from shared memory).  Accumulator -> A-fragment conversions are quad-local shuffles.  Rows never
+// interact: no block-level synchronisation after the load.  128 rows per CTA.
+constexpr int TR_ROWS = 128;
+constexpr int LDI = 12;
+__device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double& a0, double& a1)
+{
+    const int gq = lane & ~3, t4 = lane & 3;
+    const int s0 = gq + (t4 >> 1), s1 = gq + 2 + (t4 >> 1);
+    const double v0 = __shfl_sync(0xffffffffu, c0, s0), v1 = __shfl_sync(0xffffffffu, c1, s0);
+    const double w0 = __shfl_sync(0xffffffffu, c0, s1), w1 = __shfl_sync(0xffffffffu, c1, s1);
+    a0 = (t4 & 1) ? v1 : v0;  // element (row g, column t4)
+    a1 = (t4 & 1) ? w1 : w0;  // element (row g, column 4 + t4)
+}
+
 __global__ void __launch_bounds__(NT, 1)
 trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __restrict__ l, size_t ldl,
                  int nb, const double* __restrict__ rdiag_g)
 {
     extern __shared__ double sm[];
-    double* S = sm;                  // [NB][LDT] : L
-    double* rdiag = sm + NB * LDT;   // [NB]
-    const int tid = threadIdx.x;
-    const int i = tid >> 4, cq = tid & 15;
-    const int lane = tid & 31;
-    const size_t row = (size_t)blockIdx.x * TR_ROWS + i;
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-        int r = idx >> 7, c = idx & (NB - 1);
-        S[r * LDT + c] = (r < nb && c <= r) ? l[(size_t)r * ldl + c] : 0.0;
-    }
-    if (tid < NB) rdiag[tid] = tid < nb ? rdiag_g[tid] : 0.0;
+    double* S = sm;                  // [NB][LDB] : L (lower, zero-padded)
+    double* I8 = sm + NB * LDB;      // [16][8][LDI] : inverses of the 8 x 8 diagonal blocks
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    (void)rdiag_g;
+    load_block(S, l, ldl, nb, tid, true);  // potf2 left zeros above the diagonal
     __syncthreads();
+    {   // warp w inverts diagonal block w: lane c < 8 solves L_bb y = e_c
+        const int j0 = 8 * warp;
+        if (lane < 8) {
+            double y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                double v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+                    if (t < i) v = fma(-S[(j0 + i) * LDB + j0 + t], y[t], v);
+                const double d = (j0 + i < nb) ? S[(j0 + i) * LDB + j0 + i] : 1.0;
+                y[i] = v / d;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) I8[(warp * 8 + i) * LDI + lane] = y[i];
+        }
+    }
+    __syncthreads();
+
+    const size_t r0 = (size_t)blockIdx.x * TR_ROWS + warp * 8;
+    const size_t row = r0 + g;
     const bool live = row < (size_t)nrows;
     double* xr = x + (live ? row : 0) * ldx;
-    double R[8];
+    double acc[16][2];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int c = cq + 16 * u;
-        R[u] = (live && c < nb) ? xr[c] : 0.0;
+    for (int t = 0; t < 16; t++) {
+        const int c = 8 * t + 2 * t4;
+        acc[t][0] = (live && c < nb) ? xr[c] : 0.0;
+        acc[t][1] = (live && c + 1 < nb) ? xr[c + 1] : 0.0;
     }
-    const int ngroups = (nb + 15) >> 4;
-    for (int jj = 0; jj < ngroups; jj++) {
-        const int c0 = cq + 16 * jj;
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int t = 16 * jj + q;  // column being solved (uniform)
-            // x_t = residual_t / L[t][t], owned by the row's thread cq == q.  Columns t >= nb have
-            // rdiag = 0 and zero rows of L: they solve to 0 and change nothing.
-            double xt = R[0] * rdiag[t];
-            xt = __shfl_sync(0xffffffffu, xt, (lane & 16) | q);
-            if (cq == q) R[0] = xt;
-            else if (cq > q) R[0] = fma(-xt, S[c0 * LDT + t], R[0]);
+    for (int b = 0; b < 16; b++) {
+        if (8 * b < nb) {  // uniform
+            double a0, a1;
+            c_to_a(acc[b][0], acc[b][1], lane, a0, a1);
+            double x0 = 0.0, x1 = 0.0;
+            dmma_sub(x0, x1, a0, I8[(b * 8 + g) * LDI + t4]);
+            dmma_sub(x0, x1, a1, I8[(b * 8 + g) * LDI + 4 + t4]);
+            const int c = 8 * b + 2 * t4;
+            if (live && c < nb) xr[c] = x0;
+            if (live && c + 1 < nb) xr[c + 1] = x1;
+            double xa0, xa1;
+            c_to_a(x0, x1, lane, xa0, xa1);
+            xa0 = -xa0;
+            xa1 = -xa1;
 #pragma unroll
-            for (int u = 1; u < 8; u++) {
-                if (jj + u < 8) R[u] = fma(-xt, S[(c0 + 16 * u) * LDT + t], R[u]);  // uniform guard
+            for (int tc = b + 1; tc < 16; tc++) {
+                if (8 * tc < nb) {  // uniform
+                    const double* lr = S + (tc * 8 + g) * LDB + 8 * b + t4;
+                    dmma_sub(acc[tc][0], acc[tc][1], xa0, lr[0]);
+                    dmma_sub(acc[tc][0], acc[tc][1], xa1, lr[4]);
+                }
             }
         }
-        if (live && c0 < nb) xr[c0] = R[0];
-#pragma unroll
-        for (int u = 0; u < 7; u++) R[u] = R[u + 1];
-        R[7] = 0.0;
     }
 }
 
@@ -319,7 +370,7 @@ extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows,
 {
     if (nrows <= 0 || nb <= 0) return 0;
     if (nb > NB) return -202;
-    const size_t smem = (size_t)(NB * LDT + NB) * sizeof(double);
+    const size_t smem = (size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double);
     if (cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     trsm_rows_kernel<<<(nrows + TR_ROWS - 1) / TR_ROWS, NT, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
