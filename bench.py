@@ -225,13 +225,13 @@ def main():
     t_wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
-        step(args.warmup + i)
-        phases.append(h.phase_timing())     # reads events of THIS step (syncs on its last mark)
+        step(args.warmup + i)               # phase marks are CUDA events: recorded per step, read after the loop
     e1.record()
     barrier()
     launches = h.launch_count() - launches0
     t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    phases = [h.phase_timing()]             # per-phase averages over the timed steps
     h.phase_timing(False)
     clk = None
     if rank == 0:
@@ -299,7 +299,8 @@ def main():
                 "peak_source": "in-run DMMA (mma.sync m8n8k4 f64) microbenchmark, htn_fp64_tensor_peak_tflops; "
                                "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs=%s)" % measured.get("hbm_gbs"),
                 "kernel_ms": gemm_avg,
-                "step_phases_ms": {k_: sum(p[k_] for p in phases) / len(phases) for k_ in phases[0]}}
+                "step_phases_ms": {k_: v for k_, v in phases[0].items() if k_ != "calls"},
+                "kernel_launches_timed": phases[0]["calls"]}
         traffic_path = os.path.join(ROOT, "profiles", "gemm_traffic_bytes.json")
         if os.path.exists(traffic_path):
             roof["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")

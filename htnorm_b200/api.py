@@ -337,11 +337,11 @@ def fp64_fma_peak_tflops(device=-1, ms=50.0):
 
 
 def phase_timing(enable=None):
-    """enable/disable the CUDA-event phase marks, or (enable=None) read the last call's phases in ms:
-    dict(setup, normals, coeff, gemm)."""
+    """enable/disable the CUDA-event phase marks, or (enable=None) read the per-phase AVERAGES in ms over the
+    calls made since it was enabled: dict(setup, normals, coeff, gemm, calls)."""
     if enable is not None:
         lib.htn_phase_timing_enable(int(bool(enable)))
         return None
     ms = (C.c_double * 8)()
-    lib.htn_phase_timing_get(ms, 8)
-    return dict(setup=ms[0], normals=ms[1], coeff=ms[2], gemm=ms[3])
+    ncalls = lib.htn_phase_timing_get(ms, 8)
+    return dict(setup=ms[0], normals=ms[1], coeff=ms[2], gemm=ms[3], calls=ncalls)

@@ -110,45 +110,66 @@ void htn_dfree(htn_ctx_t* ctx, void* p)
     if (p) cudaFreeAsync(p, ctx->stream);
 }
 
-/* ---- optional phase timing (CUDA events on the caller's stream; off by default) ---- */
-#define HTN_PROF_SLOTS 8
+/* ---- optional phase timing (CUDA events on the caller's stream; off by default) ----
+ * Every call of the shared-covariance hyperplane path records one SET of marks; up to HTN_PROF_SETS sets are
+ * kept since the facility was enabled, so a benchmark loop can run without synchronising per step and read
+ * the per-phase averages afterwards. */
+#define HTN_PROF_SLOTS 5
+#define HTN_PROF_SETS 256
 static int g_prof_on = 0;
-static cudaEvent_t g_prof_ev[HTN_PROF_SLOTS];
-static int g_prof_set[HTN_PROF_SLOTS];
-static int g_prof_dev = -1;
+static cudaEvent_t g_prof_ev[HTN_PROF_SETS][HTN_PROF_SLOTS];
+static unsigned char g_prof_set[HTN_PROF_SETS][HTN_PROF_SLOTS];
+static int g_prof_created = 0, g_prof_dev = -1, g_prof_cur = -1;
 
 void htn_phase_timing_enable(int on)
 {
     g_prof_on = on;
-    if (!on) memset(g_prof_set, 0, sizeof(g_prof_set));
+    g_prof_cur = -1;
+    memset(g_prof_set, 0, sizeof(g_prof_set));
 }
 
 void htn_prof_mark(htn_ctx_t* ctx, int slot)
 {
     if (!g_prof_on || slot < 0 || slot >= HTN_PROF_SLOTS) return;
-    if (g_prof_dev != ctx->device) { /* events belong to a device: (re)create them here */
-        for (int i = 0; i < HTN_PROF_SLOTS; i++) {
-            cudaEventCreate(&g_prof_ev[i]);
-            g_prof_set[i] = 0;
-        }
+    if (g_prof_dev != ctx->device || !g_prof_created) { /* events belong to a device: (re)create them here */
+        for (int s = 0; s < HTN_PROF_SETS; s++)
+            for (int i = 0; i < HTN_PROF_SLOTS; i++) cudaEventCreate(&g_prof_ev[s][i]);
+        memset(g_prof_set, 0, sizeof(g_prof_set));
+        g_prof_created = 1;
         g_prof_dev = ctx->device;
+        g_prof_cur = -1;
     }
-    if (cudaEventRecord(g_prof_ev[slot], ctx->stream) == cudaSuccess) g_prof_set[slot] = 1;
+    if (slot == 0) { /* a new call: next set (the ring overwrites the oldest) */
+        g_prof_cur = (g_prof_cur + 1) % HTN_PROF_SETS;
+        memset(g_prof_set[g_prof_cur], 0, HTN_PROF_SLOTS);
+    }
+    if (g_prof_cur < 0) return;
+    if (cudaEventRecord(g_prof_ev[g_prof_cur][slot], ctx->stream) == cudaSuccess) g_prof_set[g_prof_cur][slot] = 1;
 }
 
-/* ms[i] = time between mark i and mark i+1 of the last call (after synchronising on the later event);
- * -1 where a mark is missing.  Returns the number of intervals written (nslots - 1). */
+/* ms[i] = AVERAGE over the recorded calls of the time between mark i and mark i+1 (after synchronising on
+ * the events); -1 where no call has both marks.  Returns the number of calls averaged. */
 int htn_phase_timing_get(double* ms, int n)
 {
-    int w = 0;
-    for (int i = 0; i + 1 < HTN_PROF_SLOTS && i < n; i++, w++) {
-        ms[i] = -1.0;
-        if (g_prof_set[i] && g_prof_set[i + 1]) {
-            float t = 0;
-            if (cudaEventSynchronize(g_prof_ev[i + 1]) == cudaSuccess &&
-                cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]) == cudaSuccess)
-                ms[i] = t;
+    int ncalls = 0;
+    double sum[HTN_PROF_SLOTS - 1];
+    int cnt[HTN_PROF_SLOTS - 1];
+    for (int i = 0; i < HTN_PROF_SLOTS - 1; i++) { sum[i] = 0.0; cnt[i] = 0; }
+    for (int s = 0; s < HTN_PROF_SETS; s++) {
+        int any = 0;
+        for (int i = 0; i + 1 < HTN_PROF_SLOTS; i++) {
+            if (g_prof_set[s][i] && g_prof_set[s][i + 1]) {
+                float t = 0;
+                if (cudaEventSynchronize(g_prof_ev[s][i + 1]) == cudaSuccess &&
+                    cudaEventElapsedTime(&t, g_prof_ev[s][i], g_prof_ev[s][i + 1]) == cudaSuccess) {
+                    sum[i] += t;
+                    cnt[i]++;
+                    any = 1;
+                }
+            }
         }
+        ncalls += any;
     }
-    return w;
+    for (int i = 0; i < n; i++) ms[i] = (i < HTN_PROF_SLOTS - 1 && cnt[i]) ? sum[i] / cnt[i] : -1.0;
+    return ncalls;
 }

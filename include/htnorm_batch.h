@@ -87,9 +87,10 @@ unsigned long long htn_launch_count(void); /* kernels this library has launched 
 const char* htn_version(void);
 
 /* Optional phase timing of the shared-covariance hyperplane path: when enabled, CUDA events are recorded
- * on the call's stream at the phase boundaries; htn_phase_timing_get writes the milliseconds of
- * [0] setup (factorisation etc.), [1] normal generation, [2] W z + coefficient solve, [3] the sampling
- * GEMM of the LAST chunk of the last call (-1 where unavailable) and returns the count written. */
+ * on the call's stream at the phase boundaries of every call (up to 256 calls are kept, no synchronisation);
+ * htn_phase_timing_get synchronises on them and writes the AVERAGE milliseconds of [0] setup (factorisation
+ * etc.), [1] exposed wait for the normals, [2] W z + coefficient solve, [3] the sampling GEMM (-1 where
+ * unavailable; with several chunks per call the last chunk counts) and returns the number of calls averaged. */
 void htn_phase_timing_enable(int on);
 int htn_phase_timing_get(double* ms, int n);
 
