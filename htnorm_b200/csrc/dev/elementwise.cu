@@ -286,6 +286,21 @@ extern "C" int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const
     return status();
 }
 
+namespace {
+__global__ void fill_info_kernel(int* p, size_t n, const int* codes)
+{
+    const int v = codes[0] ? codes[0] : codes[1];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+}  // namespace
+extern "C" int htnk_fill_info(cudaStream_t st, int* p, size_t n, const int* codes)
+{
+    if (n == 0) return 0;
+    fill_info_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, codes);
+    return status();
+}
+
 extern "C" int htnk_fill_i32(cudaStream_t st, int* p, size_t n, int v)
 {
     if (n == 0) return 0;

@@ -41,6 +41,7 @@ struct GemmParams {
     size_t lda, ldb, ldc;
     int mode, ktri, kext0;
     int tiles_m, tiles_n;
+    const int* skip;  // device flag: non-zero turns the launch into a no-op
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes)
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
     double* sA = smem;
     double* sB = smem + STAGES * A_STAGE;
 
+    if (p.skip != nullptr && *p.skip != 0) return;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -256,6 +258,10 @@ int launch(cudaStream_t st, const GemmParams& p)
 
 }  // namespace
 
+// one-shot guard for the NEXT htnk_gemm_tn launch of this thread: the kernel returns at once when *flag != 0
+static thread_local const int* g_next_skip = nullptr;
+extern "C" void htnk_gemm_guard_next(const int* flag) { g_next_skip = flag; }
+
 // wide-N configuration: 64 (default) or an experimental one selected with HTN_GEMM_WIDE
 static int wide_config()
 {
@@ -292,6 +298,8 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     p.A = A; p.B = B; p.C = C; p.bias = bias;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
+    p.skip = g_next_skip;
+    g_next_skip = nullptr;
     p.tiles_m = tiles_m;
     const int bn_cols = bn >= 128 ? 128 : (bn >= 64 ? 64 : bn);
     p.tiles_n = (N + bn_cols - 1) / bn_cols;
@@ -299,7 +307,7 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     switch (bn) {
         case 128: return launch<128, 2, 4, 8, 4, 1>(st, p);
         case 70: {  // TMA + mbarrier ring (gemm_tma.cu); falls back if a tensor map cannot be built
-            int r = htnk_gemm_tn_tma(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, mode, ktri, kext0);
+            int r = htnk_gemm_tn_tma(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, mode, ktri, kext0, p.skip);
             if (r != 1) return r;
             return launch<64, 2, 2, 8, 4, 2>(st, p);
         }

@@ -32,6 +32,7 @@ struct TmaGemmParams {
     size_t ldc;
     int mode, ktri, kext0;
     int tiles_m, tiles_n;
+    const int* skip;  // device flag: a non-zero value turns the launch into a no-op (failed factorisation)
     int paired;  // B_LOWER: one CTA runs the N tiles (tiles_n-1-q, q) of a row slab back to back
 };
 
@@ -120,6 +121,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
     uint64_t* empty = full + STAGES;
 
+    if (p.skip != nullptr && *p.skip != 0) return;  // uniform: the factor this GEMM would read is invalid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const int bid = blockIdx.x;
@@ -316,7 +318,7 @@ bool make_map(CUtensorMap* map, const double* ptr, size_t ld, int rows, int cols
 // returns 1 if the TMA path cannot be used for these operands (caller falls back to the cp.async kernel)
 extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
                                 const double* B, size_t ldb, double beta, double* C, size_t ldc,
-                                const double* bias, int mode, int ktri, int kext0)
+                                const double* bias, int mode, int ktri, int kext0, const int* skip)
 {
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) ||
@@ -329,6 +331,7 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     p.alpha = alpha; p.beta = beta;
     p.C = C; p.bias = bias; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
+    p.skip = skip;
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;

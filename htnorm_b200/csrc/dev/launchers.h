@@ -64,7 +64,9 @@ int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, const doubl
 /* TMA-fed variant for wide N (gemm_tma.cu); returns 1 when the operands do not admit a tensor map */
 int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
                      const double* B, size_t ldb, double beta, double* C, size_t ldc, const double* bias,
-                     int mode, int ktri, int kext0);
+                     int mode, int ktri, int kext0, const int* skip);
+/* one-shot guard: the NEXT htnk_gemm_tn launch of this thread becomes a no-op on the device if *flag != 0 */
+void htnk_gemm_guard_next(const int* flag);
 
 /* ---- factorisation building blocks (chol.cu) ---- */
 /* Factor the nb x nb (nb <= 128) diagonal block at a (row-major, ld) in place: lower triangle := L,
@@ -103,6 +105,8 @@ int htnk_diag_extract(cudaStream_t st, const double* a, size_t lda, int n, int o
 /* m[i*ld + i] += (or =) v[i] / constant */
 int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const double* v, double cval);
 int htnk_fill_i32(cudaStream_t st, int* p, size_t n, int v);
+/* p[i] = codes[0] ? codes[0] : codes[1]  (codes: two device ints, e.g. chol(cov) and chol(G cov G^T)) */
+int htnk_fill_info(cudaStream_t st, int* p, size_t n, const int* codes);
 /* y[c] = r[c] - sum_i g[c][i] * mean[i]   (k2 rows) */
 int htnk_r_minus_gmean(cudaStream_t st, const double* g, size_t ldg, int k2, int k, const double* mean,
                        const double* r, double* y);

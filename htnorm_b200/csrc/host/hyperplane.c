@@ -29,6 +29,11 @@ int htn_ht_last_cov_failed(void) { return g_cov_failed; }
 /* Host-memory batches: the wrapper points this at the caller's output array; the shared dense path then
  * draws in chunks and copies each finished chunk device -> host on its own stream WHILE the next chunk is in
  * the sampling GEMM (the PCIe copy of the samples is the longest leg of a host-to-host call). */
+/* Device-memory batches run fully asynchronously: the LAPACK codes stay on the device, the sampling GEMM is
+ * guarded by them, and the per-sample info array is filled by a kernel.  Host-memory callers (which must
+ * leave `out` untouched on failure and return the code) set this and get the synchronous behaviour. */
+static _Thread_local int g_need_codes = 1;
+static _Thread_local int* g_async_info_out = NULL;
 static _Thread_local double* g_host_sink = NULL;
 static _Thread_local int g_host_sink_used = 0;
 #define SINK_CHUNK 8192
@@ -171,8 +176,11 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_TRY(htnk_transpose(st, WT, k2p, k, k2, W, kp));
 
     int h_info[2] = {0, 0};
-    HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
-    HTN_CUDA(cudaStreamSynchronize(st));
+    const int async = !g_need_codes && k2 <= ALPHA_K2_MAX && g_async_info_out != NULL;
+    if (!async) {
+        HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
+        HTN_CUDA(cudaStreamSynchronize(st));
+    }
     if (h_info[0]) { /* cov not positive definite: no draw, out untouched (src/htnorm_distributions.c:78) */
         *first_info = h_info[0];
         g_cov_failed = 1;
@@ -201,7 +209,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
             /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
             HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Zc, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
             if (k2 <= ALPHA_K2_MAX) {
-                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, NULL, Zc, ldz, kp));
+                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, async ? d_info + 1 : NULL, Zc, ldz, kp));
             } else {
                 HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
                 HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Zc + kp, ldz, NULL));
@@ -209,6 +217,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         }
         htn_prof_mark(ctx, 3);
         /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
+        if (async) htnk_gemm_guard_next(d_info); /* cov not PD: the launch is a no-op, out stays untouched */
         HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Zc, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
                              (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 0));
         HTN_CUDA(cudaEventRecord(ev_gemm[buf], st));
@@ -223,6 +232,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         HTN_CUDA(cudaStreamSynchronize(copy_st));
         g_host_sink_used = 1;
     }
+    if (async) HTN_TRY(htnk_fill_info(st, g_async_info_out, nsamples, d_info));
 done:
     /* never free a buffer the side stream may still be writing */
     if (rng_pending >= 0 && ev_rng[rng_pending]) cudaStreamWaitEvent(st, ev_rng[rng_pending], 0);
@@ -383,7 +393,7 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
         rc = ht_shared_diag(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
     else
         rc = ht_shared_dense(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
-    if (!rc && d_info_out) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
+    if (!rc && d_info_out && !(g_async_info_out && !diag)) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
 done:
     return rc;
 }
@@ -438,8 +448,13 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     int first = 0;
     htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL, NULL};
     if (b->mem == HTN_MEM_DEVICE) {
+        /* asynchronous: nothing in this branch waits for the device (shared dense inputs, k2 <= 16, info given) */
+        g_need_codes = 0;
+        g_async_info_out = (!b->independent && !conf->diag && k2 <= ALPHA_K2_MAX) ? info : NULL;
         rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
                            conf->diag, out, info, &first);
+        g_need_codes = 1;
+        g_async_info_out = NULL;
         int rc2 = htn_ctx_end(&ctx, 0);
         return rc ? rc : rc2;
     }

@@ -314,6 +314,30 @@ def test_device_pointer_path_and_shard_invariance(h):
     assert torch.equal(torch.cat(parts), full)
 
 
+def test_device_mode_failures_are_reported_without_host_sync(h):
+    """Device-memory batches never wait for the GPU: the LAPACK codes stay on the device, guard the sampling
+    GEMM and fill the info array.  Same outcomes as the host path."""
+    import torch
+    dev = "cuda:0"
+    k = 40
+    z = lambda *s_: torch.zeros(*s_, dtype=torch.float64, device=dev)
+    out = torch.full((3, k), 7.0, dtype=torch.float64, device=dev)
+    x, info = h.hyperplane_truncated_mvnorm_batch(3, z(k), z(k, k), torch.ones(2, k, dtype=torch.float64, device=dev),
+                                                  z(2), out=out, raise_on_error=False)
+    torch.cuda.synchronize()
+    assert info.cpu().tolist() == [1, 1, 1] and bool((out == 7.0).all())
+    # G cov G^T singular: info 2, the unprojected y comes back -- identical to the host-memory call
+    cov = 4.0 * np.eye(16)
+    g = np.ones((2, 16))
+    xd, infod = h.hyperplane_truncated_mvnorm_batch(5, torch.zeros(16, dtype=torch.float64, device=dev),
+                                                    torch.from_numpy(cov).to(dev), torch.from_numpy(g).to(dev),
+                                                    z(2), raise_on_error=False, seed0=9)
+    xh, infoh = h.hyperplane_truncated_mvnorm_batch(5, np.zeros(16), cov, g, np.zeros(2), raise_on_error=False, seed0=9)
+    torch.cuda.synchronize()
+    assert infod.cpu().tolist() == infoh.tolist() == [2] * 5
+    assert np.array_equal(xd.cpu().numpy(), xh)
+
+
 def test_colmajor_flag_matches_reference_colmajor_build(h):
     """HTN_FLAG_COLMAJOR == the reference compiled with -DHTNORM_COLMAJOR (its R binding, src/Makevars:1):
     g / phi column-major.  Golden vectors come from that build (tools/make_golden.py)."""
