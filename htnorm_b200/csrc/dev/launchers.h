@@ -45,6 +45,8 @@ typedef struct {
 
 int htnk_raw_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, size_t nwords, uint64_t* out);
 /* nseg = 1 or 2 segments drawn back to back from each stream; ndraws: u32 per stream or NULL */
+/* one-shot hint: the NEXT htnk_normal_fill of this thread overlaps other kernels and leaves some SMs to them */
+void htnk_normal_fill_shares_device_next(void);
 int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, int nseg,
                      const htnk_segment_t* seg, uint32_t* ndraws);
 

@@ -79,12 +79,13 @@ static __device__ const uint64_t zig_table[768] = {
 #include "../common/zig_tables_u64.inc"
 };
 
-// copy ki (u64) and wi (f64) into shared memory; call from all threads, then __syncthreads()
-__device__ __forceinline__ void zig_stage_tables(uint64_t* s_ki, double* s_wi)
+// copy ki (u64), wi (f64) and fi (f64) into shared memory; call from all threads, then __syncthreads()
+__device__ __forceinline__ void zig_stage_tables(uint64_t* s_ki, double* s_wi, double* s_fi)
 {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         s_ki[i] = zig_table[i];
         s_wi[i] = __longlong_as_double((long long)zig_table[256 + i]);
+        s_fi[i] = __longlong_as_double((long long)zig_table[512 + i]);
     }
 }
 
@@ -109,15 +110,17 @@ __device__ __forceinline__ bool zig_fast(uint64_t r, const uint64_t* __restrict_
     // OR + one subtraction instead of the multi-instruction I2F.F64.U64
     const double rd = __dadd_rn(__longlong_as_double((long long)(d.rabs | 0x4330000000000000ULL)),
                                 -4503599627370496.0);
-    double x = __dmul_rn(rd, s_wi[d.idx]);
-    d.x = sign ? -x : x;
+    const double x = __dmul_rn(rd, s_wi[d.idx]);
+    // sign ? -x : x  as one integer XOR on the high word (identical bits, -0.0 included)
+    d.x = __hiloint2double(__double2hiint(x) ^ (int)((uint32_t)sign << 31), __double2loint(x));
     return d.rabs < s_ki[d.idx];
 }
 
 // slow path for a rejected fast draw (src/htnorm_distributions.c:38-52).  Returns true and sets z
 // when a normal is produced; false when the wedge test rejects (caller draws a fresh word).
 template <int GEN>
-__device__ __forceinline__ bool zig_slow(GenState& g, const ZigDraw& d, double& z, uint32_t& ncalls)
+__device__ __forceinline__ bool zig_slow(GenState& g, const ZigDraw& d, double& z, uint32_t& ncalls,
+                                         const double* __restrict__ s_fi = nullptr)
 {
     if (d.idx == 0) {
         for (;;) {
@@ -133,17 +136,24 @@ __device__ __forceinline__ bool zig_slow(GenState& g, const ZigDraw& d, double& 
             }
         }
     }
-    double f1 = __longlong_as_double((long long)zig_table[512 + d.idx - 1]);
-    double f0 = __longlong_as_double((long long)zig_table[512 + d.idx]);
+    double f1 = s_fi ? s_fi[d.idx - 1] : __longlong_as_double((long long)zig_table[512 + d.idx - 1]);
+    double f0 = s_fi ? s_fi[d.idx] : __longlong_as_double((long long)zig_table[512 + d.idx]);
     double u = u64_to_unit(gen_next<GEN>(g));
     ncalls += 1;
-    double lhs = __dadd_rn(__dmul_rn(__dadd_rn(f1, -f0), u), f0);
-    double rhs = exp(__dmul_rn(__dmul_rn(-0.5, d.x), d.x));
-    if (lhs < rhs) {
-        z = d.x;
-        return true;
-    }
-    return false;
+    const double lhs = __dadd_rn(__dmul_rn(__dadd_rn(f1, -f0), u), f0);
+    const double arg = __dmul_rn(__dmul_rn(-0.5, d.x), d.x);
+    // The decision is lhs < exp(arg).  A single-precision exp2 brackets exp(arg) to ~1e-6 relative
+    // (|arg| < 6.7: 4e-7 from rounding arg * log2(e) to float, 2.4e-7 from ex2.approx); outside a 1e-5 band the
+    // comparison is already decided and the 45-instruction double exp() is skipped (it runs for ~0.2 % of the
+    // wedge tests).  Inside the band the full-precision test below decides, exactly as before.
+    const float e32 = exp2f((float)(arg * 1.4426950408889634));
+    const double lo = (double)e32 * (1.0 - 1e-5), hi = (double)e32 * (1.0 + 1e-5);
+    bool accept;
+    if (lhs < lo) accept = true;
+    else if (lhs > hi) accept = false;
+    else accept = lhs < exp(arg);
+    if (accept) z = d.x;
+    return accept;
 }
 
 // load the initial state of stream b

@@ -13,6 +13,7 @@
 // catch-up of parked lanes at tile boundaries cost 2.1x the iterations (ncu: 21 of 32 lanes active), so
 // the simpler lockstep loop is both faster and smaller.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "launchers.h"
 #include "rng.cuh"
@@ -21,9 +22,7 @@ namespace {
 
 using namespace htn;
 
-constexpr int kWarpsPerBlock = 16;   // 512 threads: one CTA per SM (135 KB of staging tiles)
-constexpr int kMaxBlocks = 128;      // leave SMs free: the generator overlaps the factorisation kernels
-constexpr int kTile = 32;
+constexpr int kMaxBlocks = 128;      // overlapped launches leave SMs free for the factorisation kernels
 
 template <int GEN>
 __global__ void __launch_bounds__(128) raw_fill_kernel(const uint64_t* seeds, uint64_t seed0,
@@ -47,16 +46,18 @@ struct Seg {
     const double* add;
 };
 
-template <int GEN>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
+// kWarpsPerBlock warps per CTA (one CTA per SM), each staging a 32-stream x kTile-element tile
+template <int GEN, int kWarpsPerBlock, int kTile>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kWarpsPerBlock >= 16 ? 1 : 16 / kWarpsPerBlock)
 normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size_t nstreams, int nseg,
                    Seg seg0, Seg seg1, uint32_t* ndraws)
 {
     extern __shared__ double s_dyn[];
     uint64_t* s_ki = reinterpret_cast<uint64_t*>(s_dyn);
     double* s_wi = s_dyn + 256;
-    double(*s_tile)[kTile][kTile + 1] = reinterpret_cast<double(*)[kTile][kTile + 1]>(s_dyn + 512);
-    zig_stage_tables(s_ki, s_wi);
+    double* s_fi = s_dyn + 512;
+    double(*s_tile)[32][kTile + 1] = reinterpret_cast<double(*)[32][kTile + 1]>(s_dyn + 768);
+    zig_stage_tables(s_ki, s_wi, s_fi);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -72,10 +73,12 @@ normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size
 
     GenState g;
     uint32_t ncalls = 0;
-    if (live) stream_begin<GEN>(g, seeds, seed0, states, b);
+    // lanes past the last stream replay the last one (their results are never stored): no per-draw liveness test
+    stream_begin<GEN>(g, seeds, seed0, states, live ? b : nstreams - 1);
 
     for (int sgi = 0; sgi < nseg; sgi++) {
         const Seg sg = sgi == 0 ? seg0 : seg1;
+        const bool plain = !sg.div && !sg.mul && !sg.add;
         for (size_t pos0 = 0; pos0 < sg.n; pos0 += kTile) {
             const int cnt = (int)((sg.n - pos0) < (size_t)kTile ? (sg.n - pos0) : (size_t)kTile);
             // Lanes advance in lockstep: iteration t produces the (pos0 + t)-th normal of EVERY stream of
@@ -83,34 +86,44 @@ normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size
             // the warp runs the wedge / tail test for those lanes right there (the other lanes idle for
             // that one divergent region) - the stream cannot advance past an unresolved test.
             for (int t = 0; t < cnt; t++) {
-                if (live) {
-                    double z;
-                    for (;;) {
-                        ZigDraw d;
-                        const uint64_t r = gen_next<GEN>(g);
-                        ncalls++;
-                        if (zig_fast(r, s_ki, s_wi, d)) { z = d.x; break; }
-                        if (zig_slow<GEN>(g, d, z, ncalls)) break;
-                    }
-                    tile[lane][t] = z;
+                double z;
+                for (;;) {
+                    ZigDraw d;
+                    const uint64_t r = gen_next<GEN>(g);
+                    ncalls++;
+                    if (zig_fast(r, s_ki, s_wi, d)) { z = d.x; break; }
+                    if (zig_slow<GEN>(g, d, z, ncalls, s_fi)) break;
                 }
+                tile[lane][t] = z;
             }
             __syncwarp();
-            // write-out: row rr of the tile = stream warp_base + rr; lane t holds draw pos0 + t
-            const int t = lane;
+            // write-out: row rr of the tile = stream warp_base + rr; lane (rsub, t) holds draw pos0 + t of the rows
+            // rr = rsub, rsub + 32 / kTile, ...: every store instruction writes 32 / kTile runs of kTile doubles
+            constexpr int kRowsPerStore = 32 / kTile;
+            const int t = lane % kTile, rsub = lane / kTile;
             if (t < cnt) {
                 const size_t i = sg.n - 1 - (pos0 + (size_t)t);
-                double dv = sg.div ? sg.div[i] : 1.0;
-                double mv = sg.mul ? sg.mul[i] : 1.0;
-                double av = sg.add ? sg.add[i] : 0.0;
-                for (int rr = 0; rr < 32; rr++) {
-                    const size_t bb = warp_base + rr;
-                    if (bb >= nstreams) break;
-                    double v = tile[rr][t];
-                    if (sg.div) v = __ddiv_rn(v, dv);
-                    if (sg.mul) v = __dmul_rn(v, mv);
-                    if (sg.add) v = __dadd_rn(av, v);
-                    sg.out[bb * sg.ld + i] = v;
+                const int nrows = (int)(nstreams - warp_base < 32 ? nstreams - warp_base : 32);
+                double* op = sg.out + (warp_base + rsub) * sg.ld + i;
+                const size_t ostep = (size_t)kRowsPerStore * sg.ld;
+                if (plain) {  // the common case: 3 instructions per stored element
+                    if (nrows == 32) {
+#pragma unroll 8
+                        for (int rr = rsub; rr < 32; rr += kRowsPerStore, op += ostep) *op = tile[rr][t];
+                    } else {
+                        for (int rr = rsub; rr < nrows; rr += kRowsPerStore, op += ostep) *op = tile[rr][t];
+                    }
+                } else {
+                    const double dv = sg.div ? sg.div[i] : 1.0;
+                    const double mv = sg.mul ? sg.mul[i] : 1.0;
+                    const double av = sg.add ? sg.add[i] : 0.0;
+                    for (int rr = rsub; rr < nrows; rr += kRowsPerStore, op += ostep) {
+                        double v = tile[rr][t];
+                        if (sg.div) v = __ddiv_rn(v, dv);
+                        if (sg.mul) v = __dmul_rn(v, mv);
+                        if (sg.add) v = __dadd_rn(av, v);
+                        *op = v;
+                    }
                 }
             }
             __syncwarp();
@@ -166,9 +179,27 @@ extern "C" int htnk_raw_fill(cudaStream_t st, const htnk_streams_t* s, size_t ns
     return launch_status();
 }
 
+// one-shot hint for the NEXT htnk_normal_fill of this thread: it runs beside other kernels (side stream), so keep
+// its persistent CTAs to kMaxBlocks SMs; without the hint the generator takes every SM of the device
+static thread_local bool g_shared_next = false;
+extern "C" void htnk_normal_fill_shares_device_next(void) { g_shared_next = true; }
+
+static int sm_count(void)
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = kMaxBlocks;
+    }
+    return n;
+}
+
 extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t nstreams, int nseg,
                                 const htnk_segment_t* seg, uint32_t* ndraws)
 {
+    const bool shared = g_shared_next;
+    g_shared_next = false;
     if (nstreams == 0 || nseg <= 0) return 0;
     if (s->zpre) {  // pre-drawn normals: scatter only
         size_t total = 0, off = 0;
@@ -187,12 +218,28 @@ extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t
     Seg a[2] = {{0, nullptr, 0, nullptr, nullptr, nullptr}, {0, nullptr, 0, nullptr, nullptr, nullptr}};
     for (int i = 0; i < nseg && i < 2; i++)
         a[i] = Seg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};
-    const size_t per_block = (size_t)kWarpsPerBlock * 32;
-    size_t nblocks = (nstreams + per_block - 1) / per_block;
-    unsigned grid = (unsigned)(nblocks < (size_t)kMaxBlocks ? nblocks : (size_t)kMaxBlocks);
-    const size_t smem = (512 + (size_t)kWarpsPerBlock * kTile * (kTile + 1)) * sizeof(double);
-    auto kern = s->gen == 0 ? normal_fill_kernel<0> : normal_fill_kernel<1>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
-    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(s->seeds, s->seed0, s->states, nstreams, nseg, a[0], a[1], ndraws);
-    return launch_status();
+    static int cfg = -1;  // HTN_RNG_CFG (experiments): 0 = 16 warps x 32-wide tiles, 1 = 24 x 32, 2 = 32 x 16
+    if (cfg < 0) {
+        const char* e = getenv("HTN_RNG_CFG");
+        cfg = e ? atoi(e) : 0;
+    }
+    const int max_blocks = shared ? kMaxBlocks : sm_count();
+    auto go = [&](auto kern, int warps, int tile) {
+        const size_t per_block = (size_t)warps * 32;
+        size_t nblocks = (nstreams + per_block - 1) / per_block;
+        const size_t cap = (size_t)max_blocks * (warps >= 16 ? 1 : 16 / warps);
+        unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
+        const size_t smem = (768 + (size_t)warps * 32 * (tile + 1)) * sizeof(double);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+        kern<<<grid, warps * 32, smem, st>>>(s->seeds, s->seed0, s->states, nstreams, nseg, a[0], a[1], ndraws);
+        return launch_status();
+    };
+    if (cfg == 1) return s->gen == 0 ? go(normal_fill_kernel<0, 24, 32>, 24, 32) : go(normal_fill_kernel<1, 24, 32>, 24, 32);
+    if (cfg == 2) return s->gen == 0 ? go(normal_fill_kernel<0, 32, 16>, 32, 16) : go(normal_fill_kernel<1, 32, 16>, 32, 16);
+    // few streams: small CTAs so that every SM still gets warps (a stream is one thread; nothing else to split)
+    if (nstreams <= (size_t)kMaxBlocks * 32 * 4)
+        return s->gen == 0 ? go(normal_fill_kernel<0, 2, 32>, 2, 32) : go(normal_fill_kernel<1, 2, 32>, 2, 32);
+    if (nstreams < (size_t)kMaxBlocks * 32 * 16)
+        return s->gen == 0 ? go(normal_fill_kernel<0, 4, 32>, 4, 32) : go(normal_fill_kernel<1, 4, 32>, 4, 32);
+    return s->gen == 0 ? go(normal_fill_kernel<0, 16, 32>, 16, 32) : go(normal_fill_kernel<1, 16, 32>, 16, 32);
 }

@@ -68,6 +68,7 @@ static int ht_draw_chunk(cudaStream_t st, const htn_streams_t* s, size_t b0, siz
     streams_view(s, b0, &sv);
     HTN_CUDA(cudaMemset2DAsync(Z + k, ldz * 8, 0, (ldz - (size_t)k) * 8, nb, st));
     htnk_segment_t seg = {(size_t)k, Z, ldz, NULL, NULL, NULL};
+    htnk_normal_fill_shares_device_next();
     HTN_TRY(htnk_normal_fill(st, &sv, nb, 1, &seg, NULL));
 done:
     return rc;

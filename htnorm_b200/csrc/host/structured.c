@@ -118,6 +118,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         HTN_CUDA(cudaEventRecord(ev_fork, st));
         if (!s->states) { /* batched (seeded) streams: overlap with the factorisations */
             HTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            htnk_normal_fill_shares_device_next();
             HTN_TRY(htnk_normal_fill(side, &sv, nb0, 2, seg, NULL));
             HTN_CUDA(cudaEventRecord(ev_rng, side));
             rng_in_flight = 1;
