@@ -36,11 +36,12 @@ __device__ __forceinline__ double fast_rsqrt(double x)
 
 // full 128 x 128 block global -> shared by 16-byte LDGSTS (every element in flight at once); partial blocks
 // (nb < 128) take the masked scalar path so that the padding stays zero
+template <int NTHREADS = NT>
 __device__ __forceinline__ void load_block(double* S, const double* __restrict__ a, size_t ld, int nb, int tid,
                                            bool mask_upper)
 {
     if (nb == NB && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
-        for (int idx = tid; idx < NB * (NB / 2); idx += NT) {
+        for (int idx = tid; idx < NB * (NB / 2); idx += NTHREADS) {
             const int r = idx >> 6, ch = idx & 63;
             const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * LDB + 2 * ch);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(a + (size_t)r * ld + 2 * ch));
@@ -48,22 +49,22 @@ __device__ __forceinline__ void load_block(double* S, const double* __restrict__
         asm volatile("cp.async.commit_group;\n" ::);
         asm volatile("cp.async.wait_group 0;\n" ::);
     } else {
-        for (int idx = tid; idx < NB * NB; idx += NT) {
+        for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
             const int r = idx >> 7, c = idx & (NB - 1);
             S[r * LDB + c] = (r < nb && c < nb && (!mask_upper || c <= r)) ? a[(size_t)r * ld + c] : 0.0;
         }
     }
 }
 
-// potf2: the 128 x 128 block is factorised in 16 column panels of width 8.
-//   panel   : threads 0..127 (thread = row) each read the 8 x 8 diagonal sub-block and factor it LOCALLY in
-//             registers (redundantly - no communication on the 8-pivot chain), then solve their own row of
-//             the panel against it (28 FMAs) and publish the row (final L) to shared memory;
-//   update  : the trailing lower triangle gets its rank-8 update on the tensor cores: every 8 x 8 tile is
-//             two DMMAs (m8n8k4) on fragments read straight from the published panel; warp w owns tile row
-//             b + 1 + w.
-// Two barriers per panel, i.e. 32 per block instead of one per column; the pivot chain (128 dependent
-// rsqrt + a few FMAs each) is all that remains serial.
+// potf2: the 128 x 128 block is factorised in 16 column panels of width 8, with a FACTOR WARP and look-ahead:
+//   factor  : warp 0 factors the 8 x 8 diagonal sub-block in registers (every lane alike: no communication on
+//             the 8-pivot chain) together with T = inverse of its factor; lane 0 parks T in shared memory;
+//   panel   : L[:, panel] = A[:, panel] * T^T on the tensor cores, one 8-row tile per warp (2 DMMAs);
+//   update  : rank-8 update of the trailing lower triangle (2 DMMAs per 8 x 8 tile).  Warp 0 takes only the NEXT
+//             diagonal tile and goes straight on to factor it; warps 1..15 share every other tile (a flat tile
+//             list, four tiles per pass, all operands loaded before the DMMAs are issued).
+// The 128-step pivot chain (rsqrt + two dependent FP64 operations per column) is what remains serial; everything
+// else runs beside it.  Two barriers per panel.
 __device__ __forceinline__ void dmma_sub(double& c0, double& c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -71,9 +72,11 @@ __device__ __forceinline__ void dmma_sub(double& c0, double& c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
-constexpr int LDP = 12;  // panel row stride (doubles): 8 + 4 keeps the DMMA fragment reads conflict-free
+constexpr int LDP = 12;      // panel row stride (doubles): 8 + 4 keeps the DMMA fragment reads conflict-free
+constexpr int NPAN = NB / 8;  // 16 panels
+constexpr int NTP = 512;      // potf2: 16 warps, one 8-row tile of the panel each
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NTP, 1)
 potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ rdiag_out,
              int* __restrict__ info)
 {
@@ -81,104 +84,163 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     double* S = sm;                  // [NB][LDB]  the block (lower triangle meaningful)
     double* P = sm + NB * LDB;       // [NB][LDP]  current panel: L[:, 8b .. 8b+7]
     double* rdiag = P + NB * LDP;    // [NB]       1 / L[j][j]
+    double* Tsm = rdiag + NB;        // [8][12]    inverse of the current 8 x 8 factor
     __shared__ int s_fail;
+    __shared__ short2 tiles[NPAN * (NPAN + 1) / 2];  // (8 tr, 8 tc), tr >= tc, column by column
+    __shared__ int colstart[NPAN + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
 
     // the strictly upper part of a full block may hold junk (diagonal tiles of earlier trailing updates): it is
-    // never used - sub-block loads read c <= r, diagonal rows mask their result, the write-back masks too
-    load_block(S, a, ld, nb, tid, true);
-    for (int idx = tid; idx < NB * LDP; idx += NT) P[idx] = 0.0;
+    // never used - sub-block loads read c <= r, diagonal tiles mirror, the write-back masks too
+    load_block<NTP>(S, a, ld, nb, tid, true);
+    for (int idx = tid; idx < NB * LDP; idx += NTP) P[idx] = 0.0;
+    for (int idx = tid; idx < 8 * 12; idx += NTP) Tsm[idx] = 0.0;
+    const int npanels = (nb + 7) >> 3;
+    if (tid < npanels) {
+        int first = 0;
+        for (int t = 0; t < tid; t++) first += npanels - t;
+        colstart[tid] = first;
+        if (tid == npanels - 1) colstart[npanels] = first + 1;
+        for (int tr = tid; tr < npanels; tr++) tiles[first + tr - tid] = make_short2((short)(8 * tr), (short)(8 * tid));
+    }
     if (tid == 0) s_fail = 0;
     __syncthreads();
 
-    const int npanels = (nb + 7) >> 3;
-    int nfact = nb;
-    for (int b = 0; b < npanels; b++) {
-        const int j0 = 8 * b;
-        if (tid < NB) {
-            // ---- local Cholesky of the 8 x 8 diagonal sub-block (identical in every thread) ----
-            double l[8][8];
+    auto factor_block = [&](int bb) {  // warp 0 only
+        const int j0 = 8 * bb;
+        const double* Sb = S + j0 * LDB + j0;
+        double l[8][8];  // the sub-block / its factor (c <= r)
+        double w[8];     // column (lane & 7) of the inverse of the factor: forward substitution on e_c
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                l[r][c] = (c <= r) ? Sb[r * LDB + c] : 0.0;
+            }
+#pragma unroll
+        for (int r = 0; r < 8; r++) w[r] = (r == (lane & 7)) ? 1.0 : 0.0;
+        int bad = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double ajj = l[j][j];
+            // columns beyond nb (partial last panel) are padding: treat them as the identity
+            if (j0 + j >= nb) ajj = 1.0;
+            if (ajj <= 0.0 && bad < 0) bad = j;  // NaN passes
+            const double rinv = fast_rsqrt(ajj);
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                if (r > j) l[r][j] *= rinv;
 #pragma unroll
             for (int r = 0; r < 8; r++)
 #pragma unroll
-                for (int c = 0; c < 8; c++) l[r][c] = (c <= r) ? S[(j0 + r) * LDB + j0 + c] : 0.0;
-            double ri[8];
-            int bad = -1;
+                for (int c = 0; c < 8; c++)
+                    if (r > j && c > j && c <= r) l[r][c] = fma(-l[r][j], l[c][j], l[r][c]);
+            // forward substitution on this lane's unit vector (off the critical path): 36 FP64 instructions for
+            // the whole inverse instead of 120 when every lane carried all of it
+            w[j] *= rinv;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                double ajj = l[j][j];
-                // columns beyond nb (partial last panel) are padding: treat them as the identity
-                if (j0 + j >= nb) ajj = 1.0;
-                if (ajj <= 0.0 && bad < 0) bad = j;  // NaN passes
-                const double rinv = fast_rsqrt(ajj);
-                ri[j] = rinv;
-                double d = ajj * rinv;
-                d = fma(fma(-d, d, ajj), 0.5 * rinv, d);
-                l[j][j] = d;
+            for (int r = 0; r < 8; r++)
+                if (r > j) w[r] = fma(-l[r][j], w[j], w[r]);
+        }
+        if (lane == 0 && bad >= 0) {
+            atomicCAS(info, 0, col0 + j0 + bad + 1);
+            s_fail = j0 + bad + 1;
+        }
+        if (lane < 8) {  // lane c publishes column c of T (zeros above the diagonal come out by themselves)
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-                    if (r > j) l[r][j] *= rinv;
-#pragma unroll
-                for (int r = 0; r < 8; r++)
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        if (r > j && c > j && c <= r) l[r][c] = fma(-l[r][j], l[c][j], l[r][c]);
+            for (int r = 0; r < 8; r++) {
+                Tsm[r * 12 + lane] = w[r];
+                if (lane == r && j0 + r < nb) rdiag[j0 + r] = w[r];  // T[r][r] = 1 / L[r][r]
             }
-            if (bad >= 0) {  // uniform over the 128 threads: every one factored the same block
-                if (tid == 0) {
-                    atomicCAS(info, 0, col0 + j0 + bad + 1);
-                    s_fail = j0 + bad + 1;
+        }
+    };
+
+    if (warp == 0) factor_block(0);
+    __syncthreads();
+    int nfact = nb;
+    for (int b = 0; b < npanels; b++) {
+        if (s_fail) { nfact = s_fail - 1; break; }
+        const int j0 = 8 * b;
+        // ---- panel: 8-row tile tr = b + warp, X = A_tile * T^T (the diagonal tile is read symmetrically) ----
+        for (int tr = b + warp; tr < npanels; tr += NTP / 32) {
+            {
+                const double tb0 = Tsm[g * 12 + t4], tb1 = Tsm[g * 12 + 4 + t4];  // B[k][n] = T[n][k]
+                const double* ar = S + (tr * 8 + g) * LDB + j0;
+                double a0, a1;
+                if (tr == b) {  // symmetric block, lower triangle valid: element (g, c) lives at (max, min)
+                    a0 = t4 <= g ? ar[t4] : S[(j0 + t4) * LDB + j0 + g];
+                    a1 = 4 + t4 <= g ? ar[4 + t4] : S[(j0 + 4 + t4) * LDB + j0 + g];
+                } else {
+                    a0 = ar[t4];
+                    a1 = ar[4 + t4];
                 }
-            } else {
-                // ---- my row of the panel: x = a L11^-T (rows below), or L11's own row (diagonal rows) ----
-                const int r = tid;
-                if (r >= j0 && r < nb) {
-                    double x[8];
-#pragma unroll
-                    for (int c = 0; c < 8; c++) x[c] = S[r * LDB + j0 + c];
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        double v = x[c];
-#pragma unroll
-                        for (int t = 0; t < 8; t++)
-                            if (t < c) v = fma(-x[t], l[c][t], v);
-                        const double vraw = v, ric = ri[c];
-                        v *= ric;
-                        // a diagonal row's own entry is the pivot (sqrt with one Heron step); nothing above it
-                        const double piv = fma(fma(-v, v, vraw), 0.5 * ric, v);
-                        const int dr = r - j0;
-                        v = (dr == c) ? piv : ((dr < c) ? 0.0 : v);
-                        if (j0 + c >= nb) v = 0.0;
-                        x[c] = v;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        S[r * LDB + j0 + c] = x[c];
-                        P[r * LDP + c] = x[c];
-                    }
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                dmma_sub(c0, c1, a0, tb0);
+                dmma_sub(e0, e1, a1, tb1);
+                double2 v = make_double2(c0 + e0, c1 + e1);
+                const int row = tr * 8 + g;
+                if (tr == b) {  // nothing above the diagonal
+                    if (2 * t4 > g) v.x = 0.0;
+                    if (2 * t4 + 1 > g) v.y = 0.0;
                 }
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (tid == j && j0 + j < nb) rdiag[j0 + j] = ri[j];
+                if (row >= nb) v = make_double2(0.0, 0.0);
+                if (j0 + 2 * t4 >= nb) v.x = 0.0;
+                if (j0 + 2 * t4 + 1 >= nb) v.y = 0.0;
+                *reinterpret_cast<double2*>(S + row * LDB + j0 + 2 * t4) = v;
+                *reinterpret_cast<double2*>(P + row * LDP + 2 * t4) = v;
             }
         }
         __syncthreads();
-        if (s_fail) { nfact = s_fail - 1; break; }
-        // ---- rank-8 update of the trailing lower triangle on the tensor cores ----
-        {
-            const int tr = b + 1 + warp;  // this warp's tile row
-            if (tr < npanels) {
-                const int g = lane >> 2, t4 = lane & 3;
-                const double a0 = -P[(tr * 8 + g) * LDP + t4];
-                const double a1 = -P[(tr * 8 + g) * LDP + 4 + t4];
-                for (int tc = b + 1; tc <= tr; tc++) {
-                    const double b0 = P[(tc * 8 + g) * LDP + t4];
-                    const double b1 = P[(tc * 8 + g) * LDP + 4 + t4];
-                    double2* cp = reinterpret_cast<double2*>(&S[(tr * 8 + g) * LDB + tc * 8 + 2 * t4]);
-                    double2 c = *cp;
-                    dmma_sub(c.x, c.y, a0, b0);
-                    dmma_sub(c.x, c.y, a1, b1);
-                    *cp = c;
+        // ---- rank-8 update of the trailing lower triangle on the tensor cores, with look-ahead ----
+        if (b + 1 < npanels) {
+            if (warp == 0) {  // next diagonal tile: update it, then factor it
+                const int r0 = (b + 1) * 8 + g;
+                const double pa0 = P[r0 * LDP + t4], pa1 = P[r0 * LDP + 4 + t4];
+                double2* cp = reinterpret_cast<double2*>(&S[r0 * LDB + (b + 1) * 8 + 2 * t4]);
+                double2 c = *cp;
+                double e0 = 0.0, e1 = 0.0;
+                dmma_sub(c.x, c.y, -pa0, pa0);
+                dmma_sub(e0, e1, -pa1, pa1);
+                *cp = make_double2(c.x + e0, c.y + e1);
+                __syncwarp();
+                factor_block(b + 1);
+            } else if ((warp & 3) != 0) {
+                // DMMA executes on the FP64 pipe of the issuing warp's scheduler partition (warp id mod 4), the same
+                // pipe the pivot chain of warp 0 lives on: the update is left to the warps of the OTHER three
+                // partitions, so the chain runs undisturbed (clock64 probes: 1.2 k instead of 1.7 k cycles per 8 pivots)
+                constexpr int NUW = 3 * (NTP / 128);
+                const int uw = warp - 1 - (warp >> 2);
+                const int tend = colstart[npanels];
+                for (int e0i = colstart[b + 1] + 1 + 4 * uw; e0i < tend; e0i += 4 * NUW) {
+                    short2 te[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) te[u] = tiles[min(e0i + u, tend - 1)];
+                    double a0[4], a1[4], b0[4], b1[4];
+                    double2 c[4];
+                    double2* cp[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double* pa = P + (te[u].x + g) * LDP + t4;
+                        const double* pb = P + (te[u].y + g) * LDP + t4;
+                        a0[u] = -pa[0];
+                        a1[u] = -pa[4];
+                        b0[u] = pb[0];
+                        b1[u] = pb[4];
+                        cp[u] = reinterpret_cast<double2*>(&S[(te[u].x + g) * LDB + te[u].y + 2 * t4]);
+                        c[u] = *cp[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        double e0 = 0.0, e1 = 0.0;  // second, independent chain
+                        dmma_sub(c[u].x, c[u].y, a0[u], b0[u]);
+                        dmma_sub(e0, e1, a1[u], b1[u]);
+                        c[u].x += e0;
+                        c[u].y += e1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (e0i + u < tend) *cp[u] = c[u];
                 }
             }
         }
@@ -186,12 +248,23 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     }
     const bool failed = nfact < nb;
     // write L back: lower triangle, zeros above; nothing beyond a failed column is meaningful
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        if (r < nb && c < nb) a[(size_t)r * ld + c] = (c <= r && c < ((nfact + 7) & ~7)) ? S[r * LDB + c] : 0.0;
+    const int cmax = (nfact + 7) & ~7;
+    if (nb == NB && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        for (int idx = tid; idx < NB * (NB / 2); idx += NTP) {  // 16 bytes per store
+            const int r = idx >> 6, c = 2 * (idx & 63);
+            double2 v = *reinterpret_cast<const double2*>(S + r * LDB + c);
+            if (c > r || c >= cmax) v.x = 0.0;
+            if (c + 1 > r || c + 1 >= cmax) v.y = 0.0;
+            *reinterpret_cast<double2*>(a + (size_t)r * ld + c) = v;
+        }
+    } else {
+        for (int idx = tid; idx < NB * NB; idx += NTP) {
+            const int r = idx >> 7, c = idx & (NB - 1);
+            if (r < nb && c < nb) a[(size_t)r * ld + c] = (c <= r && c < cmax) ? S[r * LDB + c] : 0.0;
+        }
     }
     if (rdiag_out != nullptr && !failed)
-        for (int c = tid; c < nb; c += NT) rdiag_out[c] = rdiag[c];
+        for (int c = tid; c < nb; c += NTP) rdiag_out[c] = rdiag[c];
 }
 
 // ---- inverse of diagonal blocks, batched: one CTA per block, all blocks in parallel ----
@@ -345,10 +418,10 @@ extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col
 {
     if (nb <= 0) return 0;
     if (nb > NB) return -202;
-    const size_t smem = (size_t)(NB * LDB + NB * LDP + NB) * sizeof(double);
+    const size_t smem = (size_t)(NB * LDB + NB * LDP + NB + 8 * 12) * sizeof(double);
     if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
-    potf2_kernel<<<1, NT, smem, st>>>(a, ld, nb, col0, rdiag, info);
+    potf2_kernel<<<1, NTP, smem, st>>>(a, ld, nb, col0, rdiag, info);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }

@@ -337,14 +337,16 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
             auto factor_block = [&](int bb) {  // warp 0 only
                 const double* Ab = A + toff[bb];
                 const int lb = tld[bb], j0 = 8 * bb;
-                double l[8][8], w[8][8];  // l[r][c] = U[j0 + c][j0 + r] (c <= r); w -> inverse of the lower factor
+                double l[8][8];  // l[r][c] = U[j0 + c][j0 + r] (c <= r)
+                double w[8];     // column (lane & 7) of the inverse of the lower factor: forward substitution on e_c
 #pragma unroll
                 for (int r = 0; r < 8; r++)
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         l[r][c] = (c <= r) ? Ab[c * lb + r] : 0.0;
-                        w[r][c] = 0.0;
                     }
+#pragma unroll
+                for (int r = 0; r < 8; r++) w[r] = (r == (lane & 7)) ? 1.0 : 0.0;
                 int bad = -1;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
@@ -360,24 +362,17 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
 #pragma unroll
                         for (int c = 0; c < 8; c++)
                             if (r > j && c > j && c <= r) l[r][c] = fma(-l[r][j], l[c][j], l[r][c]);
-                    // forward substitution on the identity, one row per pivot (off the critical path)
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        if (c < j) w[j][c] *= rinv;
-                    w[j][j] = rinv;
+                    // forward substitution on this lane's unit vector (off the critical path): 36 FP64 instructions for
+                    // the whole inverse instead of 120 when every lane carried all of it
+                    w[j] *= rinv;
 #pragma unroll
                     for (int r = 0; r < 8; r++)
-#pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            if (r > j && c <= j) w[r][c] = fma(-l[r][j], w[j][c], w[r][c]);
+                        if (r > j) w[r] = fma(-l[r][j], w[j], w[r]);
                 }
-                if (lane == 0) {
-                    if (bad >= 0) s_fail = j0 + bad + 1;
+                if (lane == 0 && bad >= 0) s_fail = j0 + bad + 1;
+                if (lane < 8) {  // lane c publishes column c of T (zeros above the diagonal come out by themselves)
 #pragma unroll
-                    for (int r = 0; r < 8; r++)
-#pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            if (c <= r) Tsm[r * 12 + c] = w[r][c];
+                    for (int r = 0; r < 8; r++) Tsm[r * 12 + lane] = w[r];
                 }
             };
             if (warp == 0) factor_block(0);
