@@ -15,7 +15,8 @@
 // "Upper world": the reference reads the UPPER triangle of a row-major cov, so the rows are staged
 // as they lie in HBM (16-byte cp.async of the part right of the diagonal, nothing is symmetrised or transposed)
 // and the factorisation is carried out as cov = U^T U on that triangle; U = L^T holds exactly the numbers of
-// the reference's lower factor.  A lower-triangle source (HTN_FLAG_COLMAJOR) is transposed while staging.
+// the reference's lower factor.  With HTN_FLAG_COLMAJOR the lower triangle is the valid one and g is column-major:
+// both are transposed while staging.
 //
 //   cov * G^T on the tensor cores (DMMA), symmetric reads through the one triangle   dsymm,  src/htnorm.c:154
 //   G cov G^T accumulated per warp from its own rows of cov G^T                      dgemm,  src/htnorm.c:164
@@ -224,15 +225,23 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
                 }
             }
         }
-        if (vec_ok) {
+        if (lower_src) {  // HTN_FLAG_COLMAJOR: g is k2 x k column-major, i.e. element (c, j) at j * k2 + c
+            for (int idx = tid; idx < k2 * k; idx += NTH) {
+                const int j = idx / k2, c = idx - j * k2;
+                cp_async8(&G[c * ldg + j], gp + idx);
+            }
+        } else if (vec_ok) {
             for (int idx = tid; idx < k2 * (k >> 1); idx += NTH) {
                 const int c = idx / (k >> 1), j = 2 * (idx - c * (k >> 1));
                 cp_async16(&G[c * ldg + j], gp + (size_t)c * k + j);
             }
-            for (int j = 2 * tid; j < k; j += 2 * NTH) cp_async16(&z[j], zs + pb * (size_t)k + j);
         } else {
             for (int c = warp; c < k2; c += NW)
                 for (int j = lane; j < k; j += 32) cp_async8(&G[c * ldg + j], gp + (size_t)c * k + j);
+        }
+        if (vec_ok) {
+            for (int j = 2 * tid; j < k; j += 2 * NTH) cp_async16(&z[j], zs + pb * (size_t)k + j);
+        } else {
             for (int i = tid; i < k; i += NTH) cp_async8(&z[i], zs + pb * (size_t)k + i);
         }
         asm volatile("cp.async.commit_group;\n" ::);

@@ -417,6 +417,57 @@ def test_potrf_wide_panels(h, n):
     assert np.abs(x @ a - x0).max() < 1e-9          # x = x0 A^-1
 
 
+@pytest.mark.parametrize("k,k2,diag", [(5, 1, False), (8, 2, False), (17, 3, False), (40, 8, False), (63, 4, False),
+                                       (64, 16, False), (65, 4, False), (100, 5, False), (128, 12, False),
+                                       (33, 2, True), (96, 4, True)])
+def test_independent_problems_all_shapes(h, oracle, k, k2, diag):
+    """The one-CTA-per-problem kernel has shape-dependent paths (padding to 8, odd k -> 8-byte staging, 64 / 128
+    threads, register / shared k2 x k2 solve, diagonal cov): each against the oracle on fresh inputs."""
+    c = cases.ht_independent_case(nproblems=37, k=k, k2=k2, rng_seed=100 + k)
+    if diag:
+        c["cov"] = np.stack([np.diag(np.diag(m)) for m in c["cov"]])
+    x, info = h.hyperplane_truncated_mvnorm_batch(37, c["mean"], c["cov"], c["g"], c["r"], diag=diag, independent=True,
+                                                  seed0=5)
+    xo, io, _ = oracle.hyperplane("pcg64", 37, c["mean"], c["cov"], c["g"], c["r"], diag=diag, independent=True,
+                                  seed0=5)
+    assert np.array_equal(info, io) and not info.any()
+    assert rel_err(x, xo) < REL_TOL
+    resid = np.abs(np.einsum("bck,bk->bc", c["g"], x) - c["r"]).max()
+    assert resid < RESID_TOL * 50 * max(1.0, np.abs(c["r"]).max())
+
+
+def test_independent_problems_failures_and_layouts(h, oracle):
+    """Per-problem error codes: a problem whose cov is not PD reports its pivot and leaves its row of
+    `out` untouched, one whose G cov G^T is singular returns the unprojected y; the others are unaffected.
+    Triangle rule (Q4) and HTN_FLAG_COLMAJOR for per-problem inputs."""
+    c = cases.ht_independent_case(nproblems=6, k=16, k2=2, rng_seed=9)
+    cov, g = c["cov"].copy(), c["g"].copy()
+    cov[1] = 0.0                       # not PD at pivot 1
+    cov[3][5, 5] = -1.0                # not PD at pivot 6
+    cov[4] = 4.0 * np.eye(16)          # exactly representable G cov G^T = [[64, 64], [64, 64]] -> info 2
+    g[4] = 1.0
+    out = np.full((6, 16), 7.0)
+    x, info = h.hyperplane_truncated_mvnorm_batch(6, c["mean"], cov, g, c["r"], independent=True, seed0=1, out=out,
+                                                  raise_on_error=False)
+    xo, io, _ = oracle.hyperplane("pcg64", 6, c["mean"], cov, g, c["r"], independent=True, seed0=1)
+    assert info.tolist() == io.tolist() == [0, 1, 0, 6, 2, 0]
+    assert (out[1] == 7.0).all() and (out[3] == 7.0).all()
+    ok = [0, 2, 4, 5]
+    assert rel_err(x[ok], xo[ok]) < REL_TOL
+    # triangles: garbage below the diagonal is ignored (row-major); COLMAJOR reads the lower one and a transposed g
+    rng = np.random.default_rng(0)
+    junk = rng.standard_normal(c["cov"].shape)
+    up_ok = np.triu(c["cov"]) + np.tril(junk, -1)
+    lo_ok = np.tril(c["cov"]) + np.triu(junk, 1)
+    base, _ = h.hyperplane_truncated_mvnorm_batch(6, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=2)
+    xu, _ = h.hyperplane_truncated_mvnorm_batch(6, c["mean"], up_ok, c["g"], c["r"], independent=True, seed0=2)
+    assert np.array_equal(xu, base)
+    gcm = np.ascontiguousarray(np.swapaxes(c["g"], 1, 2)).reshape(c["g"].shape)
+    xc, _ = h.hyperplane_truncated_mvnorm_batch(6, c["mean"], lo_ok, gcm, c["r"], independent=True, seed0=2,
+                                                flags=h._lib.HTN_FLAG_COLMAJOR)
+    assert rel_err(xc, base) < REL_TOL
+
+
 def test_edge_cases_empty_ragged_chunked(h, oracle):
     """empty batch; independent problems too large for the one-CTA kernel (k > 128: one factorisation each);
     device-resident seed array; a host-memory batch long enough to be drawn in several overlapped chunks
