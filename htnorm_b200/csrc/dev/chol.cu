@@ -343,7 +343,8 @@ __device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double& a
     a1 = (t4 & 1) ? w1 : w0;  // element (row g, column 4 + t4)
 }
 
-__global__ void __launch_bounds__(NT, 1)
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
 trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __restrict__ l, size_t ldl,
                  int nb, const double* __restrict__ rdiag_g)
 {
@@ -352,11 +353,12 @@ trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __
     double* I8 = sm + NB * LDB;      // [16][8][LDI] : inverses of the 8 x 8 diagonal blocks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    (void)rdiag_g;
-    load_block(S, l, ldl, nb, tid, true);  // potf2 left zeros above the diagonal
+    load_block<NTHR>(S, l, ldl, nb, tid, true);  // potf2 left zeros above the diagonal
     __syncthreads();
-    {   // warp w inverts diagonal block w: lane c < 8 solves L_bb y = e_c
-        const int j0 = 8 * warp;
+    // the warps invert the 8 x 8 diagonal blocks: lane c < 8 solves L_bb y = e_c; the reciprocal pivots come from
+    // potf2 (rdiag), so there is no division on the chain
+    for (int blk = warp; blk < 16; blk += NTHR / 32) {
+        const int j0 = 8 * blk;
         if (lane < 8) {
             double y[8];
 #pragma unroll
@@ -365,16 +367,17 @@ trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __
 #pragma unroll
                 for (int t = 0; t < 8; t++)
                     if (t < i) v = fma(-S[(j0 + i) * LDB + j0 + t], y[t], v);
-                const double d = (j0 + i < nb) ? S[(j0 + i) * LDB + j0 + i] : 1.0;
-                y[i] = v / d;
+                double rd = 1.0;
+                if (j0 + i < nb) rd = rdiag_g ? rdiag_g[j0 + i] : 1.0 / S[(j0 + i) * LDB + j0 + i];
+                y[i] = v * rd;
             }
 #pragma unroll
-            for (int i = 0; i < 8; i++) I8[(warp * 8 + i) * LDI + lane] = y[i];
+            for (int i = 0; i < 8; i++) I8[(blk * 8 + i) * LDI + lane] = y[i];
         }
     }
     __syncthreads();
 
-    const size_t r0 = (size_t)blockIdx.x * TR_ROWS + warp * 8;
+    const size_t r0 = (size_t)blockIdx.x * (NTHR / 4) + warp * 8;
     const size_t row = r0 + g;
     const bool live = row < (size_t)nrows;
     double* xr = x + (live ? row : 0) * ldx;
@@ -444,9 +447,16 @@ extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows,
     if (nrows <= 0 || nb <= 0) return 0;
     if (nb > NB) return -202;
     const size_t smem = (size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double);
-    if (cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return -201;
-    trsm_rows_kernel<<<(nrows + TR_ROWS - 1) / TR_ROWS, NT, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
+    // rows are independent: small CTAs (32 rows) until the 128-row CTAs would fill most of the device by themselves
+    if ((nrows + TR_ROWS - 1) / TR_ROWS >= 96) {
+        if (cudaFuncSetAttribute(trsm_rows_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -201;
+        trsm_rows_kernel<512><<<(nrows + TR_ROWS - 1) / TR_ROWS, 512, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
+    } else {
+        if (cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -201;
+        trsm_rows_kernel<128><<<(nrows + 31) / 32, 128, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
+    }
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }
