@@ -221,6 +221,55 @@ unsigned grid_for(size_t total, int block)
     return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
 
+
+// W = G L for a few constraint rows (k2 <= 16) and a lower-triangular L: W[c][j] = sum_{i >= j} G[c][i] L[i][j].
+// Thread = column j (rows of L are read coalesced), the row range is split over blockIdx.y; partial sums go to
+// part[chunk][c][j] and are added up in a FIXED order by wl_reduce_kernel (bit-reproducible, no atomics).
+template <int K2T>
+__global__ void __launch_bounds__(128)
+wl_partial_kernel(const double* __restrict__ g, size_t ldg, int k2, const double* __restrict__ l, size_t ldl, int k,
+                  int rows_per_chunk, double* __restrict__ part, size_t ldp)
+{
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int i0 = blockIdx.y * rows_per_chunk;
+    const int i1 = min(k, i0 + rows_per_chunk);
+    __shared__ double gs[K2T][128];  // G[:, i0 + 0 .. 127] of the current 128-row slice
+    double acc[K2T];
+#pragma unroll
+    for (int c = 0; c < K2T; c++) acc[c] = 0.0;
+    for (int s0 = i0; s0 < i1; s0 += 128) {
+        __syncthreads();
+        for (int c = 0; c < K2T; c++) {
+            const int i = s0 + threadIdx.x;
+            gs[c][threadIdx.x] = (c < k2 && i < i1) ? g[(size_t)c * ldg + i] : 0.0;
+        }
+        __syncthreads();
+        const int s1 = min(i1, s0 + 128);
+        if (j < k) {
+            for (int i = max(s0, j); i < s1; i++) {
+                const double lv = l[(size_t)i * ldl + j];
+#pragma unroll
+                for (int c = 0; c < K2T; c++) acc[c] = fma(gs[c][i - s0], lv, acc[c]);
+            }
+        }
+    }
+    if (j < k) {
+#pragma unroll
+        for (int c = 0; c < K2T; c++)
+            if (c < k2) part[((size_t)blockIdx.y * k2 + c) * ldp + j] = acc[c];
+    }
+}
+
+__global__ void wl_reduce_kernel(const double* __restrict__ part, size_t ldp, int nchunks, int k2, int k,
+                                 double* __restrict__ w, size_t ldw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (j >= k) return;
+    double v = 0.0;
+    for (int q = 0; q < nchunks; q++) v += part[((size_t)q * k2 + c) * ldp + j];
+    w[(size_t)c * ldw + j] = v;
+}
 }  // namespace
 
 extern "C" int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, int n, int lower_src,
@@ -361,4 +410,29 @@ extern "C" int htnk_fill_test_spd(cudaStream_t st, double* f, size_t ld, int n)
     fill_test_spd_kernel<<<148 * 8, 256, 0, st>>>(f, ld, n);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+/* W (k2 x ldw) = G (k2 x ldg) * L (k x ldl, lower triangular), k2 <= 16.  part: workspace of
+ * htnk_wl_workspace(k) * k2 * ldp doubles with ldp >= k. */
+extern "C" int htnk_wl_chunks(int k)
+{
+    int n = (k + 127) / 128;  // one 128-row slice per chunk up to 16 chunks, then longer chunks
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+extern "C" int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, const double* l, size_t ldl, int k,
+                       double* part, size_t ldp, double* w, size_t ldw)
+{
+    if (k2 <= 0 || k <= 0) return 0;
+    if (k2 > 16) return -202;
+    const int nch = htnk_wl_chunks(k);
+    int rows = (k + nch - 1) / nch;
+    rows = (rows + 127) / 128 * 128;
+    dim3 grid((unsigned)((k + 127) / 128), (unsigned)nch);
+    if (k2 == 1) wl_partial_kernel<1><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);
+    else if (k2 <= 4) wl_partial_kernel<4><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);
+    else wl_partial_kernel<16><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);
+    if (status()) return -201;
+    wl_reduce_kernel<<<dim3((unsigned)((k + 255) / 256), (unsigned)k2), 256, 0, st>>>(part, ldp, nch, k2, k, w, ldw);
+    return status();
 }

@@ -316,7 +316,7 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
         case 66: return launch<64, 2, 2, 8, 4, 2, 32, 2>(st, p);  // BK = 32, two stages: half the barriers
         case 67: return launch<64, 2, 2, 8, 4, 2, 16, 4>(st, p);  // four stages (1 CTA/SM fits only: smem)
         case 129: return launch<128, 4, 4, 4, 4, 1>(st, p);  // 16 warps / SM in one CTA
-        case 32: return launch<32, 8, 1, 2, 4, 1>(st, p);
+        case 32: return launch<32, 8, 1, 2, 4, 2>(st, p);  // small accumulators: two CTAs per SM, one wave for the panel updates
         case 8: return launch<8, 8, 1, 2, 1, 1>(st, p);
         default: return -202;
     }

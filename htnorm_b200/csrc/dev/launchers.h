@@ -106,6 +106,10 @@ int htnk_rsub_rows(cudaStream_t st, double* dst, size_t ldd, int rows, int cols,
 int htnk_diag_extract(cudaStream_t st, const double* a, size_t lda, int n, int op, double* d);
 /* m[i*ld + i] += (or =) v[i] / constant */
 int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const double* v, double cval);
+/* W (k2 x ldw) = G (k2 x ldg) * L (k x ldl, lower triangular), k2 <= 16; part: htnk_wl_chunks(k) * k2 * ldp doubles */
+int htnk_wl_chunks(int k);
+int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, const double* l, size_t ldl, int k, double* part,
+            size_t ldp, double* w, size_t ldw);
 int htnk_fill_i32(cudaStream_t st, int* p, size_t n, int v);
 /* p[i] = codes[0] ? codes[0] : codes[1]  (codes: two device ints, e.g. chol(cov) and chol(G cov G^T)) */
 int htnk_fill_info(cudaStream_t st, int* p, size_t n, const int* codes);

@@ -171,10 +171,25 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_TRY(htn_potrf(ctx, &fa, d_info));
     /* join the G cov G^T branch (it reads Sfull, which is recycled next) */
     HTN_CUDA(cudaStreamWaitEvent(st, ev_sbranch, 0));
-    /* W = G L  via  W^T = L^T G^T  (L^T parked in the Sfull buffer, free from here on) */
-    HTN_TRY(htnk_transpose(st, F, ldz, k, k, Sfull, kp));
-    HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, WT, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-    HTN_TRY(htnk_transpose(st, WT, k2p, k, k2, W, kp));
+    if (k2 <= 16) {
+        /* W = G L: a few rows against the triangle, column-parallel with a fixed-order reduction; the partial sums
+         * park in the Sfull buffer (free from here on: 16 * k2 * kp <= k * kp doubles whenever k >= 256, else WT) */
+        const size_t need = (size_t)htnk_wl_chunks(k) * (size_t)k2 * kp;
+        if (need <= (size_t)k * kp) {
+            HTN_TRY(htnk_wl(st, Gp, kp, k2, F, ldz, k, Sfull, kp, W, kp));
+        } else {
+            double* part = NULL;
+            HTN_TRY(htn_dalloc(ctx, (void**)&part, need * 8));
+            rc = htnk_wl(st, Gp, kp, k2, F, ldz, k, part, kp, W, kp);
+            htn_dfree(ctx, part);
+            if (rc) goto done;
+        }
+    } else {
+        /* W = G L  via  W^T = L^T G^T  (L^T parked in the Sfull buffer, free from here on) */
+        HTN_TRY(htnk_transpose(st, F, ldz, k, k, Sfull, kp));
+        HTN_TRY(htnk_gemm_tn(st, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, WT, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        HTN_TRY(htnk_transpose(st, WT, k2p, k, k2, W, kp));
+    }
 
     int h_info[2] = {0, 0};
     const int async = !g_need_codes && k2 <= ALPHA_K2_MAX && g_async_info_out != NULL;
