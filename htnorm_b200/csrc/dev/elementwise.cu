@@ -233,24 +233,27 @@ wl_partial_kernel(const double* __restrict__ g, size_t ldg, int k2, const double
     const int j = blockIdx.x * 128 + threadIdx.x;
     const int i0 = blockIdx.y * rows_per_chunk;
     const int i1 = min(k, i0 + rows_per_chunk);
-    __shared__ double gs[K2T][128];  // G[:, i0 + 0 .. 127] of the current 128-row slice
+    __shared__ double gs[K2T][32];  // G[:, s0 .. s0 + 31] of the current 32-row slice
     double acc[K2T];
 #pragma unroll
     for (int c = 0; c < K2T; c++) acc[c] = 0.0;
-    for (int s0 = i0; s0 < i1; s0 += 128) {
+    // rows above this block's first column contribute nothing (L is zero there): skipped slice-wise; inside a
+    // slice all 32 loads are issued before the FMAs (the stored zeros above the diagonal make that safe)
+    for (int s0 = max(i0, (int)(blockIdx.x * 128) & ~31); s0 < i1; s0 += 32) {
         __syncthreads();
-        for (int c = 0; c < K2T; c++) {
-            const int i = s0 + threadIdx.x;
-            gs[c][threadIdx.x] = (c < k2 && i < i1) ? g[(size_t)c * ldg + i] : 0.0;
+        for (int e = threadIdx.x; e < K2T * 32; e += 128) {
+            const int c = e >> 5, i = s0 + (e & 31);
+            gs[c][e & 31] = (c < k2 && i < i1) ? g[(size_t)c * ldg + i] : 0.0;
         }
         __syncthreads();
-        const int s1 = min(i1, s0 + 128);
         if (j < k) {
-            for (int i = max(s0, j); i < s1; i++) {
-                const double lv = l[(size_t)i * ldl + j];
+            double lv[32];
 #pragma unroll
-                for (int c = 0; c < K2T; c++) acc[c] = fma(gs[c][i - s0], lv, acc[c]);
-            }
+            for (int u = 0; u < 32; u++) lv[u] = (s0 + u < i1) ? l[(size_t)(s0 + u) * ldl + j] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 32; u++)
+#pragma unroll
+                for (int c = 0; c < K2T; c++) acc[c] = fma(gs[c][u], lv[u], acc[c]);
         }
     }
     if (j < k) {
@@ -416,8 +419,8 @@ extern "C" int htnk_fill_test_spd(cudaStream_t st, double* f, size_t ld, int n)
  * htnk_wl_workspace(k) * k2 * ldp doubles with ldp >= k. */
 extern "C" int htnk_wl_chunks(int k)
 {
-    int n = (k + 127) / 128;  // one 128-row slice per chunk up to 16 chunks, then longer chunks
-    return n < 1 ? 1 : (n > 16 ? 16 : n);
+    int n = (k + 31) / 32;  // one 32-row slice per chunk up to 64 chunks, then longer chunks
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
 }
 
 extern "C" int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, const double* l, size_t ldl, int k,
@@ -427,7 +430,7 @@ extern "C" int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, con
     if (k2 > 16) return -202;
     const int nch = htnk_wl_chunks(k);
     int rows = (k + nch - 1) / nch;
-    rows = (rows + 127) / 128 * 128;
+    rows = (rows + 31) / 32 * 32;
     dim3 grid((unsigned)((k + 127) / 128), (unsigned)nch);
     if (k2 == 1) wl_partial_kernel<1><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);
     else if (k2 <= 4) wl_partial_kernel<4><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);

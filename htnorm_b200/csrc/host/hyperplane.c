@@ -173,7 +173,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_CUDA(cudaStreamWaitEvent(st, ev_sbranch, 0));
     if (k2 <= 16) {
         /* W = G L: a few rows against the triangle, column-parallel with a fixed-order reduction; the partial sums
-         * park in the Sfull buffer (free from here on: 16 * k2 * kp <= k * kp doubles whenever k >= 256, else WT) */
+         * park in the Sfull buffer (free from here on) when they fit: chunks * k2 * kp <= k * kp doubles */
         const size_t need = (size_t)htnk_wl_chunks(k) * (size_t)k2 * kp;
         if (need <= (size_t)k * kp) {
             HTN_TRY(htnk_wl(st, Gp, kp, k2, F, ldz, k, Sfull, kp, W, kp));
