@@ -191,7 +191,13 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("HTN_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner (and INFO lines) to stdout at any
+        # NCCL_DEBUG level, so its log goes to a file instead (NCCL_DEBUG=INFO from outside still works, there)
+        if "HTN_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["HTN_NCCL_DEBUG"]
+        elif os.environ.get("NCCL_DEBUG", "").upper() in ("", "WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/htn_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     clocks = ClockSampler(local)
     if rank == 0:
