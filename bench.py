@@ -298,7 +298,7 @@ def main():
         alg_flops = B * (K * K + 2.0 * K * K2)                  # per launch of the sampling GEMM
         gemm_avg = sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
         achieved = alg_flops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
-        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<128,...> (sampling GEMM out = Z~ F^T + mean)",
+        roof = {"bound": "tensor", "kernel": "gemm_tma_kernel (sampling GEMM out = Z~ F^T + mean; TMA + mbarrier ring, DMMA m8n8k4 f64)",
                 "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
                 "frac": achieved / dmma_peak if achieved and dmma_peak > 0 else None,
                 "traffic": None,

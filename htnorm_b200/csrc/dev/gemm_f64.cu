@@ -161,13 +161,18 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
         int k0, kend;
         chunk_range(c, k0, kend);
         const int klim = min(BK, kend - k0);
-        const double* a_s = sA + (c % STAGES) * A_STAGE + (wm * WM * 8 + g) * LDS + t4;
-        const double* b_s = sB + (c % STAGES) * B_STAGE + (wn * WN * 8 + g) * LDS + t4;
+        // K order inside a 16-wide chunk: k4 step s multiplies k = {2s, 2s+1, 8+2s, 9+2s} - the SAME order as the
+        // TMA kernel (gemm_tma.cu), so that both kernels sum every output element in the identical sequence and a
+        // result never depends on which of them a batch / shard / chunk size selects (bit-identical shards)
+        const int tp = (t4 & 1) + 8 * (t4 >> 1);
+        const double* a_s = sA + (c % STAGES) * A_STAGE + (wm * WM * 8 + g) * LDS + tp;
+        const double* b_s = sB + (c % STAGES) * B_STAGE + (wn * WN * 8 + g) * LDS + tp;
         // does this chunk need trimming for this warp?  (all conditions are warp-uniform)
         const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < nc1) && (k0 + BK > nw);
         if (!diag && jhi == WN && klim == BK) {
 #pragma unroll
-            for (int kk = 0; kk < BK; kk += 4) {
+            for (int s4 = 0; s4 < BK / 4; s4++) {
+                const int kk = 16 * (s4 >> 2) + 2 * (s4 & 3);
                 double af[WM], bf[WN];
 #pragma unroll
                 for (int i = 0; i < WM; i++) af[i] = a_s[i * 8 * LDS + kk];
@@ -180,7 +185,8 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
             }
         } else {
 #pragma unroll
-            for (int kk = 0; kk < BK; kk += 4) {
+            for (int s4 = 0; s4 < BK / 4; s4++) {
+                const int kk = 16 * (s4 >> 2) + 2 * (s4 & 3);  // the step's smallest k is k0 + kk
                 if (kk < klim) {
                     // sub-tile j (columns nw + 8j .. +7) of a lower-triangular B is non-zero only for
                     // k <= nw + 8j + 7: the first sub-tile that still needs k = k0 + kk

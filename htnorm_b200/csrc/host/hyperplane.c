@@ -36,7 +36,7 @@ static _Thread_local int g_need_codes = 1;
 static _Thread_local int* g_async_info_out = NULL;
 static _Thread_local double* g_host_sink = NULL;
 static _Thread_local int g_host_sink_used = 0;
-#define SINK_CHUNK 8192
+#define SINK_CHUNK 32768 /* upper bound on the rows of a host-sink chunk */
 
 static void streams_view(const htn_streams_t* s, size_t offset, htnk_streams_t* v)
 {
@@ -117,7 +117,16 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
     double* const sink = g_host_sink;
     cudaStream_t copy_st = NULL;
-    if (sink && chunk > SINK_CHUNK) chunk = SINK_CHUNK;
+    if (sink) {
+        /* about 16 MB of samples per chunk: the first device->host copy starts early, and a chunk's copy (0.3 ms)
+         * still dwarfs the launch cost of its kernels */
+        size_t sc = htn_round_up(((size_t)16 << 20) / ((size_t)k * 8) + 1, 128);
+        if (sc < 1024) sc = 1024;
+        if (sc > SINK_CHUNK) sc = SINK_CHUNK;
+        const char* e = getenv("HTN_SINK_CHUNK"); /* experiments */
+        if (e && atol(e) >= 128) sc = (size_t)atol(e);
+        if (chunk > sc) chunk = sc;
+    }
     const size_t nchunks = (nsamples + chunk - 1) / chunk;
     HTN_TRY(htn_dalloc(ctx, (void**)&Z[0], chunk * ldz * 8));
     if (nchunks > 1) HTN_TRY(htn_dalloc(ctx, (void**)&Z[1], chunk * ldz * 8));

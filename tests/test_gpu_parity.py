@@ -312,6 +312,14 @@ def test_device_pointer_path_and_shard_invariance(h):
         parts.append(o)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts), full)
+    # very unequal shards select DIFFERENT GEMM kernels (TMA ring vs cp.async, by tile count): both sum K in the
+    # same order, so the bits must not depend on the split
+    B = 20000
+    full, _ = h.hyperplane_truncated_mvnorm_batch(B, t["mean"], t["cov"], t["g"], t["r"], seed0=5)
+    a, _ = h.hyperplane_truncated_mvnorm_batch(B - 100, t["mean"], t["cov"], t["g"], t["r"], seed0=5)
+    b, _ = h.hyperplane_truncated_mvnorm_batch(100, t["mean"], t["cov"], t["g"], t["r"], seed0=5 + B - 100)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([a, b]), full)
 
 
 def test_device_mode_failures_are_reported_without_host_sync(h):
