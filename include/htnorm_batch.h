@@ -35,7 +35,7 @@ typedef enum { HTN_MEM_HOST = 0, HTN_MEM_DEVICE = 1 } htn_mem_t;
 #define HTN_E_CUDA        (-201) /* a CUDA runtime call or kernel launch failed; see htn_last_error() */
 #define HTN_E_ARG         (-202) /* NULL / zero-sized / inconsistent argument */
 #define HTN_E_NO_DEVICE   (-203) /* no usable sm_100 device: there is NO CPU fallback */
-#define HTN_E_FOREIGN_RNG (-204) /* rng_t was not created by this library's constructors */
+#define HTN_E_FOREIGN_RNG (-204) /* reserved: foreign rng_t objects are served through their callbacks */
 
 /* flags */
 #define HTN_FLAG_PAPER_SIGN 0x1u /* structured precision: use the sign of Cong et al. (2017), not the
