@@ -9,6 +9,7 @@
  */
 #include "htn_internal.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 int htn_factor_init(htn_ctx_t* ctx, htn_factor_t* fa, double* f, size_t ld, int n, int want_u)
@@ -65,10 +66,16 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
      * right-looking algorithm (most parallel tiles per launch: best for small n); large n uses wide panels so
      * that the trailing update has a long K loop (W / 16 chunks instead of 8) and the trailing matrix is
      * re-read and re-written n / W instead of n / 128 times. */
+    static int la_max = -1; /* HTN_POTRF_LA (experiments): largest n factorised by the look-ahead variant */
+    if (la_max < 0) {
+        const char* e = getenv("HTN_POTRF_LA");
+        la_max = e ? atoi(e) : 4096;
+    }
     const int W = n >= 8192 ? 1024 : (n >= 2048 ? 512 : HTN_NB);
-    if (W == HTN_NB && n >= 1536) {
-        /* Mid-size n (measured: 0.91 instead of 1.00 ms at n = 2000; at n = 1000 the trailing updates are too short
-         * to pay for the cross-stream hand-offs, 0.46 instead of 0.40 ms): plain right-looking with LOOK-AHEAD.  The rank-128 update of panel j is split into (a) the next
+    if (n >= 1536 && n <= la_max) {
+        /* Mid-size n (measured: 0.90 instead of 1.00 ms at n = 2000, 2.25 instead of 2.76 ms at n = 4096; at n = 1000
+         * the trailing updates are too short to pay for the cross-stream hand-offs, 0.46 instead of 0.40 ms, and from
+         * n = 8192 the wide super-panels below win): plain right-looking with LOOK-AHEAD.  The rank-128 update of panel j is split into (a) the next
          * block column - all that potf2(j+1) and the row solve (j+1) need - on the main stream, and (b) the rest of
          * the trailing matrix on a side stream, beside potf2(j+1) + solve(j+1), which are single-CTA / latency
          * bound.  (a)_{j+1} writes what (b)_j writes, so it waits for it; nothing else is shared. */
