@@ -72,20 +72,37 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
         la_max = e ? atoi(e) : 4096;
     }
     const int W = n >= 8192 ? 1024 : (n >= 2048 ? 512 : HTN_NB);
-    if (n >= 1536 && n <= la_max) {
+    static int la_min = -1;
+    if (la_min < 0) {
+        const char* e = getenv("HTN_POTRF_LA_MIN");
+        la_min = e ? atoi(e) : 1536;
+    }
+    if (n >= la_min && n > 2 * HTN_NB && n <= la_max) {
         /* Mid-size n (measured: 0.90 instead of 1.00 ms at n = 2000, 2.25 instead of 2.76 ms at n = 4096; at n = 1000
          * the trailing updates are too short to pay for the cross-stream hand-offs, 0.46 instead of 0.40 ms, and from
          * n = 8192 the wide super-panels below win): plain right-looking with LOOK-AHEAD.  The rank-128 update of panel j is split into (a) the next
          * block column - all that potf2(j+1) and the row solve (j+1) need - on the main stream, and (b) the rest of
          * the trailing matrix on a side stream, beside potf2(j+1) + solve(j+1), which are single-CTA / latency
          * bound.  (a)_{j+1} writes what (b)_j writes, so it waits for it; nothing else is shared. */
-        cudaStream_t side = NULL;
-        cudaEvent_t ev_t = NULL, ev_b = NULL;
+        /* the side stream and the two events are created once per host thread and device, and kept */
+        static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_t, ev_b; } la = {-1, NULL, NULL, NULL};
+        if (la.device != ctx->device) {
+            if (la.device >= 0) { /* another device was current before: let go of its objects */
+                cudaEventDestroy(la.ev_t);
+                cudaEventDestroy(la.ev_b);
+                cudaStreamDestroy(la.side);
+                la.device = -1;
+            }
+            if (cudaStreamCreateWithFlags(&la.side, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.ev_t, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.ev_b, cudaEventDisableTiming) == cudaSuccess)
+                la.device = ctx->device;
+            else
+                rc = HTN_E_CUDA;
+        }
+        cudaStream_t side = la.side;
+        cudaEvent_t ev_t = la.ev_t, ev_b = la.ev_b;
         int pending_b = 0;
-        rc = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ev_t, cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming) == cudaSuccess
-                 ? 0 : HTN_E_CUDA;
         for (int j0 = 0; j0 < n && !rc; j0 += HTN_NB) {
             const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
             const int J1 = j0 + nb, rows = n - J1;
@@ -114,9 +131,6 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
             }
         }
         if (pending_b) cudaStreamWaitEvent(ctx->stream, ev_b, 0); /* the factor is complete on the main stream */
-        if (ev_t) cudaEventDestroy(ev_t);
-        if (ev_b) cudaEventDestroy(ev_b);
-        if (side) cudaStreamDestroy(side);
         if (rc == HTN_E_CUDA) htn_set_error("potrf look-ahead: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc) goto done;
         if (fa->solves) HTN_TRY(htnk_trtri_batched(ctx->stream, fa->f, ld, n, fa->dinv, fa->dinvt));
