@@ -171,6 +171,83 @@ ht_alpha_kernel(size_t nsamples, int k2, const double* d, size_t ldd, const doub
         if (c < k2) z[b * ldz + koff + c] = v[c];
 }
 
+// Fused coefficient pass for k2 <= 4 (replaces the skinny GEMM D = Z W^T + ht_alpha_kernel): one warp per sample
+// streams its z row ONCE from HBM (16-byte loads, W comes from L1/L2), reduces the k2 dot products by shuffles,
+// and lane 0 solves the k2 x k2 system (factor ls of G cov G^T) and stores alpha into the row's coefficient
+// columns.  HBM-bound: 8 (k + k2) B per sample.  (G y of src/htnorm.c:132 without the mean part; dposv :169.)
+template <int K2T>
+__global__ void __launch_bounds__(256)
+ht_coeff_kernel(size_t nsamples, int k, int k2, double* __restrict__ z, size_t ldz, size_t koff,
+                const double* __restrict__ w, size_t ldw, const double* __restrict__ c0,
+                const double* __restrict__ ls, size_t ldls, const int* __restrict__ info_s)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nsamples) return;
+    const double* zr = z + b * ldz;
+    double acc[K2T];
+#pragma unroll
+    for (int c = 0; c < K2T; c++) acc[c] = 0.0;
+    const int kev = k & ~1;
+#pragma unroll 4
+    for (int j = 2 * lane; j < kev; j += 64) {
+        const double2 zv = *reinterpret_cast<const double2*>(zr + j);
+#pragma unroll
+        for (int c = 0; c < K2T; c++) {
+            if (c < k2) {
+                const double2 wv = __ldg(reinterpret_cast<const double2*>(w + (size_t)c * ldw + j));
+                acc[c] = fma(zv.x, wv.x, acc[c]);
+                acc[c] = fma(zv.y, wv.y, acc[c]);
+            }
+        }
+    }
+    if ((k & 1) && lane == 0) {
+        const double zv = zr[k - 1];
+#pragma unroll
+        for (int c = 0; c < K2T; c++)
+            if (c < k2) acc[c] = fma(zv, w[(size_t)c * ldw + k - 1], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < K2T; c++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane == 0) {
+        const bool skip = info_s && *info_s != 0;
+        double v[K2T];
+#pragma unroll
+        for (int c = 0; c < K2T; c++) v[c] = (c < k2 && !skip) ? c0[c] - acc[c] : 0.0;
+        if (!skip) {
+            if (k2 == 1) {
+                v[0] = v[0] / ls[0];
+            } else {
+#pragma unroll
+                for (int i = 0; i < K2T; i++) {
+                    if (i < k2) {
+                        double sv = v[i];
+#pragma unroll
+                        for (int t = 0; t < K2T; t++)
+                            if (t < i) sv -= ls[(size_t)i * ldls + t] * v[t];
+                        v[i] = sv / ls[(size_t)i * ldls + i];
+                    }
+                }
+#pragma unroll
+                for (int i = K2T - 1; i >= 0; i--) {
+                    if (i < k2) {
+                        double sv = v[i];
+#pragma unroll
+                        for (int t = 0; t < K2T; t++)
+                            if (t > i && t < k2) sv -= ls[(size_t)t * ldls + i] * v[t];
+                        v[i] = sv / ls[(size_t)i * ldls + i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < K2T; c++)
+            if (c < k2) z[b * ldz + koff + c] = v[c];
+    }
+}
+
 // out[b][i] += sum_c cgt[i][c] * alpha[b][c]   (dgemv, reference src/htnorm.c:176, diagonal-cov path)
 __global__ void __launch_bounds__(256)
 ht_diag_project_kernel(size_t nsamples, int k, int k2, const double* __restrict__ cgt, size_t ldc,
@@ -437,5 +514,23 @@ extern "C" int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, con
     else wl_partial_kernel<16><<<grid, 128, 0, st>>>(g, ldg, k2, l, ldl, k, rows, part, ldp);
     if (status()) return -201;
     wl_reduce_kernel<<<dim3((unsigned)((k + 255) / 256), (unsigned)k2), 256, 0, st>>>(part, ldp, nch, k2, k, w, ldw);
+    return status();
+}
+
+/* alpha_b = (G cov G^T)^-1 (c0 - W z_b) for every sample row of Z~ in one HBM pass (k2 <= 4); alpha goes to
+ * z[b * ldz + koff + c].  ls: Cholesky factor of G cov G^T (k2 == 1: the scalar itself); *info_s != 0 -> alpha = 0. */
+extern "C" int htnk_ht_coeff(cudaStream_t st, size_t nsamples, int k, int k2, double* z, size_t ldz, size_t koff,
+                             const double* w, size_t ldw, const double* c0, const double* ls, size_t ldls,
+                             const int* info_s)
+{
+    if (nsamples == 0) return 0;
+    if (k2 < 1 || k2 > 4 || (ldz & 1) || (ldw & 1) || (reinterpret_cast<uintptr_t>(z) & 15) ||
+        (reinterpret_cast<uintptr_t>(w) & 15))
+        return -202;
+    const unsigned grid = (unsigned)((nsamples + 7) / 8);
+    if (k2 == 1)
+        ht_coeff_kernel<1><<<grid, 256, 0, st>>>(nsamples, k, k2, z, ldz, koff, w, ldw, c0, ls, ldls, info_s);
+    else
+        ht_coeff_kernel<4><<<grid, 256, 0, st>>>(nsamples, k, k2, z, ldz, koff, w, ldw, c0, ls, ldls, info_s);
     return status();
 }

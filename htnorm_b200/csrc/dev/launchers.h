@@ -106,6 +106,9 @@ int htnk_rsub_rows(cudaStream_t st, double* dst, size_t ldd, int rows, int cols,
 int htnk_diag_extract(cudaStream_t st, const double* a, size_t lda, int n, int op, double* d);
 /* m[i*ld + i] += (or =) v[i] / constant */
 int htnk_diag_set(cudaStream_t st, double* m, size_t ld, int n, const double* v, double cval);
+/* fused coefficient pass (k2 <= 4): alpha_b = (G cov G^T)^-1 (c0 - W z_b) into z[b * ldz + koff + c], one HBM pass */
+int htnk_ht_coeff(cudaStream_t st, size_t nsamples, int k, int k2, double* z, size_t ldz, size_t koff, const double* w,
+                  size_t ldw, const double* c0, const double* ls, size_t ldls, const int* info_s);
 /* W (k2 x ldw) = G (k2 x ldg) * L (k x ldl, lower triangular), k2 <= 16; part: htnk_wl_chunks(k) * k2 * ldp doubles */
 int htnk_wl_chunks(int k);
 int htnk_wl(cudaStream_t st, const double* g, size_t ldg, int k2, const double* l, size_t ldl, int k, double* part,

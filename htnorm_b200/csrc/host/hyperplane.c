@@ -231,13 +231,20 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         rng_pending = (c + 1 < nchunks) ? (buf ^ 1) : -1;
         htn_prof_mark(ctx, 2);
         if (!h_info[1]) {
-            /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
-            HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Zc, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-            if (k2 <= ALPHA_K2_MAX) {
-                HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, async ? d_info + 1 : NULL, Zc, ldz, kp));
+            if (k2 <= 4) {
+                /* one pass over Z~: D = Z W^T (the G y of src/htnorm.c:132 without the mean part) and the
+                 * k2 x k2 solve (dposv :169), fused */
+                HTN_TRY(htnk_ht_coeff(st, nb, k, k2, Zc, ldz, kp, W, kp, c0, Sm, k2p, async ? d_info + 1 : NULL));
             } else {
-                HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
-                HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Zc + kp, ldz, NULL));
+                /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
+                HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Zc, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0,
+                                     0));
+                if (k2 <= ALPHA_K2_MAX) {
+                    HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, async ? d_info + 1 : NULL, Zc, ldz, kp));
+                } else {
+                    HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
+                    HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Zc + kp, ldz, NULL));
+                }
             }
         }
         htn_prof_mark(ctx, 3);
