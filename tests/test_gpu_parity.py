@@ -476,6 +476,39 @@ def test_independent_problems_failures_and_layouts(h, oracle):
     assert rel_err(xc, base) < REL_TOL
 
 
+def test_concurrent_host_threads(h, oracle):
+    """SURVEY 8(b) threading contract: the library is reentrant, safe across host threads as long as each uses its
+    own generator (here: its own seeds).  Four threads call the batched and the single-sample entry points at the
+    same time; every result must equal the one obtained sequentially."""
+    import threading
+    c = cases.ht_case("k7_dense_333")
+    s = cases.sp_case("nn_plain")
+    seeds = [11, 22, 33, 44]
+    want_ht = [h.hyperplane_truncated_mvnorm_batch(257, c["mean"], c["cov"], c["g"], c["r"], seed0=sd)[0] for sd in seeds]
+    want_sp = [h.structured_precision_mvnorm_batch(65, s["mean"], s["a"], s["phi"], s["omega"], s["struct_mean"],
+                                                   s["a_type"], s["o_type"], seed0=sd)[0] for sd in seeds]
+    got_ht, got_sp, got_one, errs = [None] * 4, [None] * 4, [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got_ht[i] = h.hyperplane_truncated_mvnorm_batch(257, c["mean"], c["cov"], c["g"], c["r"], seed0=seeds[i])[0]
+                got_sp[i] = h.structured_precision_mvnorm_batch(65, s["mean"], s["a"], s["phi"], s["omega"],
+                                                                s["struct_mean"], s["a_type"], s["o_type"],
+                                                                seed0=seeds[i])[0]
+                got_one[i] = h.HTNGenerator(seeds[i]).hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"])
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for i in range(4):
+        assert np.array_equal(got_ht[i], want_ht[i]) and np.array_equal(got_sp[i], want_sp[i])
+        assert np.array_equal(got_one[i], want_ht[i][0])   # single-sample call == sample 0 of the batch (seed_i = seed0 + i)
+
+
 def test_edge_cases_empty_ragged_chunked(h, oracle):
     """empty batch; independent problems too large for the one-CTA kernel (k > 128: one factorisation each);
     device-resident seed array; a host-memory batch long enough to be drawn in several overlapped chunks
