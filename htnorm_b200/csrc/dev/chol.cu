@@ -93,7 +93,27 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
 
     // the strictly upper part of a full block may hold junk (diagonal tiles of earlier trailing updates): it is
     // never used - sub-block loads read c <= r, diagonal tiles mirror, the write-back masks too
-    load_block<NTP>(S, a, ld, nb, tid, true);
+    // Full, aligned blocks take the streaming path: only the lower triangle is loaded (16-byte LDGSTS), the zeros
+    // above the diagonal go to global memory right away (fire-and-forget), and every 8 x 8 tile of L is stored the
+    // moment its panel is final - there is no write-back phase at the end.
+    const bool fastio = nb == NB && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+    if (fastio) {
+        for (int idx = tid; idx < NB * (NB / 2); idx += NTP) {
+            const int r = idx >> 6, c = 2 * (idx & 63);
+            if (c <= r) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * LDB + c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(a + (size_t)r * ld + c));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        for (int idx = tid; idx < NB * (NB / 2); idx += NTP) {
+            const int r = idx >> 6, c = 2 * (idx & 63);
+            if (c > r) *reinterpret_cast<double2*>(a + (size_t)r * ld + c) = make_double2(0.0, 0.0);
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::);
+    } else {
+        load_block<NTP>(S, a, ld, nb, tid, true);
+    }
     for (int idx = tid; idx < NB * LDP; idx += NTP) P[idx] = 0.0;
     for (int idx = tid; idx < 8 * 12; idx += NTP) Tsm[idx] = 0.0;
     const int npanels = (nb + 7) >> 3;
@@ -189,6 +209,7 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
                 if (j0 + 2 * t4 + 1 >= nb) v.y = 0.0;
                 *reinterpret_cast<double2*>(S + row * LDB + j0 + 2 * t4) = v;
                 *reinterpret_cast<double2*>(P + row * LDP + 2 * t4) = v;
+                if (fastio) *reinterpret_cast<double2*>(a + (size_t)row * ld + j0 + 2 * t4) = v;  // final: out it goes
             }
         }
         __syncthreads();
@@ -249,14 +270,14 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     const bool failed = nfact < nb;
     // write L back: lower triangle, zeros above; nothing beyond a failed column is meaningful
     const int cmax = (nfact + 7) & ~7;
-    if (nb == NB && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
-        for (int idx = tid; idx < NB * (NB / 2); idx += NTP) {  // 16 bytes per store
-            const int r = idx >> 6, c = 2 * (idx & 63);
-            double2 v = *reinterpret_cast<const double2*>(S + r * LDB + c);
-            if (c > r || c >= cmax) v.x = 0.0;
-            if (c + 1 > r || c + 1 >= cmax) v.y = 0.0;
-            *reinterpret_cast<double2*>(a + (size_t)r * ld + c) = v;
-        }
+    if (fastio) {
+        // everything is out already; after a failure the columns from the failing panel on are zeroed, as the
+        // write-back of the general path does
+        if (failed)
+            for (int idx = tid; idx < NB * (NB / 2); idx += NTP) {
+                const int r = idx >> 6, c = 2 * (idx & 63);
+                if (c >= cmax && c <= r) *reinterpret_cast<double2*>(a + (size_t)r * ld + c) = make_double2(0.0, 0.0);
+            }
     } else {
         for (int idx = tid; idx < NB * NB; idx += NTP) {
             const int r = idx >> 7, c = idx & (NB - 1);
