@@ -76,11 +76,137 @@ constexpr int LDP = 12;      // panel row stride (doubles): 8 + 4 keeps the DMMA
 constexpr int NPAN = NB / 8;  // 16 panels
 constexpr int NTP = 512;      // potf2: 16 warps, one 8-row tile of the panel each
 
+// ---- fused panel: the row blocks under the diagonal block, solved in the same launch (CTAs 1, 2, ...) ----
+// CTA 0 (the potf2 role below) publishes, per 8-column sub-panel b, the inverse T_b of the 8 x 8 factor (scratch
+// `tscr`) and - by storing its tiles of L straight into the matrix - the sub-panel's columns of L11; then it
+// releases flags[b] = epoch.  A row-block CTA acquires the flag, stages T_b and L11[8(b+1).., 8b..8b+7], forms
+// its X_b = A_b T_b^T and updates its later columns, all on DMMA (32 rows per CTA): it trails the factorisation by about one
+// sub-panel, so the panel solve (13 us as a kernel of its own) disappears behind the 128-pivot chain.
+// No cluster is needed: the only producer is CTA 0, which never waits, so co-residency is irrelevant for
+// progress; flags carry a launch-unique (even) epoch and are never reset; epoch | 1 means "not PD, stop".
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int RB = 32;  // rows per row-block CTA: 32 x 128 x 128 FMAs (8 k cycles of one SM's FP64 pipe) keep pace with
+                        // the 128-pivot chain of CTA 0; a 128-row block (33 k cycles) would not
+
+__device__ void panel_rows_role(double* __restrict__ xr, size_t ld, int nrows, const double* __restrict__ adiag,
+                                const double* __restrict__ tscr, const unsigned* __restrict__ flags, unsigned epoch,
+                                double* sm)
+{
+    // Warps 12..15 are LOADERS: they acquire flags[b+1] and stage T_{b+1} and L11's sub-panel b+1 into the other
+    // half of the double buffers while warps 0..11 compute sub-panel b (4 row tiles x 3 column groups).  One CTA
+    // barrier per sub-panel; the compute warps meet once more, among themselves, between the solve and the update.
+    double* S = sm;                       // [RB][LDB]     this CTA's rows of the panel
+    double* Pb = sm + RB * LDB;           // [2][NB][LDP]  L11[:, 8b .. 8b+7] (rows > 8b+7 used), double-buffered
+    double* Px = Pb + 2 * NB * LDP;       // [RB][LDP]     this CTA's X_b (A operand of its update)
+    double* Tl = Px + RB * LDP;           // [2][8][12]    T_b, double-buffered
+    __shared__ int s_stop[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    constexpr int NLOAD = 128, NCOMP = NTP - NLOAD;
+    const bool loader = tid >= NCOMP;
+    const int ltid = tid - NCOMP;
+    for (int idx = tid; idx < RB * (NB / 2); idx += NTP) {
+        const int r = idx >> 6, c = 2 * (idx & 63);
+        if (r < nrows) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * LDB + c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(xr + (size_t)r * ld + c));
+        } else {
+            *reinterpret_cast<double2*>(S + r * LDB + c) = make_double2(0.0, 0.0);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+
+    auto stage = [&](int bb) {  // loaders only
+        const int buf = bb & 1;
+        if (ltid == 0) {
+            unsigned v;
+            do v = ld_acquire_u32(flags + bb); while ((v & ~1u) != epoch);  // plain spin: one L2 round trip per poll
+            s_stop[buf] = (int)(v & 1u);                                     // epoch | 1: not positive definite, stop
+        }
+        asm volatile("bar.sync 2, %0;\n" ::"n"(NLOAD) : "memory");           // the loaders: flag seen
+        if (s_stop[buf]) return;
+        double* Tb = Tl + buf * 96;
+        double* Pd = Pb + buf * NB * LDP;
+        if (ltid < 64) Tb[(ltid >> 3) * 12 + (ltid & 7)] = __ldcg(tscr + bb * 64 + ltid);
+        for (int idx = ltid; idx < (NB - 8 * (bb + 1)) * 8; idx += NLOAD) {
+            const int r = 8 * (bb + 1) + (idx >> 3), c = idx & 7;
+            Pd[r * LDP + c] = __ldcg(adiag + (size_t)r * ld + 8 * bb + c);
+        }
+    };
+
+    if (loader) stage(0);
+    __syncthreads();
+    const int rt = warp & 3, cgp = warp >> 2;  // compute warps: row tile, column group (0..2)
+    const int row = rt * 8 + g;
+    for (int b = 0; b < NPAN; b++) {
+        const int buf = b & 1;
+        if (s_stop[buf]) break;
+        if (loader) {
+            if (b + 1 < NPAN) stage(b + 1);
+        } else {
+            const double* Tb = Tl + buf * 96;
+            const double* Pd = Pb + buf * NB * LDP;
+            if (cgp == 0) {  // X_b tile of row tile rt
+                const double* ar = S + row * LDB + 8 * b;
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                dmma_sub(c0, c1, ar[t4], Tb[g * 12 + t4]);
+                dmma_sub(e0, e1, ar[4 + t4], Tb[g * 12 + 4 + t4]);
+                const double2 v = make_double2(c0 + e0, c1 + e1);
+                *reinterpret_cast<double2*>(Px + row * LDP + 2 * t4) = v;
+                if (row < nrows) *reinterpret_cast<double2*>(xr + (size_t)row * ld + 8 * b + 2 * t4) = v;  // final
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NCOMP) : "memory");  // the compute warps: X_b is in Px
+            // later columns tc = b+1+cgp, +3, ...: C[row tile][tc] -= X_b * L11[tc][b]^T, at most five tiles: one pass
+            const double a0 = -Px[row * LDP + t4], a1 = -Px[row * LDP + 4 + t4];
+            double* crow = S + row * LDB + 2 * t4;
+            const int tc0 = b + 1 + cgp;
+            double2 c[5];
+            double b0[5], b1[5];
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int tc = min(tc0 + 3 * u, NPAN - 1);
+                b0[u] = Pd[(tc * 8 + g) * LDP + t4];
+                b1[u] = Pd[(tc * 8 + g) * LDP + 4 + t4];
+                c[u] = *reinterpret_cast<const double2*>(crow + tc * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                double e0 = 0.0, e1 = 0.0;
+                dmma_sub(c[u].x, c[u].y, a0, b0[u]);
+                dmma_sub(e0, e1, a1, b1[u]);
+                c[u].x += e0;
+                c[u].y += e1;
+            }
+#pragma unroll
+            for (int u = 0; u < 5; u++)
+                if (tc0 + 3 * u < NPAN) *reinterpret_cast<double2*>(crow + (tc0 + 3 * u) * 8) = c[u];
+        }
+        __syncthreads();  // sub-panel b consumed, sub-panel b+1 staged
+    }
+}
+
 __global__ void __launch_bounds__(NTP, 1)
 potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __restrict__ rdiag_out,
-             int* __restrict__ info)
+             int* __restrict__ info, int nrows_below, double* __restrict__ tscr, unsigned* __restrict__ flags,
+             unsigned epoch)
 {
     extern __shared__ double sm[];
+    if (blockIdx.x > 0) {  // a row block under the diagonal block
+        const int r0 = ((int)blockIdx.x - 1) * RB;
+        panel_rows_role(a + (size_t)(NB + r0) * ld, ld, min(RB, nrows_below - r0), a, tscr, flags, epoch, sm);
+        return;
+    }
     double* S = sm;                  // [NB][LDB]  the block (lower triangle meaningful)
     double* P = sm + NB * LDB;       // [NB][LDP]  current panel: L[:, 8b .. 8b+7]
     double* rdiag = P + NB * LDP;    // [NB]       1 / L[j][j]
@@ -171,6 +297,7 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 Tsm[r * 12 + lane] = w[r];
+                if (tscr != nullptr) tscr[bb * 64 + r * 8 + lane] = w[r];  // for the row-block CTAs
                 if (lane == r && j0 + r < nb) rdiag[j0 + r] = w[r];  // T[r][r] = 1 / L[r][r]
             }
         }
@@ -180,7 +307,14 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
     __syncthreads();
     int nfact = nb;
     for (int b = 0; b < npanels; b++) {
-        if (s_fail) { nfact = s_fail - 1; break; }
+        if (s_fail) {
+            nfact = s_fail - 1;
+            if (flags != nullptr && tid == 0) {  // wake every waiting row block and tell it to stop
+                __threadfence();
+                for (int q = b; q < NPAN; q++) st_release_u32(flags + q, epoch | 1u);
+            }
+            break;
+        }
         const int j0 = 8 * b;
         // ---- panel: 8-row tile tr = b + warp, X = A_tile * T^T (the diagonal tile is read symmetrically) ----
         for (int tr = b + warp; tr < npanels; tr += NTP / 32) {
@@ -213,6 +347,12 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
             }
         }
         __syncthreads();
+        // sub-panel b of L11 and T_b are in global memory: release the row blocks.  Done by a thread of warp 4, which
+        // has no part in the update phase - the fence must not sit on the factor warp's chain
+        if (flags != nullptr && tid == 128) {
+            __threadfence();
+            st_release_u32(flags + b, epoch);
+        }
         // ---- rank-8 update of the trailing lower triangle on the tensor cores, with look-ahead ----
         if (b + 1 < npanels) {
             if (warp == 0) {  // next diagonal tile: update it, then factor it
@@ -438,16 +578,46 @@ trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __
 
 }  // namespace
 
-extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info)
+static int potf2_launch(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info,
+                        int nrows_below, double* tscr, unsigned* flags, int* rows_done)
 {
+    if (rows_done) *rows_done = 0;
     if (nb <= 0) return 0;
     if (nb > NB) return -202;
-    const size_t smem = (size_t)(NB * LDB + NB * LDP + NB + 8 * 12) * sizeof(double);
+    // max over the two roles: [NB][LDB] + [NB][LDP] + NB + 96  |  [RB][LDB] + 2 [NB][LDP] + [RB][LDP] + 2 * 96
+    const size_t smem = (size_t)(NB * LDB + 2 * NB * LDP + NB + 2 * 8 * 12) * sizeof(double);
     if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
-    potf2_kernel<<<1, NTP, smem, st>>>(a, ld, nb, col0, rdiag, info);
+    // the fused panel needs the streaming path of the kernel (full, aligned block) and its scratch
+    // (very tall panels keep the separate row-solve kernel: its 128-row CTAs amortise the load of L11 better than
+    // hundreds of 32-row followers; measured break-even between 8 k and 16 k rows)
+    const bool fused = nrows_below > 0 && nrows_below <= 8192 && tscr != nullptr && flags != nullptr && nb == NB &&
+                       (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+    unsigned grid = 1, epoch = 0;
+    if (fused) {
+        static unsigned seq = 0;
+        do epoch = __atomic_add_fetch(&seq, 1u, __ATOMIC_RELAXED) << 1; while (epoch == 0);  // even, unique per launch, never 0
+        grid = 1u + (unsigned)((nrows_below + RB - 1) / RB);
+        if (rows_done) *rows_done = 1;
+    }
+    potf2_kernel<<<grid, NTP, smem, st>>>(a, ld, nb, col0, rdiag, info, fused ? nrows_below : 0, fused ? tscr : nullptr,
+                                          fused ? flags : nullptr, epoch);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info)
+{
+    return potf2_launch(st, a, ld, nb, col0, rdiag, info, 0, nullptr, nullptr, nullptr);
+}
+
+// diagonal block + the nrows_below rows under it (L21 = A21 L11^-T) in one launch when the block is full and aligned
+// (*rows_done = 1); otherwise only the diagonal block is factorised (*rows_done = 0: the caller runs htnk_trsm_rows).
+// tscr: 16 * 64 doubles, flags: 17 unsigned (zero-initialised once, never reset), both private to the factorisation.
+extern "C" int htnk_potf2_panel(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info,
+                                int nrows_below, double* tscr, unsigned* flags, int* rows_done)
+{
+    return potf2_launch(st, a, ld, nb, col0, rdiag, info, nrows_below, tscr, flags, rows_done);
 }
 
 extern "C" int htnk_trtri_batched(cudaStream_t st, const double* f, size_t ld, int n, double* dinv, double* dinvt)

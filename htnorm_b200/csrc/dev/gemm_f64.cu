@@ -295,7 +295,12 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
         else {
             // wide N: 128 x 64 tiles, unless that leaves most of the 148 SMs (x2 CTAs) without a tile
             long long ctas64 = (long long)tiles_m * ((N + 63) / 64);
-            bn = ctas64 < 148 ? 32 : wide_config();
+            static int min64 = -1;  // HTN_GEMM_MIN64 (experiments): fewest 128 x 64 tiles that still take the wide kernel
+            if (min64 < 0) {
+                const char* e = getenv("HTN_GEMM_MIN64");
+                min64 = e ? atoi(e) : 148;
+            }
+            bn = ctas64 < min64 ? 32 : wide_config();
         }
     }
     GemmParams p;

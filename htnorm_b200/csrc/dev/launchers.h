@@ -75,6 +75,11 @@ void htnk_gemm_guard_next(const int* flag);
  * strictly-upper := 0.  rdiag (device, nb doubles, may be NULL) receives 1 / L[j][j].  *info (device int)
  * receives col0 + j + 1 at the first pivot <= 0 (only if it still holds 0). */
 int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info);
+/* diagonal block + the nrows_below rows under it (L21 = A21 L11^-T) in ONE launch when the block is full (nb = 128)
+ * and 16-byte aligned: *rows_done = 1; otherwise only the block is factorised and *rows_done = 0 (run htnk_trsm_rows).
+ * tscr: 16 * 64 doubles, flags: 17 unsigned - scratch private to the factorisation, no initialisation needed */
+int htnk_potf2_panel(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info, int nrows_below,
+                     double* tscr, unsigned* flags, int* rows_done);
 /* x (nrows x nb, leading dimension ldx) := x * L^-T with the nb x nb lower block l; rdiag = 1 / diag(l) */
 int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows, const double* l, size_t ldl, int nb,
                    const double* rdiag);

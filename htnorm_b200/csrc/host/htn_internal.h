@@ -65,6 +65,7 @@ typedef struct {
     double* dinv;   /* nblk x 128 x 128: inverse of each diagonal block of L */
     double* dinvt;  /* transposes of the above */
     double* rdiag;  /* 1 / L[j][j] */
+    double* pscr;   /* scratch of the fused panel kernel: 16 x 64 doubles (8 x 8 inverse factors) + 17 flags */
     double* linv;   /* n x ld: explicit L^-1 (lower), NULL until htn_factor_make_inverse */
     double* linvt;  /* its transpose */
     int nblk;

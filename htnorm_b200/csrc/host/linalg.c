@@ -23,6 +23,8 @@ int htn_factor_init(htn_ctx_t* ctx, htn_factor_t* fa, double* f, size_t ld, int 
     fa->solves = want_u;
     size_t blk = (size_t)HTN_NB * HTN_NB * sizeof(double);
     HTN_TRY(htn_dalloc(ctx, (void**)&fa->rdiag, (size_t)fa->nblk * HTN_NB * sizeof(double)));
+    HTN_TRY(htn_dalloc(ctx, (void**)&fa->pscr, (16 * 64 + 32) * sizeof(double)));
+    HTN_CUDA(cudaMemsetAsync(fa->pscr, 0, (16 * 64 + 32) * sizeof(double), ctx->stream));
     if (fa->solves) {
         HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinv, blk * fa->nblk));
         HTN_TRY(htn_dalloc(ctx, (void**)&fa->dinvt, blk * fa->nblk));
@@ -40,9 +42,10 @@ void htn_factor_free(htn_ctx_t* ctx, htn_factor_t* fa)
     htn_dfree(ctx, fa->dinvt);
     htn_dfree(ctx, fa->u);
     htn_dfree(ctx, fa->rdiag);
+    htn_dfree(ctx, fa->pscr);
     htn_dfree(ctx, fa->linv);
     htn_dfree(ctx, fa->linvt);
-    fa->dinv = fa->dinvt = fa->u = fa->rdiag = fa->linv = fa->linvt = NULL;
+    fa->dinv = fa->dinvt = fa->u = fa->rdiag = fa->linv = fa->linvt = fa->pscr = NULL;
 }
 
 int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa)
@@ -107,9 +110,12 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
             const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
             const int J1 = j0 + nb, rows = n - J1;
             double* ajj = fa->f + (size_t)j0 * ld + j0;
-            rc = htnk_potf2(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info);
+            int rows_done = 0;
+            rc = htnk_potf2_panel(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info, rows, fa->pscr,
+                                  (unsigned*)(fa->pscr + 16 * 64), &rows_done);
             if (rc || rows <= 0) break;
-            rc = htnk_trsm_rows(ctx->stream, fa->f + (size_t)J1 * ld + j0, ld, rows, ajj, ld, nb, fa->rdiag + j0);
+            if (!rows_done)
+                rc = htnk_trsm_rows(ctx->stream, fa->f + (size_t)J1 * ld + j0, ld, rows, ajj, ld, nb, fa->rdiag + j0);
             if (rc) break;
             const int nb2 = rows < HTN_NB ? rows : HTN_NB, J2 = J1 + nb2, R2 = n - J2;
             const double* pan = fa->f + (size_t)J1 * ld + j0; /* L[J1:, j0:J1] */
@@ -145,8 +151,12 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
             if (j0 > J0) /* A[j0:, j0:j0+nb] -= L[j0:, J0:j0] * L[j0:j0+nb, J0:j0]^T */
                 HTN_TRY(htnk_gemm_tn(ctx->stream, n - j0, nb, j0 - J0, -1.0, fa->f + (size_t)j0 * ld + J0, ld,
                                      fa->f + (size_t)j0 * ld + J0, ld, 1.0, ajj, ld, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-            HTN_TRY(htnk_potf2(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info));
-            if (rows > 0) /* panel: L21 = A21 * L11^-T, rows independent, in place */
+            /* diagonal block and, in the same launch when the block is full, the panel under it
+             * (L21 = A21 * L11^-T, rows independent, in place) */
+            int rows_done = 0;
+            HTN_TRY(htnk_potf2_panel(ctx->stream, ajj, ld, nb, j0, fa->rdiag + j0, d_info, rows, fa->pscr,
+                                     (unsigned*)(fa->pscr + 16 * 64), &rows_done));
+            if (rows > 0 && !rows_done)
                 HTN_TRY(htnk_trsm_rows(ctx->stream, fa->f + (size_t)(j0 + nb) * ld + j0, ld, rows, ajj, ld, nb,
                                        fa->rdiag + j0));
         }
