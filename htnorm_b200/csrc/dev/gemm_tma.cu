@@ -14,15 +14,16 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "launchers.h"
 
 namespace {
 
 // three stages of 24 KB: three CTAs (12 warps) per SM fit in shared memory, and in registers at 168 per thread
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, NT = 128;
-constexpr int WM = 8, WN = 4;  // warp tile 64 x 32 in m8n8 units
-constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
+constexpr int BN = 64, BK = 16, STAGES = 3, NT = 128;
+constexpr int WN = 4;  // warp tile (8 WM) x 32 in m8n8 units; WM = 8 (CTA tile 128 x 64) or 4 (64 x 64) is a template parameter
+constexpr int B_BYTES = BN * BK * 8;
 constexpr int AHEAD = 1;  // chunks issued ahead of the one being consumed
 
 struct TmaGemmParams {
@@ -110,10 +111,12 @@ __device__ __forceinline__ void tile_chunk(const TmaGemmParams& p, const TileK& 
 // 128-row slab: every CTA then runs the same number of K chunks (the longest and the shortest loop together,
 // as in causal-attention schedulers), and the TMA ring keeps streaming across the tile boundary, so the
 // second tile's first chunks are already in flight while the first tile's epilogue is being written.
-__global__ void __launch_bounds__(NT, 3)
+template <int WM, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TmaGemmParams p)
 {
+    constexpr int BM = 16 * WM, A_BYTES = BM * BK * 8;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment for the 128B swizzle pattern (the swizzle XORs address bits [4:6] with [7:9])
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -326,6 +329,20 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
         (reinterpret_cast<uintptr_t>(B) & 15))
         return 1;
     CUtensorMap tmA, tmB;
+    // CTA tile 128 x 64 (3 CTAs/SM) or 64 x 64 (4 CTAs/SM): the same speed on a full device (measured), so the small
+    // tile is taken when the large one would leave SMs without work.  HTN_TMA_WM = 8 / 4 forces one (experiments).
+    static int wm_env = -1;
+    if (wm_env < 0) {
+        const char* e = getenv("HTN_TMA_WM");
+        wm_env = e ? atoi(e) : 0;
+    }
+    int wm_cfg = wm_env == 4 || wm_env == 8 ? wm_env : 8;
+    if (wm_env != 4 && wm_env != 8) {
+        const long long t128 = (long long)((M + 127) / 128) * ((N + BN - 1) / BN);
+        const long long work = (mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_C_LOWER) ? t128 / 2 : t128;
+        if (work < 3 * 148) wm_cfg = 4;
+    }
+    const int BM = 16 * wm_cfg, A_BYTES = BM * BK * 8;
     if (!make_map(&tmA, A, lda, M, K, BM) || !make_map(&tmB, B, ldb, N, K, BN)) return 1;
     TmaGemmParams p;
     p.M = M; p.N = N; p.K = K;
@@ -340,9 +357,10 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     const unsigned grid = p.paired ? (unsigned)p.tiles_m * (unsigned)((p.tiles_n + 1) / 2)
                                    : (unsigned)p.tiles_m * (unsigned)p.tiles_n;
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
-    if (cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    auto kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4> : gemm_tma_kernel<8, 3>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
-    gemm_tma_kernel<<<grid, NT, smem, st>>>(tmA, tmB, p);
+    kern<<<grid, NT, smem, st>>>(tmA, tmB, p);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }
