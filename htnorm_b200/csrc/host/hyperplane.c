@@ -88,7 +88,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
      * are drawn WHILE cov is being factorised, and chunk c+1's while chunk c is in the sampling GEMM */
     cudaStream_t side = NULL, side2 = NULL; /* side2: the G cov G^T branch, independent of chol(cov) */
     cudaEvent_t ev_sym = NULL, ev_sbranch = NULL;
-    cudaEvent_t ev_fork = NULL, ev_rng[2] = {NULL, NULL}, ev_gemm[2] = {NULL, NULL};
+    cudaEvent_t ev_fork = NULL, ev_rng[2] = {NULL, NULL}, ev_gemm[2] = {NULL, NULL}, ev_sub = NULL;
     int rng_pending = -1; /* buffer whose generator launch the main stream has not yet waited for */
     htn_factor_t fa, fs;
     memset(&fa, 0, sizeof(fa));
@@ -117,15 +117,16 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
     double* const sink = g_host_sink;
     cudaStream_t copy_st = NULL;
+    /* Host-memory callers: the normals of a whole Z~ chunk are still drawn in ONE launch (every stream in parallel,
+     * beside the factorisation), but the coefficient pass, the sampling GEMM and the device->host copy then go
+     * through it in SUB-chunks, so that the first copy starts early and the copy engine never waits: the first
+     * sub-chunk is small (about 8 MB of samples), the following ones double up to about 64 MB. */
+    size_t sub0 = 0, submax = 0;
     if (sink) {
-        /* about 16 MB of samples per chunk: the first device->host copy starts early, and a chunk's copy (0.3 ms)
-         * still dwarfs the launch cost of its kernels */
-        size_t sc = htn_round_up(((size_t)16 << 20) / ((size_t)k * 8) + 1, 128);
-        if (sc < 1024) sc = 1024;
-        if (sc > SINK_CHUNK) sc = SINK_CHUNK;
-        const char* e = getenv("HTN_SINK_CHUNK"); /* experiments */
-        if (e && atol(e) >= 128) sc = (size_t)atol(e);
-        if (chunk > sc) chunk = sc;
+        sub0 = htn_round_up(((size_t)8 << 20) / ((size_t)k * 8) + 1, 128);
+        submax = htn_round_up(((size_t)64 << 20) / ((size_t)k * 8) + 1, 128);
+        const char* e = getenv("HTN_SINK_CHUNK"); /* experiments: fixed sub-chunk rows */
+        if (e && atol(e) >= 128) sub0 = submax = (size_t)atol(e);
     }
     const size_t nchunks = (nsamples + chunk - 1) / chunk;
     HTN_TRY(htn_dalloc(ctx, (void**)&Z[0], chunk * ldz * 8));
@@ -137,6 +138,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_sym, cudaEventDisableTiming));
     HTN_CUDA(cudaEventCreateWithFlags(&ev_sbranch, cudaEventDisableTiming));
+    if (sink) HTN_CUDA(cudaEventCreateWithFlags(&ev_sub, cudaEventDisableTiming));
     for (int e = 0; e < 2; e++) {
         HTN_CUDA(cudaEventCreateWithFlags(&ev_rng[e], cudaEventDisableTiming));
         HTN_CUDA(cudaEventCreateWithFlags(&ev_gemm[e], cudaEventDisableTiming));
@@ -230,35 +232,42 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         HTN_CUDA(cudaStreamWaitEvent(st, ev_rng[buf], 0));
         rng_pending = (c + 1 < nchunks) ? (buf ^ 1) : -1;
         htn_prof_mark(ctx, 2);
-        if (!h_info[1]) {
-            if (k2 <= 4) {
-                /* one pass over Z~: D = Z W^T (the G y of src/htnorm.c:132 without the mean part) and the
-                 * k2 x k2 solve (dposv :169), fused */
-                HTN_TRY(htnk_ht_coeff(st, nb, k, k2, Zc, ldz, kp, W, kp, c0, Sm, k2p, async ? d_info + 1 : NULL));
-            } else {
-                /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
-                HTN_TRY(htnk_gemm_tn(st, (int)nb, k2, k, 1.0, Zc, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0,
-                                     0));
-                if (k2 <= ALPHA_K2_MAX) {
-                    HTN_TRY(htnk_ht_alpha(st, nb, k2, D, k2p, c0, Sm, k2p, async ? d_info + 1 : NULL, Zc, ldz, kp));
+        size_t sub = sink ? sub0 : nb;
+        for (size_t s0 = 0; s0 < nb; s0 += sub, sub = sub * 2 < submax ? sub * 2 : (submax ? submax : sub)) {
+            const size_t sn = nb - s0 < sub ? nb - s0 : sub;
+            double* Zs = Zc + s0 * ldz;
+            double* outs = out + (b0 + s0) * (size_t)k;
+            if (!h_info[1]) {
+                if (k2 <= 4) {
+                    /* one pass over Z~: D = Z W^T (the G y of src/htnorm.c:132 without the mean part) and the
+                     * k2 x k2 solve (dposv :169), fused */
+                    HTN_TRY(htnk_ht_coeff(st, sn, k, k2, Zs, ldz, kp, W, kp, c0, Sm, k2p, async ? d_info + 1 : NULL));
                 } else {
-                    HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)nb, k2, c0));
-                    HTN_TRY(htnk_copy2d(st, D, k2p, (int)nb, k2, Zc + kp, ldz, NULL));
+                    /* D = Z W^T   (the G y of src/htnorm.c:132 without the mean part) */
+                    HTN_TRY(htnk_gemm_tn(st, (int)sn, k2, k, 1.0, Zs, ldz, W, kp, 0.0, D, k2p, NULL, HTNK_GEMM_FULL, 0, 0,
+                                         0));
+                    if (k2 <= ALPHA_K2_MAX) {
+                        HTN_TRY(htnk_ht_alpha(st, sn, k2, D, k2p, c0, Sm, k2p, async ? d_info + 1 : NULL, Zs, ldz, kp));
+                    } else {
+                        HTN_TRY(alpha_large(ctx, &fs, D, k2p, (int)sn, k2, c0));
+                        HTN_TRY(htnk_copy2d(st, D, k2p, (int)sn, k2, Zs + kp, ldz, NULL));
+                    }
                 }
             }
+            htn_prof_mark(ctx, 3);
+            /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
+            if (async) htnk_gemm_guard_next(d_info); /* cov not PD: the launch is a no-op, out stays untouched */
+            HTN_TRY(htnk_gemm_tn(st, (int)sn, k, (int)(kp + (size_t)k2), 1.0, Zs, ldz, F, ldz, 0.0, outs, (size_t)k, mean,
+                                 HTNK_GEMM_B_LOWER, k, (int)kp, 0));
+            htn_prof_mark(ctx, 4);
+            if (sink) { /* ship this sub-chunk home while the next one is being computed */
+                HTN_CUDA(cudaEventRecord(ev_sub, st));
+                HTN_CUDA(cudaStreamWaitEvent(copy_st, ev_sub, 0));
+                HTN_CUDA(cudaMemcpyAsync(sink + (b0 + s0) * (size_t)k, outs, sn * (size_t)k * 8, cudaMemcpyDeviceToHost,
+                                         copy_st));
+            }
         }
-        htn_prof_mark(ctx, 3);
-        /* out = Z~ F^T + mean   (dtrmv + daxpy, src/htnorm_distributions.c:81-83; dgemv, src/htnorm.c:176) */
-        if (async) htnk_gemm_guard_next(d_info); /* cov not PD: the launch is a no-op, out stays untouched */
-        HTN_TRY(htnk_gemm_tn(st, (int)nb, k, (int)(kp + (size_t)k2), 1.0, Zc, ldz, F, ldz, 0.0, out + b0 * (size_t)k,
-                             (size_t)k, mean, HTNK_GEMM_B_LOWER, k, (int)kp, 0));
         HTN_CUDA(cudaEventRecord(ev_gemm[buf], st));
-        htn_prof_mark(ctx, 4);
-        if (sink) { /* ship this chunk home while the next one is being computed */
-            HTN_CUDA(cudaStreamWaitEvent(copy_st, ev_gemm[buf], 0));
-            HTN_CUDA(cudaMemcpyAsync(sink + b0 * (size_t)k, out + b0 * (size_t)k, nb * (size_t)k * 8,
-                                     cudaMemcpyDeviceToHost, copy_st));
-        }
     }
     if (sink) {
         HTN_CUDA(cudaStreamSynchronize(copy_st));
@@ -279,6 +288,7 @@ done:
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_sym) cudaEventDestroy(ev_sym);
     if (ev_sbranch) cudaEventDestroy(ev_sbranch);
+    if (ev_sub) cudaEventDestroy(ev_sub);
     if (side2) cudaStreamDestroy(side2);
     if (copy_st) cudaStreamDestroy(copy_st);
     for (int e = 0; e < 2; e++) {
