@@ -140,6 +140,19 @@ def test_potrf_not_pd_and_nan(h):
     a[0, 0] = np.nan
     assert lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 0, 0, None) == 0
     assert np.isnan(l[:, 0]).all()
+    # failure INSIDE a full 128-block that has rows under it: the row-block CTAs of the fused panel kernel are
+    # following the factorisation through flags and must be told to stop (no hang); the columns to the left of the
+    # failing panel are those of the true factor
+    n = 600
+    for bad in (70, 300):
+        a = cases.spd(rng, n)
+        good = np.linalg.cholesky(a)
+        a[bad, bad] = -1.0
+        a = np.ascontiguousarray(a)
+        l = np.empty((n, n))
+        assert lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 0, 0, None) == bad + 1
+        done = (bad // 8) * 8
+        assert np.abs(l[:, :done] - good[:, :done]).max() < 1e-11
 
 
 # ------------------------------------------------------------------ samplers vs golden / oracle
