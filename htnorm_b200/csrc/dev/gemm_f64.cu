@@ -221,13 +221,15 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
         for (int j = 0; j < WN; j++) {
             const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
             if (n >= p.N) continue;
-            double v0 = p.alpha * acc[i][j][0];
-            double v1 = p.alpha * acc[i][j][1];
             double* cp = p.C + (size_t)m * p.ldc + n;
             const bool two = (n + 1 < p.N);
-            if (p.bias) {
-                v0 += p.bias[n];
-                if (two) v1 += p.bias[n + 1];
+            double v0, v1;
+            if (p.bias) {  // explicitly fused, as in gemm_tma.cu: the two kernels must round alike
+                v0 = fma(p.alpha, acc[i][j][0], p.bias[n]);
+                v1 = two ? fma(p.alpha, acc[i][j][1], p.bias[n + 1]) : 0.0;
+            } else {
+                v0 = p.alpha * acc[i][j][0];
+                v1 = p.alpha * acc[i][j][1];
             }
             if (vec_ok && two) {
                 if (p.beta != 0.0) {

@@ -247,7 +247,27 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
         }
 
-        // epilogue of this tile
+        // epilogue of this tile.  Common case first (interior tile, beta = 0, 16-byte aligned C): column pair by column
+        // pair - the two bias values are fetched once for the eight rows of the pair - and nothing but FMA + STG.128
+        if (vec_ok && p.beta == 0.0 && n0 + BN <= p.N && m0 + BM <= p.M) {
+            double* crow = p.C + (size_t)(m0 + wm * WM * 8 + g) * p.ldc + nw + 2 * t4;
+#pragma unroll
+            for (int j = 0; j < WN; j++) {
+                if (p.bias) {
+                    const double bz0 = p.bias[nw + j * 8 + 2 * t4], bz1 = p.bias[nw + j * 8 + 2 * t4 + 1];
+#pragma unroll
+                    for (int i = 0; i < WM; i++)
+                        *reinterpret_cast<double2*>(crow + (size_t)i * 8 * p.ldc + j * 8) =
+                            make_double2(fma(p.alpha, acc[i][j][0], bz0), fma(p.alpha, acc[i][j][1], bz1));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < WM; i++)
+                        *reinterpret_cast<double2*>(crow + (size_t)i * 8 * p.ldc + j * 8) =
+                            make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < WM; i++) {
             const int m = m0 + wm * WM * 8 + i * 8 + g;
@@ -256,13 +276,15 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < WN; j++) {
                 const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
                 if (n >= p.N) continue;
-                double v0 = p.alpha * acc[i][j][0];
-                double v1 = p.alpha * acc[i][j][1];
                 double* cp = p.C + (size_t)m * p.ldc + n;
                 const bool two = (n + 1 < p.N);
-                if (p.bias) {
-                    v0 += p.bias[n];
-                    if (two) v1 += p.bias[n + 1];
+                double v0, v1;
+                if (p.bias) {  // the same fused form as the interior-tile path above: one result whatever the tile
+                    v0 = fma(p.alpha, acc[i][j][0], p.bias[n]);
+                    v1 = two ? fma(p.alpha, acc[i][j][1], p.bias[n + 1]) : 0.0;
+                } else {
+                    v0 = p.alpha * acc[i][j][0];
+                    v1 = p.alpha * acc[i][j][1];
                 }
                 if (vec_ok && two) {
                     if (p.beta != 0.0) {
