@@ -82,6 +82,11 @@ struct TileK {
     int n0, kbeg1, kend1, kbeg2, nc1, nchunks;
 };
 
+// MODE >= 0: compile-time mode; MODE < 0: the mode comes from the parameters at run time
+template <int MODE>
+__device__ __forceinline__ int mode_of(const TmaGemmParams& p) { return MODE < 0 ? p.mode : MODE; }
+
+template <int MODE>
 __device__ __forceinline__ TileK make_tile(const TmaGemmParams& p, int tn)
 {
     TileK t;
@@ -89,11 +94,11 @@ __device__ __forceinline__ TileK make_tile(const TmaGemmParams& p, int tn)
     t.kbeg1 = 0;
     t.kend1 = p.K;
     t.kbeg2 = p.K;
-    if (p.mode == HTNK_GEMM_B_LOWER) {
+    if (mode_of<MODE>(p) == HTNK_GEMM_B_LOWER) {
         int n1 = min(p.N, t.n0 + BN);
         t.kend1 = min(n1, p.ktri);
         t.kbeg2 = min(p.kext0, p.K);
-    } else if (p.mode == HTNK_GEMM_B_UPPER) {
+    } else if (mode_of<MODE>(p) == HTNK_GEMM_B_UPPER) {
         t.kbeg1 = min((t.n0 / BK) * BK, p.K);  // B[n][k] == 0 for k < n: skip the chunks left of the tile
     }
     t.nc1 = (t.kend1 - t.kbeg1 + BK - 1) / BK;
@@ -111,7 +116,7 @@ __device__ __forceinline__ void tile_chunk(const TmaGemmParams& p, const TileK& 
 // 128-row slab: every CTA then runs the same number of K chunks (the longest and the shortest loop together,
 // as in causal-attention schedulers), and the TMA ring keeps streaming across the tile boundary, so the
 // second tile's first chunks are already in flight while the first tile's epilogue is being written.
-template <int WM, int MINB>
+template <int WM, int MINB, int MODE>
 __global__ void __launch_bounds__(NT, MINB)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TmaGemmParams p)
@@ -132,19 +137,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int ntl = 1;
     TileK T[2];
     int m0;
-    if (p.paired) {
+    if (mode_of<MODE>(p) == HTNK_GEMM_B_LOWER && p.paired) {
         const int npairs = (p.tiles_n + 1) >> 1;
         const int q = bid % npairs;
         m0 = (bid / npairs) * BM;
-        T[0] = make_tile(p, p.tiles_n - 1 - q);
-        T[1] = make_tile(p, q);
+        T[0] = make_tile<MODE>(p, p.tiles_n - 1 - q);
+        T[1] = make_tile<MODE>(p, q);
         ntl = (p.tiles_n - 1 - q != q) ? 2 : 1;
     } else {
         const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
         m0 = (bid / p.tiles_n) * BM;
-        T[0] = make_tile(p, tn);
+        T[0] = make_tile<MODE>(p, tn);
         T[1] = T[0];
-        if (p.mode == HTNK_GEMM_C_LOWER && m0 + BM - 1 < T[0].n0) return;
+        if (mode_of<MODE>(p) == HTNK_GEMM_C_LOWER && m0 + BM - 1 < T[0].n0) return;
     }
     const int total_chunks = T[0].nchunks + (ntl == 2 ? T[1].nchunks : 0);
 
@@ -203,7 +208,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tile_chunk(p, tk, c, k0, kend);
             const unsigned char* a_s = sA + st * A_BYTES + a_off;
             const unsigned char* b_s = sB + st * B_BYTES + b_off;
-            const bool diag = (p.mode == HTNK_GEMM_B_LOWER) && (c < tk.nc1) && (k0 + BK > nw);
+            const bool diag = (mode_of<MODE>(p) == HTNK_GEMM_B_LOWER) && (c < tk.nc1) && (k0 + BK > nw);
             if (!diag && jhi == WN && kend - k0 >= BK) {
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
@@ -379,7 +384,14 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     const unsigned grid = p.paired ? (unsigned)p.tiles_m * (unsigned)((p.tiles_n + 1) / 2)
                                    : (unsigned)p.tiles_m * (unsigned)p.tiles_n;
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
-    auto kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4> : gemm_tma_kernel<8, 3>;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TmaGemmParams) = nullptr;
+    switch (mode) {  // the mode is a template parameter: each instance carries only its own tile logic
+        // (the triangular mode keeps the run-time form: ptxas spills more in its specialised instance - measured slower)
+        case HTNK_GEMM_B_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, -1> : gemm_tma_kernel<8, 3, -1>; break;
+        case HTNK_GEMM_C_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_C_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_C_LOWER>; break;
+        case HTNK_GEMM_B_UPPER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_UPPER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_UPPER>; break;
+        default: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_FULL> : gemm_tma_kernel<8, 3, HTNK_GEMM_FULL>; break;
+    }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
     kern<<<grid, NT, smem, st>>>(tmA, tmB, p);
