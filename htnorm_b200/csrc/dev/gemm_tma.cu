@@ -134,24 +134,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const int bid = blockIdx.x;
-    int ntl = 1;
-    TileK T[2];
-    int m0;
+    // the CTA's tiles as two tile indices and one chunk count: the descriptors are recomputed where they are needed
+    // (a dozen integer instructions) instead of being carried in registers next to the 128 accumulators
+    int ntl = 1, tn0, tn1, m0;
     if (mode_of<MODE>(p) == HTNK_GEMM_B_LOWER && p.paired) {
         const int npairs = (p.tiles_n + 1) >> 1;
         const int q = bid % npairs;
         m0 = (bid / npairs) * BM;
-        T[0] = make_tile<MODE>(p, p.tiles_n - 1 - q);
-        T[1] = make_tile<MODE>(p, q);
-        ntl = (p.tiles_n - 1 - q != q) ? 2 : 1;
+        tn0 = p.tiles_n - 1 - q;
+        tn1 = q;
+        ntl = (tn0 != tn1) ? 2 : 1;
     } else {
-        const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
+        tn0 = tn1 = p.tiles_n - 1 - (bid % p.tiles_n);
         m0 = (bid / p.tiles_n) * BM;
-        T[0] = make_tile<MODE>(p, tn);
-        T[1] = T[0];
-        if (mode_of<MODE>(p) == HTNK_GEMM_C_LOWER && m0 + BM - 1 < T[0].n0) return;
+        if (mode_of<MODE>(p) == HTNK_GEMM_C_LOWER && m0 + BM - 1 < tn0 * BN) return;
     }
-    const int total_chunks = T[0].nchunks + (ntl == 2 ? T[1].nchunks : 0);
+    const int nch0 = make_tile<MODE>(p, tn0).nchunks;
+    const int total_chunks = nch0 + (ntl == 2 ? make_tile<MODE>(p, tn1).nchunks : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -168,12 +167,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (cg >= total_chunks) return;
         const int s = cg % STAGES, round = cg / STAGES;
         if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-        const int t = cg < T[0].nchunks ? 0 : 1;
+        const bool first = cg < nch0;
+        const TileK tt = make_tile<MODE>(p, first ? tn0 : tn1);
         int k0, kend;
-        tile_chunk(p, T[t], t ? cg - T[0].nchunks : cg, k0, kend);
+        tile_chunk(p, tt, first ? cg : cg - nch0, k0, kend);
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
         tma_load_2d(sA + s * A_BYTES, &tmA, k0, m0, &full[s]);
-        tma_load_2d(sB + s * B_BYTES, &tmB, k0, T[t].n0, &full[s]);
+        tma_load_2d(sB + s * B_BYTES, &tmB, k0, tt.n0, &full[s]);
     };
     if (tid == 0) {
         for (int c = 0; c < AHEAD; c++) issue(c);
@@ -190,7 +190,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     int cg = 0;
     for (int tl = 0; tl < ntl; tl++) {
-        const TileK tk = T[tl];
+        const TileK tk = make_tile<MODE>(p, tl == 0 ? tn0 : tn1);
         const int n0 = tk.n0;
         const int nw = n0 + wn * WN * 8;
         const int jhi = min(WN, (p.N - nw + 7) >> 3);
