@@ -386,8 +386,7 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
     void (*kern)(const CUtensorMap, const CUtensorMap, const TmaGemmParams) = nullptr;
     switch (mode) {  // the mode is a template parameter: each instance carries only its own tile logic
-        // (the triangular mode keeps the run-time form: ptxas spills more in its specialised instance - measured slower)
-        case HTNK_GEMM_B_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, -1> : gemm_tma_kernel<8, 3, -1>; break;
+        case HTNK_GEMM_B_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_LOWER>; break;
         case HTNK_GEMM_C_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_C_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_C_LOWER>; break;
         case HTNK_GEMM_B_UPPER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_UPPER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_UPPER>; break;
         default: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_FULL> : gemm_tma_kernel<8, 3, HTNK_GEMM_FULL>; break;
