@@ -220,14 +220,59 @@ done:
 /* Explicit inverse of the factor, so that solves with MANY right-hand-side rows become one triangular DMMA
  * GEMM each (full-width grids) instead of n/128 dependent panel steps: linv = L^-1 (lower) by the blocked
  * solve X L = I, linvt = its transpose. */
+/* inv(L[lo:hi, lo:hi]) into linv (and its transpose into linvt), by halving:
+ *   L = [L11 0; L21 L22]  ->  L^-1 = [L11^-1 0; -L22^-1 L21 L11^-1, L22^-1]
+ * The leaves are the 128 x 128 diagonal-block inverses of trtri_batched; every inner node is two large GEMMs
+ * (instead of a 16-step column sweep whose GEMMs have 64 CTAs each): n = 2000: 1.5 -> 0.5 ms. */
+static int inverse_rec(htn_ctx_t* ctx, htn_factor_t* fa, int lo, int hi, double* tt, size_t ldt)
+{
+    int rc = 0;
+    const size_t ld = fa->ld;
+    const int n = hi - lo;
+    if (n <= HTN_NB) {
+        const int jb = lo / HTN_NB;
+        HTN_TRY(htnk_copy2d(ctx->stream, fa->dinv + (size_t)jb * HTN_NB * HTN_NB, HTN_NB, n, n,
+                            fa->linv + (size_t)lo * ld + lo, ld, NULL));
+        HTN_TRY(htnk_copy2d(ctx->stream, fa->dinvt + (size_t)jb * HTN_NB * HTN_NB, HTN_NB, n, n,
+                            fa->linvt + (size_t)lo * ld + lo, ld, NULL));
+        return 0;
+    }
+    const int mid = lo + (int)htn_round_up((size_t)(n / 2), HTN_NB);
+    HTN_TRY(inverse_rec(ctx, fa, lo, mid, tt, ldt));
+    HTN_TRY(inverse_rec(ctx, fa, mid, hi, tt, ldt));
+    {
+        const int M = hi - mid, N = mid - lo;
+        double* x21 = fa->linv + (size_t)mid * ld + lo;
+        /* T^T (N x M) = inv(L11)^T * L21^T */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, N, M, N, 1.0, fa->linvt + (size_t)lo * ld + lo, ld,
+                             fa->f + (size_t)mid * ld + lo, ld, 0.0, tt, ldt, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        /* X21 (M x N) = -inv(L22) * T */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, M, N, M, -1.0, fa->linv + (size_t)mid * ld + mid, ld, tt, ldt, 0.0, x21, ld,
+                             NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        HTN_TRY(htnk_transpose(ctx->stream, x21, ld, M, N, fa->linvt + (size_t)lo * ld + mid, ld));
+    }
+done:
+    return rc;
+}
+
 int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa)
 {
     int rc = 0;
     const size_t bytes = (size_t)fa->n * fa->ld * sizeof(double);
+    double* tt = NULL;
     if (!fa->linv) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linv, bytes));
     if (!fa->linvt) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linvt, bytes));
     HTN_CUDA(cudaMemsetAsync(fa->linv, 0, bytes, ctx->stream));
     HTN_CUDA(cudaMemsetAsync(fa->linvt, 0, bytes, ctx->stream));
+    if (fa->dinv && fa->dinvt) {
+        const size_t half = htn_round_up((size_t)(fa->n / 2), HTN_NB) + HTN_NB;
+        const size_t ldt = htn_round_up(half, 16);
+        HTN_TRY(htn_dalloc(ctx, (void**)&tt, half * ldt * sizeof(double)));
+        rc = inverse_rec(ctx, fa, 0, fa->n, tt, ldt);
+        htn_dfree(ctx, tt);
+        return rc;
+    }
+    /* no block inverses at hand: column sweep on the identity */
     HTN_TRY(htnk_diag_set(ctx->stream, fa->linv, fa->ld, fa->n, NULL, 1.0));
     HTN_TRY(htn_trsm_right_l(ctx, fa, fa->linv, fa->ld, fa->n));
     HTN_TRY(htnk_transpose(ctx->stream, fa->linv, fa->ld, fa->n, fa->n, fa->linvt, fa->ld));
