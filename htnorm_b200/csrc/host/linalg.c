@@ -241,15 +241,19 @@ static int inverse_rec(htn_ctx_t* ctx, htn_factor_t* fa, int lo, int hi, double*
     HTN_TRY(inverse_rec(ctx, fa, lo, mid, tt, ldt));
     HTN_TRY(inverse_rec(ctx, fa, mid, hi, tt, ldt));
     {
+        /* both products have a triangular operand, placed where the GEMM can skip its zero blocks (the B side) */
         const int M = hi - mid, N = mid - lo;
-        double* x21 = fa->linv + (size_t)mid * ld + lo;
-        /* T^T (N x M) = inv(L11)^T * L21^T */
-        HTN_TRY(htnk_gemm_tn(ctx->stream, N, M, N, 1.0, fa->linvt + (size_t)lo * ld + lo, ld,
-                             fa->f + (size_t)mid * ld + lo, ld, 0.0, tt, ldt, NULL, HTNK_GEMM_FULL, 0, 0, 0));
-        /* X21 (M x N) = -inv(L22) * T */
-        HTN_TRY(htnk_gemm_tn(ctx->stream, M, N, M, -1.0, fa->linv + (size_t)mid * ld + mid, ld, tt, ldt, 0.0, x21, ld,
-                             NULL, HTNK_GEMM_FULL, 0, 0, 0));
-        HTN_TRY(htnk_transpose(ctx->stream, x21, ld, M, N, fa->linvt + (size_t)lo * ld + mid, ld));
+        double* t = tt;                      /* T   (M x N) */
+        double* ttr = tt + (size_t)ldt * ldt; /* T^T (N x M) */
+        /* T = L21 * inv(L11):  B[n][k] = inv(L11)[k][n] = linvt11[n][k], zero for k < n */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, M, N, N, 1.0, fa->f + (size_t)mid * ld + lo, ld,
+                             fa->linvt + (size_t)lo * ld + lo, ld, 0.0, t, ldt, NULL, HTNK_GEMM_B_UPPER, 0, 0, 0));
+        HTN_TRY(htnk_transpose(ctx->stream, t, ldt, M, N, ttr, ldt));
+        /* X21^T (N x M) = -T^T * inv(L22)^T:  B[m][k] = inv(L22)[m][k], zero for k > m; straight into linvt */
+        double* x21t = fa->linvt + (size_t)lo * ld + mid;
+        HTN_TRY(htnk_gemm_tn(ctx->stream, N, M, M, -1.0, ttr, ldt, fa->linv + (size_t)mid * ld + mid, ld, 0.0, x21t, ld,
+                             NULL, HTNK_GEMM_B_LOWER, M, M, 0));
+        HTN_TRY(htnk_transpose(ctx->stream, x21t, ld, N, M, fa->linv + (size_t)mid * ld + lo, ld));
     }
 done:
     return rc;
@@ -267,7 +271,7 @@ int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa)
     if (fa->dinv && fa->dinvt) {
         const size_t half = htn_round_up((size_t)(fa->n / 2), HTN_NB) + HTN_NB;
         const size_t ldt = htn_round_up(half, 16);
-        HTN_TRY(htn_dalloc(ctx, (void**)&tt, half * ldt * sizeof(double)));
+        HTN_TRY(htn_dalloc(ctx, (void**)&tt, 2 * ldt * ldt * sizeof(double))); /* T and T^T */
         rc = inverse_rec(ctx, fa, 0, fa->n, tt, ldt);
         htn_dfree(ctx, tt);
         return rc;
