@@ -132,16 +132,39 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_TRY(htn_dalloc(ctx, (void**)&Z[0], chunk * ldz * 8));
     if (nchunks > 1) HTN_TRY(htn_dalloc(ctx, (void**)&Z[1], chunk * ldz * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&D, chunk * k2p * 8));
-    HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    HTN_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
-    if (sink) HTN_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_sym, cudaEventDisableTiming));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_sbranch, cudaEventDisableTiming));
-    if (sink) HTN_CUDA(cudaEventCreateWithFlags(&ev_sub, cudaEventDisableTiming));
-    for (int e = 0; e < 2; e++) {
-        HTN_CUDA(cudaEventCreateWithFlags(&ev_rng[e], cudaEventDisableTiming));
-        HTN_CUDA(cudaEventCreateWithFlags(&ev_gemm[e], cudaEventDisableTiming));
+    {
+        /* the side streams and events are created once per host thread and device, and kept: creating and destroying
+         * three streams and eight events costs more host time than a small batch takes on the GPU */
+        static _Thread_local struct {
+            int device;
+            cudaStream_t side, side2, copy;
+            cudaEvent_t ev[8];
+        } sy = {-1, NULL, NULL, NULL, {NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL}};
+        if (sy.device != ctx->device) {
+            if (sy.device >= 0) { /* another device was current before: let go of its objects */
+                for (int e = 0; e < 8; e++) cudaEventDestroy(sy.ev[e]);
+                cudaStreamDestroy(sy.side);
+                cudaStreamDestroy(sy.side2);
+                cudaStreamDestroy(sy.copy);
+                sy.device = -1;
+            }
+            HTN_CUDA(cudaStreamCreateWithFlags(&sy.side, cudaStreamNonBlocking));
+            HTN_CUDA(cudaStreamCreateWithFlags(&sy.side2, cudaStreamNonBlocking));
+            HTN_CUDA(cudaStreamCreateWithFlags(&sy.copy, cudaStreamNonBlocking));
+            for (int e = 0; e < 8; e++) HTN_CUDA(cudaEventCreateWithFlags(&sy.ev[e], cudaEventDisableTiming));
+            sy.device = ctx->device;
+        }
+        side = sy.side;
+        side2 = sy.side2;
+        if (sink) copy_st = sy.copy;
+        ev_fork = sy.ev[0];
+        ev_sym = sy.ev[1];
+        ev_sbranch = sy.ev[2];
+        ev_sub = sy.ev[3];
+        ev_rng[0] = sy.ev[4];
+        ev_rng[1] = sy.ev[5];
+        ev_gemm[0] = sy.ev[6];
+        ev_gemm[1] = sy.ev[7];
     }
     htn_prof_mark(ctx, 0);
     HTN_CUDA(cudaEventRecord(ev_fork, st));
@@ -285,17 +308,7 @@ done:
     if (ev_sbranch) { /* the branch may still be running if we bailed out early */
         cudaStreamWaitEvent(st, ev_sbranch, 0);
     }
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_sym) cudaEventDestroy(ev_sym);
-    if (ev_sbranch) cudaEventDestroy(ev_sbranch);
-    if (ev_sub) cudaEventDestroy(ev_sub);
-    if (side2) cudaStreamDestroy(side2);
-    if (copy_st) cudaStreamDestroy(copy_st);
-    for (int e = 0; e < 2; e++) {
-        if (ev_rng[e]) cudaEventDestroy(ev_rng[e]);
-        if (ev_gemm[e]) cudaEventDestroy(ev_gemm[e]);
-    }
-    if (side) cudaStreamDestroy(side); /* asynchronous: resources are released once its work has drained */
+    /* (streams and events belong to the per-thread cache) */
     htn_dfree(ctx, c0);
     htn_dfree(ctx, Sm);
     htn_dfree(ctx, WT);
