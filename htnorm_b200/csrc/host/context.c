@@ -68,7 +68,16 @@ int htn_ctx_begin(htn_ctx_t* ctx, int device, void* stream, int host_mode)
         pool_configured[ctx->device] = 1;
     }
     if (host_mode) {
-        HTN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        /* the library's own stream for host-memory calls: one per host thread and device, created once and kept
+         * (the call still synchronises on it before returning) */
+        static _Thread_local struct { int device; cudaStream_t stream; } own = {-1, NULL};
+        if (own.device != ctx->device) {
+            if (own.device >= 0) cudaStreamDestroy(own.stream);
+            own.device = -1;
+            HTN_CUDA(cudaStreamCreateWithFlags(&own.stream, cudaStreamNonBlocking));
+            own.device = ctx->device;
+        }
+        ctx->stream = own.stream;
         ctx->own_stream = 1;
     } else {
         ctx->stream = (cudaStream_t)stream;
@@ -87,7 +96,6 @@ int htn_ctx_end(htn_ctx_t* ctx, int sync)
             rc = HTN_E_CUDA;
         }
     }
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->device != ctx->prev_device) cudaSetDevice(ctx->prev_device);
     return rc;
 }
