@@ -21,3 +21,13 @@ for B in (128, 2048, 65536):
         for i in range(7):
             t0 = time.perf_counter(); f(2 + i); ts.append(time.perf_counter() - t0)
         print(f"B={B:6d} {name:12s}: best {min(ts)*1e3:.3f} ms  median {sorted(ts)[3]*1e3:.3f} ms", flush=True)
+
+# single-sample API (reference-compatible entry point, generator advanced on the GPU and written back)
+gen = h.HTNGenerator(7)
+out1 = np.empty(K)
+def one(i): gen.hyperplane_truncated_mvnorm(mean, cov, g, r, out=out1)
+one(0); one(1)
+ts = []
+for i in range(9):
+    t0 = time.perf_counter(); one(i); ts.append(time.perf_counter() - t0)
+print(f"single-sample htn_hyperplane_truncated_mvn, k={K} (pageable numpy inputs): best {min(ts)*1e3:.3f} ms  median {sorted(ts)[4]*1e3:.3f} ms", flush=True)
