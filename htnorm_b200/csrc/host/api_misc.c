@@ -10,6 +10,7 @@ static int streams_setup(htn_ctx_t* ctx, const htn_batch_t* b, htnk_streams_t* s
     sv->gen = (int)b->gen;
     sv->seed0 = b->seed0;
     sv->states = NULL;
+    sv->zpre = NULL;
     sv->seeds = b->seeds;
     if (b->seeds && b->mem == HTN_MEM_HOST) {
         HTN_TRY(htn_dalloc(ctx, d_seeds, b->nsamples * 8));
@@ -28,7 +29,7 @@ int htn_rng_raw_fill(const htn_batch_t* b, size_t nwords, uint64_t* out)
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, b->mem == HTN_MEM_HOST);
     if (rc) return rc;
     void *d_seeds = NULL, *d_out = NULL;
-    htnk_streams_t sv;
+    htnk_streams_t sv = {0};
     const size_t total = b->nsamples * nwords;
     if (total == 0) goto done;
     HTN_TRY(streams_setup(&ctx, b, &sv, &d_seeds));
@@ -57,7 +58,7 @@ int htn_std_normal_fill(const htn_batch_t* b, size_t n, double* out, uint32_t* n
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, b->mem == HTN_MEM_HOST);
     if (rc) return rc;
     void *d_seeds = NULL, *d_out = NULL, *d_nd = NULL;
-    htnk_streams_t sv;
+    htnk_streams_t sv = {0};
     const size_t total = b->nsamples * n;
     if (total == 0) goto done;
     HTN_TRY(streams_setup(&ctx, b, &sv, &d_seeds));

@@ -19,6 +19,11 @@ typedef struct {
     int prev_device;
     cudaStream_t stream;
     int own_stream;
+    /* per-call options of the hyperplane path, set by the entry points (zero = defaults) */
+    double* host_sink;    /* host-memory batch: caller's output array; finished sub-chunks are copied there directly */
+    int host_sink_used;   /* out: the sink received the samples */
+    int* async_info_out;  /* device-memory batch: per-sample info array filled on the device, no host synchronisation */
+    int cov_failed;       /* out: chol(cov) failed, nothing was drawn */
 } htn_ctx_t;
 
 void htn_set_error(const char* fmt, ...);
@@ -109,7 +114,6 @@ void htn_foreign_draw(rng_t* rng, size_t n, double* z);
 int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int independent, unsigned flags,
                   size_t k2, size_t k, const double* mean, const double* cov, const double* g,
                   const double* r, int diag, double* out, int* d_info_out, int* first_info);
-int htn_ht_last_cov_failed(void);
 int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info);
 int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, size_t n, size_t p,
                   const double* mean, const double* a, const double* phi, const double* omega,

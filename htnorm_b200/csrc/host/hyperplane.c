@@ -22,20 +22,14 @@
 #define SMALL_K2_MAX 16
 #define ALPHA_K2_MAX 16
 
-/* set by the shared dense path when the covariance factorisation failed (no draw was made) */
-static _Thread_local int g_cov_failed = 0;
-int htn_ht_last_cov_failed(void) { return g_cov_failed; }
-
-/* Host-memory batches: the wrapper points this at the caller's output array; the shared dense path then
- * draws in chunks and copies each finished chunk device -> host on its own stream WHILE the next chunk is in
- * the sampling GEMM (the PCIe copy of the samples is the longest leg of a host-to-host call). */
-/* Device-memory batches run fully asynchronously: the LAPACK codes stay on the device, the sampling GEMM is
- * guarded by them, and the per-sample info array is filled by a kernel.  Host-memory callers (which must
- * leave `out` untouched on failure and return the code) set this and get the synchronous behaviour. */
-static _Thread_local int g_need_codes = 1;
-static _Thread_local int* g_async_info_out = NULL;
-static _Thread_local double* g_host_sink = NULL;
-static _Thread_local int g_host_sink_used = 0;
+/* Per-call options live in the context (htn_internal.h):
+ *   host_sink      - host-memory batches: the wrapper points it at the caller's output array; the shared dense path
+ *                    then copies each finished sub-chunk device -> host on its own stream WHILE the next one is in
+ *                    the sampling GEMM (the PCIe copy of the samples is the longest leg of a host-to-host call);
+ *   async_info_out - device-memory batches run fully asynchronously: the LAPACK codes stay on the device, the
+ *                    sampling GEMM is guarded by them, and this per-sample info array is filled by a kernel.
+ *                    Host-memory callers (which must leave `out` untouched on failure and return the code) leave it
+ *                    NULL and get the synchronous behaviour. */
 #define SINK_CHUNK 32768 /* upper bound on the rows of a host-sink chunk */
 
 static void streams_view(const htn_streams_t* s, size_t offset, htnk_streams_t* v)
@@ -115,7 +109,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     size_t chunk = nsamples;
     const size_t budget = (size_t)3 << 30; /* bytes of Z~ per chunk (two chunks are in flight) */
     if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
-    double* const sink = g_host_sink;
+    double* const sink = ctx->host_sink;
     cudaStream_t copy_st = NULL;
     /* Host-memory callers: the normals of a whole Z~ chunk are still drawn in ONE launch (every stream in parallel,
      * beside the factorisation), but the coefficient pass, the sampling GEMM and the device->host copy then go
@@ -226,14 +220,14 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     }
 
     int h_info[2] = {0, 0};
-    const int async = !g_need_codes && k2 <= ALPHA_K2_MAX && g_async_info_out != NULL;
+    const int async = k2 <= ALPHA_K2_MAX && ctx->async_info_out != NULL;
     if (!async) {
         HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
         HTN_CUDA(cudaStreamSynchronize(st));
     }
     if (h_info[0]) { /* cov not positive definite: no draw, out untouched (src/htnorm_distributions.c:78) */
         *first_info = h_info[0];
-        g_cov_failed = 1;
+        ctx->cov_failed = 1;
         goto done;
     }
     *first_info = h_info[1]; /* G cov G^T not PD: the unprojected y is returned (src/htnorm.c:169-177) */
@@ -294,9 +288,9 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     }
     if (sink) {
         HTN_CUDA(cudaStreamSynchronize(copy_st));
-        g_host_sink_used = 1;
+        ctx->host_sink_used = 1;
     }
-    if (async) HTN_TRY(htnk_fill_info(st, g_async_info_out, nsamples, d_info));
+    if (async) HTN_TRY(htnk_fill_info(st, ctx->async_info_out, nsamples, d_info));
 done:
     /* never free a buffer the side stream may still be writing */
     if (rng_pending >= 0 && ev_rng[rng_pending]) cudaStreamWaitEvent(st, ev_rng[rng_pending], 0);
@@ -396,7 +390,7 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
 {
     int rc = 0;
     *first_info = 0;
-    g_cov_failed = 0;
+    ctx->cov_failed = 0;
     if (nsamples == 0) return 0;
     if (k == 0 || k2 == 0 || !mean || !cov || !g || !r || !out || k > 0x7fffffffu / 2 || k2 > k ||
         nsamples > 0x7fffffffu) {
@@ -448,7 +442,7 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
         rc = ht_shared_diag(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
     else
         rc = ht_shared_dense(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, first_info);
-    if (!rc && d_info_out && !(g_async_info_out && !diag)) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
+    if (!rc && d_info_out && !(ctx->async_info_out && !diag)) rc = htnk_fill_i32(ctx->stream, d_info_out, nsamples, *first_info);
 done:
     return rc;
 }
@@ -504,12 +498,9 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL, NULL};
     if (b->mem == HTN_MEM_DEVICE) {
         /* asynchronous: nothing in this branch waits for the device (shared dense inputs, k2 <= 16, info given) */
-        g_need_codes = 0;
-        g_async_info_out = (!b->independent && !conf->diag && k2 <= ALPHA_K2_MAX) ? info : NULL;
+        ctx.async_info_out = (!b->independent && !conf->diag && k2 <= ALPHA_K2_MAX) ? info : NULL;
         rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
                            conf->diag, out, info, &first);
-        g_need_codes = 1;
-        g_async_info_out = NULL;
         int rc2 = htn_ctx_end(&ctx, 0);
         return rc ? rc : rc2;
     }
@@ -534,11 +525,11 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     HTN_CUDA(cudaMemsetAsync(d_info, 0, B * sizeof(int), ctx.stream));
     if (b->independent) /* a problem whose cov is not PD leaves its row of `out` as the caller had it */
         HTN_CUDA(cudaMemcpyAsync(d_out, out, B * k * 8, cudaMemcpyHostToDevice, ctx.stream));
-    g_host_sink = (!b->independent && !conf->diag) ? out : NULL;
-    g_host_sink_used = 0;
+    ctx.host_sink = (!b->independent && !conf->diag) ? out : NULL;
+    ctx.host_sink_used = 0;
     rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
                        d_info, &first);
-    g_host_sink = NULL;
+    ctx.host_sink = NULL;
     if (rc) goto done;
     {
         int* h_info = info ? info : malloc(B * sizeof(int));
@@ -550,7 +541,7 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
         if (!info) free(h_info);
     }
     /* shared inputs with cov not PD: nothing was drawn, `out` stays untouched (reference behaviour) */
-    if (!g_host_sink_used && !(first > 0 && !b->independent && !conf->diag && htn_ht_last_cov_failed()))
+    if (!ctx.host_sink_used && !(first > 0 && !b->independent && !conf->diag && ctx.cov_failed))
         HTN_CUDA(cudaMemcpyAsync(out, d_out, B * k * 8, cudaMemcpyDeviceToHost, ctx.stream));
 done:
     htn_dfree(&ctx, d_info);
