@@ -341,18 +341,19 @@ typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+encode_fn_t lookup_encode()
+{
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<encode_fn_t>(ptr);
+    return nullptr;
+}
+
 encode_fn_t get_encode()
 {
-    static encode_fn_t fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<encode_fn_t>(ptr);
-    }
+    static const encode_fn_t fn = lookup_encode();  // initialised once, thread-safe (C++11)
     return fn;
 }
 
