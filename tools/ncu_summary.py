@@ -1,9 +1,10 @@
 """Print the metrics that matter from an .ncu-rep (raw page) + top stall instructions (source page)."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 18
+which = int(sys.argv[3]) if len(sys.argv) > 3 else -1  # launch (row of the raw page) to summarise; source page = whole report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[-1]
+hdr, vals = rows[0], (rows[2:] if len(rows) > 2 else rows[1:])[which]
 keys = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__registers_per_thread",
         "launch__occupancy_limit", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct",
         "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -17,7 +18,8 @@ for h, v in zip(hdr, vals):
         print(f"{h} = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
+if topn <= 0 or not data: sys.exit(0)
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 tot = sum(int(r[isamp] or 0) for r in data)
 print(f"--- source: {len(data)} SASS instructions, {tot} samples; top {topn} by samples")
