@@ -267,6 +267,50 @@ def main():
     # parity spot check inside the bench: constraint residual of the last batch (sum-to-zero)
     resid = float((out @ d_in[2].T - d_in[3]).abs().max().item())
 
+    # ---- timed (N > 1 only): the same steps followed by the one collective of the path, an NCCL all-gather of the
+    # output shards.  Shards are double-buffered, so the gather of step i runs beside step i + 1. ----
+    gathered = None
+    if world > 1:
+        outs = [out, torch.empty_like(out)]
+        full = torch.empty((world * B, K), dtype=torch.float64, device=dev)
+        works = [None, None]
+
+        def step_gather(i):
+            o = outs[i & 1]
+            if works[i & 1] is not None:
+                works[i & 1].wait()          # this shard buffer has left for the peers
+            h.hyperplane_truncated_mvnorm_batch(B, *d_in, gen="pcg64", seed0=seed0 + i * B * world, out=o, info=info)
+            works[i & 1] = dist.all_gather_into_tensor(full.view(-1), o.view(-1), async_op=True)
+
+        def drain():
+            for w in works:
+                if w is not None:
+                    w.wait()
+        for i in range(2):
+            step_gather(i)
+        drain()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            step_gather(2 + i)
+        drain()
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        last = outs[(2 + args.steps - 1) & 1]
+        ok = bool(torch.equal(full[rank * B:(rank + 1) * B], last))
+        okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gathered = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": "samples/s",
+                    "ms_per_step": float(t.item()) / args.steps, "bytes_per_rank_per_step": 8 * B * K,
+                    "collective": "ncclAllGather of the output shards over NVLink, overlapped with the next step "
+                                  "(double-buffered shards); every rank ends with all %d samples" % (B * world),
+                    "own_shard_intact": bool(okt.item())}
+        del full, outs
+        out = last
+
     # ---- timed: end to end through the C ABI with HOST buffers (pinned), copies inside ----
     h_in = [torch.from_numpy(x).pin_memory() for x in (mean, cov, g, r)]
     h_out = torch.empty((B, K), dtype=torch.float64).pin_memory()
@@ -323,6 +367,8 @@ def main():
                         "d2h_bytes_per_step": d2h, "steps": e2e_steps},
                 "gpu_launches": launches, "roofline": roof, "clocks": clk,
                 "max_abs_constraint_residual": resid}
+        if gathered is not None:
+            line["gathered"] = gathered
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
