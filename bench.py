@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the figure that includes the NCCL all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -270,7 +271,7 @@ def main():
     # ---- timed (N > 1 only): the same steps followed by the one collective of the path, an NCCL all-gather of the
     # output shards.  Shards are double-buffered, so the gather of step i runs beside step i + 1. ----
     gathered = None
-    if world > 1:
+    if world > 1 and not args.no_gather:
         outs = [out, torch.empty_like(out)]
         full = torch.empty((world * B, K), dtype=torch.float64, device=dev)
         works = [None, None]

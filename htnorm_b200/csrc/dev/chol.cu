@@ -236,21 +236,21 @@ potf2_kernel(double* __restrict__ a, size_t ld, int nb, int col0, double* __rest
             const int r = idx >> 6, c = 2 * (idx & 63);
             if (c > r) *reinterpret_cast<double2*>(a + (size_t)r * ld + c) = make_double2(0.0, 0.0);
         }
-        asm volatile("cp.async.wait_group 0;\n" ::);
     } else {
         load_block<NTP>(S, a, ld, nb, tid, true);
     }
+    // set-up that does not depend on the block runs while the LDGSTS of the fast path are still in flight
     for (int idx = tid; idx < NB * LDP; idx += NTP) P[idx] = 0.0;
     for (int idx = tid; idx < 8 * 12; idx += NTP) Tsm[idx] = 0.0;
     const int npanels = (nb + 7) >> 3;
     if (tid < npanels) {
-        int first = 0;
-        for (int t = 0; t < tid; t++) first += npanels - t;
+        const int first = tid * npanels - tid * (tid - 1) / 2;  // tiles of the columns before this one
         colstart[tid] = first;
         if (tid == npanels - 1) colstart[npanels] = first + 1;
         for (int tr = tid; tr < npanels; tr++) tiles[first + tr - tid] = make_short2((short)(8 * tr), (short)(8 * tid));
     }
     if (tid == 0) s_fail = 0;
+    if (fastio) asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
 
     auto factor_block = [&](int bb) {  // warp 0 only
