@@ -370,6 +370,37 @@ extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, in
     return status();
 }
 
+namespace {
+// every 128 x 128 diagonal-block inverse (and its transpose), stored block after block, goes to its place on the diagonal
+// of the two n x n inverse-factor matrices: one launch for all the leaves of the recursive inversion
+__global__ void scatter_diag_blocks_kernel(const double* __restrict__ dinv, const double* __restrict__ dinvt, int nb, int n,
+                                           double* __restrict__ linv, double* __restrict__ linvt, size_t ld)
+{
+    const int jb = blockIdx.y;
+    const int rows = min(nb, n - jb * nb);
+    const double* s0 = dinv + (size_t)jb * nb * nb;
+    const double* s1 = dinvt + (size_t)jb * nb * nb;
+    double* d0 = linv + ((size_t)jb * nb) * ld + (size_t)jb * nb;
+    double* d1 = linvt + ((size_t)jb * nb) * ld + (size_t)jb * nb;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows * nb; idx += gridDim.x * blockDim.x) {
+        const int r = idx / nb, c = idx - r * nb;
+        if (c < rows) {
+            d0[(size_t)r * ld + c] = s0[(size_t)r * nb + c];
+            d1[(size_t)r * ld + c] = s1[(size_t)r * nb + c];
+        }
+    }
+}
+}  // namespace
+
+extern "C" int htnk_scatter_diag_blocks(cudaStream_t st, const double* dinv, const double* dinvt, int nb, int n,
+                                        double* linv, double* linvt, size_t ld)
+{
+    if (n <= 0) return 0;
+    const int nblk = (n + nb - 1) / nb;
+    scatter_diag_blocks_kernel<<<dim3(8, nblk), 256, 0, st>>>(dinv, dinvt, nb, n, linv, linvt, ld);
+    return status();
+}
+
 extern "C" int htnk_copy2d(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                            size_t ldd, const double* bias)
 {

@@ -302,7 +302,15 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
                 const char* e = getenv("HTN_GEMM_MIN64");
                 min64 = e ? atoi(e) : 148;
             }
-            bn = ctas64 < min64 ? 32 : wide_config();
+            // ... and unless K is long: a 64 x 64 tile of the TMA kernel covers the same area as a 128 x 32 tile
+            // here, so the narrow kernel only wins where its short prologue matters (the K = 128 panel updates)
+            static int kwide = -1;  // HTN_GEMM_KWIDE (experiments): shortest K that takes the wide kernel regardless
+            if (kwide < 0) {
+                const char* e = getenv("HTN_GEMM_KWIDE");
+                kwide = e ? atoi(e) : 512;
+            }
+            // (from 64 tiles on: the 128-column strips of the look-ahead factorisation, 30 tiles, stay narrow - measured)
+            bn = (ctas64 < min64 && (K < kwide || ctas64 < 64)) ? 32 : wide_config();
         }
     }
     GemmParams p;

@@ -97,6 +97,9 @@ int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, int n, int l
 int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                    size_t ldd);
 /* dst[r][c] = src[r][c] (rows x cols), optional bias[c] added; strided 2-D copy */
+/* all nb x nb diagonal-block inverses (stored block after block) and their transposes -> the diagonals of linv / linvt */
+int htnk_scatter_diag_blocks(cudaStream_t st, const double* dinv, const double* dinvt, int nb, int n, double* linv,
+                             double* linvt, size_t ld);
 int htnk_copy2d(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                 size_t ldd, const double* bias);
 /* dst[r][c] = src[r][c] / d[c]  (structured precision, diagonal A: src/htnorm.c:272-280) */

@@ -224,22 +224,86 @@ done:
  *   L = [L11 0; L21 L22]  ->  L^-1 = [L11^-1 0; -L22^-1 L21 L11^-1, L22^-1]
  * The leaves are the 128 x 128 diagonal-block inverses of trtri_batched; every inner node is two large GEMMs
  * (instead of a 16-step column sweep whose GEMMs have 64 CTAs each): n = 2000: 1.5 -> 0.5 ms. */
-static int inverse_rec(htn_ctx_t* ctx, htn_factor_t* fa, int lo, int hi, double* tt, size_t ldt)
+/* The two halves of a node are independent until the node's own products: the left half of the top two levels runs
+ * on a side stream (four sub-trees in flight; the lower levels are chains of small launches, n = 2000: 92 of them).
+ * Streams and events are created once per host thread and device and kept. */
+#define INV_FORKS 3 /* root, and its two children */
+static _Thread_local struct {
+    int device;
+    cudaStream_t side[INV_FORKS];
+    cudaEvent_t ev_fork[INV_FORKS], ev_join[INV_FORKS];
+} iv = {-1, {NULL, NULL, NULL}, {NULL, NULL, NULL}, {NULL, NULL, NULL}};
+
+static int inverse_forks_ready(int device)
+{
+    if (iv.device == device) return 1;
+    if (iv.device >= 0) { /* another device was current before: let go of its objects */
+        for (int i = 0; i < INV_FORKS; i++) {
+            cudaStreamDestroy(iv.side[i]);
+            cudaEventDestroy(iv.ev_fork[i]);
+            cudaEventDestroy(iv.ev_join[i]);
+        }
+        iv.device = -1;
+    }
+    int made = 0;
+    for (; made < INV_FORKS; made++) {
+        if (cudaStreamCreateWithFlags(&iv.side[made], cudaStreamNonBlocking) != cudaSuccess) break;
+        if (cudaEventCreateWithFlags(&iv.ev_fork[made], cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(iv.side[made]);
+            break;
+        }
+        if (cudaEventCreateWithFlags(&iv.ev_join[made], cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(iv.side[made]);
+            cudaEventDestroy(iv.ev_fork[made]);
+            break;
+        }
+    }
+    if (made < INV_FORKS) { /* no forks then: the recursion simply stays on one stream */
+        for (int i = 0; i < made; i++) {
+            cudaStreamDestroy(iv.side[i]);
+            cudaEventDestroy(iv.ev_fork[i]);
+            cudaEventDestroy(iv.ev_join[i]);
+        }
+        cudaGetLastError();
+        return 0;
+    }
+    iv.device = device;
+    return 1;
+}
+
+/* slot: fork resources this node may use (0 root, 1 / 2 its children), -1 = stay on the stream.  The leaves (diagonal-
+ * block inverses) are already in place (htnk_scatter_diag_blocks). */
+static int inverse_rec(htn_ctx_t* ctx, htn_factor_t* fa, int lo, int hi, double* tt, size_t ldt, int slot)
 {
     int rc = 0;
     const size_t ld = fa->ld;
     const int n = hi - lo;
-    if (n <= HTN_NB) {
-        const int jb = lo / HTN_NB;
-        HTN_TRY(htnk_copy2d(ctx->stream, fa->dinv + (size_t)jb * HTN_NB * HTN_NB, HTN_NB, n, n,
-                            fa->linv + (size_t)lo * ld + lo, ld, NULL));
-        HTN_TRY(htnk_copy2d(ctx->stream, fa->dinvt + (size_t)jb * HTN_NB * HTN_NB, HTN_NB, n, n,
-                            fa->linvt + (size_t)lo * ld + lo, ld, NULL));
-        return 0;
-    }
+    if (n <= HTN_NB) return 0;
     const int mid = lo + (int)htn_round_up((size_t)(n / 2), HTN_NB);
-    HTN_TRY(inverse_rec(ctx, fa, lo, mid, tt, ldt));
-    HTN_TRY(inverse_rec(ctx, fa, mid, hi, tt, ldt));
+    if (slot >= 0 && n >= 4 * HTN_NB) {
+        const size_t half = htn_round_up((size_t)((mid - lo) / 2), HTN_NB) + HTN_NB;
+        const size_t ldt2 = htn_round_up(half, 16);
+        double* tt2 = NULL;
+        HTN_TRY(htn_dalloc(ctx, (void**)&tt2, 2 * ldt2 * ldt2 * sizeof(double)));
+        htn_ctx_t left = *ctx;
+        left.stream = iv.side[slot];
+        int forked = cudaEventRecord(iv.ev_fork[slot], ctx->stream) == cudaSuccess &&
+                     cudaStreamWaitEvent(left.stream, iv.ev_fork[slot], 0) == cudaSuccess;
+        if (!forked) left.stream = ctx->stream;
+        const int child = slot == 0 ? 1 : -1; /* the root's children fork once more */
+        int rc_l = inverse_rec(&left, fa, lo, mid, tt2, ldt2, forked ? child : -1);
+        int rc_r = inverse_rec(ctx, fa, mid, hi, tt, ldt, forked && slot == 0 ? 2 : -1);
+        if (forked && (cudaEventRecord(iv.ev_join[slot], left.stream) != cudaSuccess ||
+                       cudaStreamWaitEvent(ctx->stream, iv.ev_join[slot], 0) != cudaSuccess)) {
+            cudaStreamSynchronize(left.stream); /* never free a buffer the side stream may still be using */
+            if (!rc_l) rc_l = HTN_E_CUDA;
+        }
+        htn_dfree(ctx, tt2);
+        if (rc_l || rc_r) return rc_l ? rc_l : rc_r;
+    } else {
+        HTN_TRY(inverse_rec(ctx, fa, lo, mid, tt, ldt, -1));
+        HTN_TRY(inverse_rec(ctx, fa, mid, hi, tt, ldt, -1));
+    }
     {
         /* both products have a triangular operand, placed where the GEMM can skip its zero blocks (the B side) */
         const int M = hi - mid, N = mid - lo;
@@ -272,7 +336,8 @@ int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa)
         const size_t half = htn_round_up((size_t)(fa->n / 2), HTN_NB) + HTN_NB;
         const size_t ldt = htn_round_up(half, 16);
         HTN_TRY(htn_dalloc(ctx, (void**)&tt, 2 * ldt * ldt * sizeof(double))); /* T and T^T */
-        rc = inverse_rec(ctx, fa, 0, fa->n, tt, ldt);
+        rc = htnk_scatter_diag_blocks(ctx->stream, fa->dinv, fa->dinvt, HTN_NB, fa->n, fa->linv, fa->linvt, fa->ld);
+        if (!rc) rc = inverse_rec(ctx, fa, 0, fa->n, tt, ldt, inverse_forks_ready(ctx->device) ? 0 : -1);
         htn_dfree(ctx, tt);
         return rc;
     }
