@@ -37,7 +37,7 @@ struct TmaGemmParams {
     int mode, ktri, kext0;
     int tiles_m, tiles_n;
     const int* skip;  // device flag: a non-zero value turns the launch into a no-op (failed factorisation)
-    int paired;  // B_LOWER: one CTA runs the N tiles (tiles_n-1-q, q) of a row slab back to back
+    int paired;  // triangular B: one CTA runs the N tiles (tiles_n-1-q, q) of a row slab back to back
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,7 +139,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // the CTA's tiles as two tile indices and one chunk count: the descriptors are recomputed where they are needed
     // (a dozen integer instructions) instead of being carried in registers next to the 128 accumulators
     int ntl = 1, tn0, tn1, m0;
-    if (mode_of<MODE>(p) == HTNK_GEMM_B_LOWER && p.paired) {
+    if ((mode_of<MODE>(p) == HTNK_GEMM_B_LOWER || mode_of<MODE>(p) == HTNK_GEMM_B_UPPER) && p.paired) {
         const int npairs = (p.tiles_n + 1) >> 1;
         const int q = bid % npairs;
         m0 = (bid / npairs) * BM;
@@ -393,7 +393,7 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     int wm_cfg = wm_env == 4 || wm_env == 8 ? wm_env : 8;
     if (wm_env != 4 && wm_env != 8) {
         const long long t128 = (long long)((M + 127) / 128) * ((N + BN - 1) / BN);
-        const long long work = (mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_C_LOWER) ? t128 / 2 : t128;
+        const long long work = (mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_C_LOWER || mode == HTNK_GEMM_B_UPPER) ? t128 / 2 : t128;
         if (work < 3 * 148) wm_cfg = 4;
     }
     const int BM = 16 * wm_cfg, A_BYTES = BM * BK * 8;
@@ -407,7 +407,8 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) return -202;
-    p.paired = (mode == HTNK_GEMM_B_LOWER && p.tiles_n >= 2) ? 1 : 0;
+    // triangular B: K length grows (B_LOWER) or shrinks (B_UPPER) linearly with the N tile - pair the ends
+    p.paired = ((mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_B_UPPER) && p.tiles_n >= 2) ? 1 : 0;
     const unsigned grid = p.paired ? (unsigned)p.tiles_m * (unsigned)((p.tiles_n + 1) / 2)
                                    : (unsigned)p.tiles_m * (unsigned)p.tiles_n;
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
