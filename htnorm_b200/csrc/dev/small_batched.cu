@@ -108,7 +108,7 @@ __host__ __device__ inline SmallGeom small_geom(int k, int k2, int nthreads)
     g.a_doubles = 0;
     for (int t = 0; t < g.ntiles; t++) g.a_doubles += 8 * tile_ld(g.ntiles, t);
     g.doubles = (size_t)g.a_doubles + (size_t)k2 * g.ldg + (size_t)g.kpad * g.kc + 8 * (size_t)g.ldg +
-                2 * (size_t)g.kpad + (size_t)g.nw * g.kc * g.kc + (size_t)g.nw * MAXK2 + MAXK2 + 8 * 12;
+                2 * (size_t)g.kpad + (size_t)g.nw * g.kc * g.kc + (size_t)g.nw * MAXK2 + MAXK2 + 2 * 8 * 12;
     return g;
 }
 
@@ -145,7 +145,7 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
     double* S2p = y + kpad;                      // [NW][kc][kc]    per-warp partial sums of G cov G^T
     double* gyp = S2p + (size_t)NW * kc * kc;    // [NW][MAXK2]     per-warp partial sums of G y
     double* alpha = gyp + NW * MAXK2;            // [MAXK2]         (k2 > 4 only)
-    double* Tsm = alpha + MAXK2;                 // [8][12]         inverse of the current diagonal block's factor
+    double* Tsm = alpha + MAXK2;                 // [2][8][12]      inverse of the diagonal block's factor (block b in half b & 1)
     __shared__ int s_fail, s_info2;
     __shared__ int toff[MAXT], tld[MAXT];
     // every tile (ti <= tj) of the triangle, row by row: {8 ti, 8 tj, A index of its element (0, 0), leading dimension}
@@ -338,10 +338,11 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
         // ---- Cholesky cov = U^T U in 8-row panels, factor warp + update warps ----
         //   warp 0 factors the 8 x 8 diagonal block in registers (all lanes alike) together with the inverse T of
         //   its factor, and lane 0 parks T in shared memory;
-        //   all warps then form the panel rows U = T * (rows of cov) with DMMA, eight columns per tile;
-        //   the trailing update (rank 8, DMMA) is split by role: warp 0 updates just the NEXT diagonal block and
-        //   factors it at once, while the other warps update every other tile - the 8-pivot dependency chain of
-        //   the next block runs beside the bulk of the update instead of after it (look-ahead).
+        //   the panel rows U = T * (rows of cov) are formed with DMMA, eight columns per tile, and the trailing update
+        //   (rank 8, DMMA) follows; both are split by role: warp 0 forms only the panel tile right of the diagonal,
+        //   updates just the NEXT diagonal block with it and factors that at once, while the other warps form the rest of
+        //   the panel row and update every other tile - the 8-pivot dependency chain of the next block runs beside all
+        //   the bulk work of the pass instead of after it (look-ahead), one block barrier per pass.
         if (!diag) {
             auto factor_block = [&](int bb) {  // warp 0 only
                 const double* Ab = A + toff[bb];
@@ -381,20 +382,54 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
                 if (lane == 0 && bad >= 0) s_fail = j0 + bad + 1;
                 if (lane < 8) {  // lane c publishes column c of T (zeros above the diagonal come out by themselves)
 #pragma unroll
-                    for (int r = 0; r < 8; r++) Tsm[r * 12 + lane] = w[r];
+                    for (int r = 0; r < 8; r++) Tsm[(bb & 1) * 96 + r * 12 + lane] = w[r];
                 }
             };
             if (warp == 0) factor_block(0);
             __syncthreads();
+            // One pass per 8-row panel, one block barrier per pass.  The pivot chain runs on warp 0 alone:
+            //   factor(b) -> panel tile (b, b+1) -> update of the diagonal block b+1 -> factor(b+1),
+            // while the other warps form the rest of panel row b and apply the rank-8 update to every other tile.  The
+            // only hand-off inside a pass is tile (b, b+1) of the panel row (named barrier 1: warp 0 arrives, the others wait).
             for (int b = 0; b < ntiles && !s_fail; b++) {
                 const int j0 = 8 * b;
-                {
-                    // panel rows: U[j0 .. j0+7][columns of tile tj] = T * cov-rows, tiles dealt to the warps
-                    double* Ab = A + toff[b];
-                    const int lb = tld[b];
-                    const double ta0 = Tsm[g * 12 + t4], ta1 = Tsm[g * 12 + 4 + t4];
-                    double* pd = P + g * ldg + j0 + 2 * t4;
-                    if (warp == 0) {  // the diagonal block is symmetric: element (row, col) lives at (min, max)
+                double* Ab = A + toff[b];
+                const int lb = tld[b];
+                // (T is double-buffered: warp 0 parks T of block b+1 during this pass, whenever it gets there)
+                const double ta0 = Tsm[(b & 1) * 96 + g * 12 + t4], ta1 = Tsm[(b & 1) * 96 + g * 12 + 4 + t4];
+                double* pd = P + g * ldg + j0 + 2 * t4;
+                const double* bs = Ab + t4 * lb + g;
+                double* cd = Ab + g * lb + 2 * t4;
+                if (warp == 0) {
+                    if (b + 1 < ntiles) {
+                        {  // panel tile (b, b+1)
+                            const double x0 = bs[8], x1 = bs[4 * lb + 8];
+                            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                            dmma_acc(c0, c1, ta0, x0);
+                            dmma_acc(e0, e1, ta1, x1);
+                            const double2 v = make_double2(c0 + e0, c1 + e1);
+                            *reinterpret_cast<double2*>(cd + 8) = v;
+                            *reinterpret_cast<double2*>(pd + 8) = v;
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        asm volatile("bar.arrive 1, %0;\n" ::"n"(NTH) : "memory");
+                        // next diagonal block: update, then factor
+                        const int ti = b + 1;
+                        const double a0 = -P[t4 * ldg + ti * 8 + g], a1 = -P[(4 + t4) * ldg + ti * 8 + g];
+                        const double b0 = P[t4 * ldg + ti * 8 + g], b1 = P[(4 + t4) * ldg + ti * 8 + g];
+                        double2* cp = reinterpret_cast<double2*>(A + toff[ti] + g * tld[ti] + 2 * t4);
+                        double2 c = *cp;
+                        double e0 = 0.0, e1 = 0.0;
+                        dmma_acc(c.x, c.y, a0, b0);
+                        dmma_acc(e0, e1, a1, b1);
+                        *cp = make_double2(c.x + e0, c.y + e1);
+                        __syncwarp();
+                        factor_block(ti);
+                    }
+                } else {
+                    // panel rows: U[j0 .. j0+7][columns of tile tj] = T * cov-rows
+                    if (warp == 1) {  // the diagonal block is symmetric: element (row, col) lives at (min, max)
                         const double b0 = g < t4 ? Ab[g * lb + t4] : Ab[t4 * lb + g];
                         const double b1 = g < 4 + t4 ? Ab[g * lb + 4 + t4] : Ab[(4 + t4) * lb + g];
                         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -404,12 +439,11 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
                         *reinterpret_cast<double2*>(Ab + g * lb + 2 * t4) = v;
                         *reinterpret_cast<double2*>(pd) = v;
                     }
-                    // the other tiles of the row, dealt to the warps, two per pass
-                    const double* bs = Ab + t4 * lb + g;
-                    double* cd = Ab + g * lb + 2 * t4;
-                    int tj = b + 1 + warp;
-                    for (; tj + NW < ntiles; tj += 2 * NW) {
-                        const int ca = (tj - b) * 8, cb2 = ca + 8 * NW;
+                    // tiles b+2 .. of the row, dealt to the update warps, two per pass
+                    constexpr int NU = NW - 1;
+                    int tj = b + 2 + (warp - 1);
+                    for (; tj + NU < ntiles; tj += 2 * NU) {
+                        const int ca = (tj - b) * 8, cb2 = ca + 8 * NU;
                         const double x0 = bs[ca], x1 = bs[4 * lb + ca], y0 = bs[cb2], y1 = bs[4 * lb + cb2];
                         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0 = 0.0, h1 = 0.0;
                         dmma_acc(c0, c1, ta0, x0);
@@ -432,25 +466,11 @@ ht_small_kernel(size_t nproblems, int k, int k2, const double* __restrict__ mean
                         *reinterpret_cast<double2*>(cd + ca) = v;
                         *reinterpret_cast<double2*>(pd + ca) = v;
                     }
-                }
-                __syncthreads();
-                PHASE(3)
-                if (b + 1 < ntiles) {
-                    if (warp == 0) {  // next diagonal block: update, then factor
-                        const int ti = b + 1;
-                        const double a0 = -P[t4 * ldg + ti * 8 + g], a1 = -P[(4 + t4) * ldg + ti * 8 + g];
-                        const double b0 = P[t4 * ldg + ti * 8 + g], b1 = P[(4 + t4) * ldg + ti * 8 + g];
-                        double2* cp = reinterpret_cast<double2*>(A + toff[ti] + g * tld[ti] + 2 * t4);
-                        double2 c = *cp;
-                        double e0 = 0.0, e1 = 0.0;
-                        dmma_acc(c.x, c.y, a0, b0);
-                        dmma_acc(e0, e1, a1, b1);
-                        *cp = make_double2(c.x + e0, c.y + e1);
-                        __syncwarp();
-                        factor_block(ti);
-                    } else {
-                        // every other tile (ti <= tj) beyond the panel: the flat tile list from the entry after
-                        // (b+1, b+1) to its end, four tiles per pass dealt to the update warps; all operands of a
+                    if (b + 1 < ntiles) {
+                        // the whole panel row (warp 0's tile included) must be in P before the update reads it
+                        asm volatile("bar.sync 1, %0;\n" ::"n"(NTH) : "memory");
+                        // every tile (ti <= tj) beyond the panel except (b+1, b+1): the flat tile list from the entry
+                        // after (b+1, b+1) to its end, four tiles per pass dealt to the update warps; all operands of a
                         // pass are loaded before its (independent) DMMAs are issued
                         const double* pb0 = P + t4 * ldg + g;
                         const double* pb1 = pb0 + 4 * ldg;
