@@ -44,6 +44,40 @@ done:
     return rc;
 }
 
+/* side streams and events of the structured path: created once per host thread and device and kept (creating and
+ * destroying them costs more host time than a small batch takes) */
+static _Thread_local struct {
+    int device;
+    cudaStream_t side, side2;
+    cudaEvent_t ev_fork, ev_rng, ev_a, ev_y1;
+} ss = {-1, NULL, NULL, NULL, NULL, NULL, NULL};
+
+static int sp_streams_ready(int device)
+{
+    if (ss.device == device) return 0;
+    if (ss.device >= 0) { /* another device was current before: let go of its objects */
+        cudaStreamDestroy(ss.side);
+        cudaStreamDestroy(ss.side2);
+        cudaEventDestroy(ss.ev_fork);
+        cudaEventDestroy(ss.ev_rng);
+        cudaEventDestroy(ss.ev_a);
+        cudaEventDestroy(ss.ev_y1);
+        ss.device = -1;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ss.side2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_rng, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_a, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_y1, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        htn_set_error("structured precision: side streams: %s", cudaGetErrorString(e));
+        return HTN_E_CUDA;
+    }
+    ss.device = device;
+    return 0;
+}
+
 int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, size_t n_, size_t p_,
                   const double* mean, const double* a, const double* phi, const double* omega, int struct_mean,
                   int a_id, int o_id, double* out, int* d_info_out, int* first_info)
@@ -65,9 +99,11 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     double *da = NULL, *sda = NULL, *sdo = NULL, *invo = NULL;
     double *Z1 = NULL, *Z2 = NULL, *Y1 = NULL, *Y2 = NULL;
     int* d_info = NULL;
-    cudaStream_t side = NULL;  /* the generator: chunk 0 is drawn while A, Omega and M are being factorised */
-    cudaEvent_t ev_fork = NULL, ev_rng = NULL, ev_done = NULL;
-    int rng_in_flight = 0;
+    /* side: the generator - chunk 0 is drawn while A, Omega and M are being factorised; side2: Y1 of chunk 0, one big
+     * triangular GEMM that needs only chol(A), beside the chain of small launches that builds X and M */
+    cudaStream_t side = NULL, side2 = NULL;
+    cudaEvent_t ev_fork = NULL, ev_rng = NULL, ev_a = NULL, ev_y1 = NULL;
+    int rng_in_flight = 0, y1_in_flight = 0, side2_used = 0;
     htn_factor_t fa, fo, fm;
     memset(&fa, 0, sizeof(fa));
     memset(&fo, 0, sizeof(fo));
@@ -103,10 +139,9 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     HTN_TRY(htn_dalloc(ctx, (void**)&Z2, chunk * np * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&Y2, chunk * np * 8));
     if (a_id == NORMAL) HTN_TRY(htn_dalloc(ctx, (void**)&Y1, chunk * pp * 8));
-    HTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_rng, cudaEventDisableTiming));
-    HTN_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    HTN_TRY(sp_streams_ready(ctx->device));
+    side = ss.side, side2 = ss.side2;
+    ev_fork = ss.ev_fork, ev_rng = ss.ev_rng, ev_a = ss.ev_a, ev_y1 = ss.ev_y1;
     /* Both runs of normals of chunk 0 are drawn up front (y1's then y2's, from the same stream).  If chol(A)
      * or chol(omega) fails the reference would have stopped earlier: only the single-draw entry cares (it
      * writes the generator back), and it re-checks the codes below before touching the caller's state. */
@@ -126,7 +161,21 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     }
 
     /* ---- A, Omega: factor (dense) (mvn_rand_prec, src/htnorm_distributions.c:110-123) ---- */
-    if (a_id == NORMAL) HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
+    if (a_id == NORMAL) {
+        HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
+        if (rng_in_flight) { /* L^T y1 = z for chunk 0 (see the loop below), started as soon as L_A^-1 exists */
+            const size_t nb0 = nsamples < chunk ? nsamples : chunk;
+            htn_ctx_t c2 = *ctx;
+            c2.stream = side2;
+            HTN_CUDA(cudaEventRecord(ev_a, st));
+            HTN_CUDA(cudaStreamWaitEvent(side2, ev_a, 0));
+            HTN_CUDA(cudaStreamWaitEvent(side2, ev_rng, 0));
+            side2_used = 1;
+            HTN_TRY(htn_solve_l(&c2, &fa, Z1, pp, Y1, pp, (int)nb0));
+            HTN_CUDA(cudaEventRecord(ev_y1, side2));
+            y1_in_flight = 1;
+        }
+    }
     if (o_id == NORMAL) HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1));
     /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs) */
     if (a_id == IDENTITY) {
@@ -190,7 +239,12 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         /* L^T y1 = z (dtrsv, src/htnorm_distributions.c:120) for the whole chunk: Y1 = Z1 L_A^-1 */
         const double* y1 = Z1;
         if (a_id == NORMAL) {
-            HTN_TRY(htn_solve_l(ctx, &fa, Z1, pp, Y1, pp, nb));
+            if (b0 == 0 && y1_in_flight) {
+                HTN_CUDA(cudaStreamWaitEvent(st, ev_y1, 0));
+                y1_in_flight = 0;
+            } else {
+                HTN_TRY(htn_solve_l(ctx, &fa, Z1, pp, Y1, pp, nb));
+            }
             y1 = Y1;
         }
         double* bm = Z2;
@@ -220,6 +274,10 @@ finish:
     if (d_info_out) rc = htnk_fill_i32(st, d_info_out, nsamples, *first_info);
 done:
     if (rng_in_flight && ev_rng) cudaStreamWaitEvent(st, ev_rng, 0); /* never free under the generator */
+    if (side2_used && (y1_in_flight || rc)) { /* ... nor under the early Y1 product, whatever state it was left in */
+        if (cudaEventRecord(ev_y1, side2) != cudaSuccess || cudaStreamWaitEvent(st, ev_y1, 0) != cudaSuccess)
+            cudaStreamSynchronize(side2);
+    }
     htn_factor_free(ctx, &fa);
     htn_factor_free(ctx, &fo);
     htn_factor_free(ctx, &fm);
@@ -239,10 +297,6 @@ done:
     htn_dfree(ctx, FA);
     htn_dfree(ctx, Phip);
     htn_dfree(ctx, d_info);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_rng) cudaEventDestroy(ev_rng);
-    if (ev_done) cudaEventDestroy(ev_done);
-    if (side) cudaStreamDestroy(side);
     return rc;
 }
 
