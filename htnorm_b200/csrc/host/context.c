@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static _Thread_local char g_err[512] = "";
@@ -16,6 +17,13 @@ void htn_set_error(const char* fmt, ...)
 }
 
 const char* htn_last_error(void) { return g_err; }
+
+size_t htn_chunk_budget(void)
+{
+    const char* e = getenv("HTN_CHUNK_BYTES");
+    if (e && atoll(e) >= 4096) return (size_t)atoll(e);
+    return (size_t)3 << 30;
+}
 const char* htn_version(void) { return "htnorm-b200 0.1 (sm_100a)"; }
 unsigned long long htn_launch_count(void) { return htnk_launch_count(); }
 

@@ -27,6 +27,8 @@ typedef struct {
 } htn_ctx_t;
 
 void htn_set_error(const char* fmt, ...);
+/* bytes of normals drawn per chunk of a large batch: 3 GiB, or HTN_CHUNK_BYTES (tests: forces many small chunks) */
+size_t htn_chunk_budget(void);
 
 /* select the device, pick/create the stream.  host_mode: create a private non-blocking stream */
 int htn_ctx_begin(htn_ctx_t* ctx, int device, void* stream, int host_mode);

@@ -107,7 +107,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     HTN_CUDA(cudaMemsetAsync(Sm, 0, (size_t)k2 * k2p * 8, st));
 
     size_t chunk = nsamples;
-    const size_t budget = (size_t)3 << 30; /* bytes of Z~ per chunk (two chunks are in flight) */
+    const size_t budget = htn_chunk_budget(); /* bytes of Z~ per chunk (two chunks are in flight) */
     if (chunk * ldz * 8 > budget) chunk = htn_round_up(budget / (ldz * 8), 128);
     double* const sink = ctx->host_sink;
     cudaStream_t copy_st = NULL;

@@ -110,7 +110,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     memset(&fm, 0, sizeof(fm));
 
     size_t chunk = nsamples;
-    const size_t budget = (size_t)3 << 30;
+    const size_t budget = htn_chunk_budget();
     if (chunk * (pp + np) * 8 > budget) chunk = htn_round_up(budget / ((pp + np) * 8), 128);
 
     HTN_TRY(htn_dalloc(ctx, (void**)&d_info, 3 * sizeof(int)));

@@ -561,6 +561,48 @@ def test_edge_cases_empty_ragged_chunked(h, oracle):
     assert rel_err(xh[spot], xo) < REL_TOL
 
 
+def test_large_batch_chunks_equal_one_chunk(h, monkeypatch):
+    """Batches whose normals exceed the per-chunk budget (3 GiB) are drawn chunk by chunk (two generator launches in
+    flight beside the GEMMs).  HTN_CHUNK_BYTES forces that path at test size: many small chunks must give the bits of
+    the single-chunk call - hyperplane (k2 <= 4 fused coefficients, k2 > 16 blocked solve) and structured precision
+    (early Y1 of chunk 0, later chunks in the loop), device and host memory."""
+    import torch
+    dev = "cuda:0"
+    rng = np.random.default_rng(21)
+    B = 3000
+    for name in ("k7_dense_333", "k20_dense_400"):
+        try:
+            c = cases.ht_case(name)
+        except Exception:
+            k, k2 = 400, 20
+            c = dict(mean=rng.standard_normal(k), cov=cases.spd(rng, k), g=rng.standard_normal((k2, k)),
+                     r=rng.standard_normal(k2))
+        t = [torch.from_numpy(np.ascontiguousarray(c[n_])).to(dev) for n_ in ("mean", "cov", "g", "r")]
+        monkeypatch.delenv("HTN_CHUNK_BYTES", raising=False)
+        one, _ = h.hyperplane_truncated_mvnorm_batch(B, *t, seed0=5)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("HTN_CHUNK_BYTES", str(1 << 20))      # 1 MiB of normals per chunk: ~8-23 chunks
+        many, info = h.hyperplane_truncated_mvnorm_batch(B, *t, seed0=5)
+        torch.cuda.synchronize()
+        host, ih = h.hyperplane_truncated_mvnorm_batch(B, c["mean"], c["cov"], c["g"], c["r"], seed0=5)
+        assert torch.equal(one, many) and not bool(info.any()), name
+        assert np.array_equal(host, one.cpu().numpy()) and not ih.any(), name
+    for name in ("nd_plain_mid", "nn_struct_mid"):
+        c = cases.sp_case(name)
+        args = (c["mean"], c["a"], c["phi"], c["omega"], c["struct_mean"], c["a_type"], c["o_type"])
+        targs = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) if isinstance(x, np.ndarray) else x for x in args)
+        monkeypatch.delenv("HTN_CHUNK_BYTES", raising=False)
+        one, _ = h.structured_precision_mvnorm_batch(B, *targs, gen=c["gen"], seed0=9)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("HTN_CHUNK_BYTES", str(1 << 20))
+        many, info = h.structured_precision_mvnorm_batch(B, *targs, gen=c["gen"], seed0=9)
+        torch.cuda.synchronize()
+        host, ih = h.structured_precision_mvnorm_batch(B, *args, gen=c["gen"], seed0=9)
+        assert torch.equal(one, many) and not bool(info.any()), name
+        assert np.array_equal(host, one.cpu().numpy()) and not ih.any(), name
+    monkeypatch.delenv("HTN_CHUNK_BYTES", raising=False)
+
+
 def test_full_size_headline_properties(h, oracle):
     """BASELINE headline size (k = 1000, k2 = 1, 65 536 samples, device-resident): size-independent properties
     (constraint residual, sample mean of the projected distribution) plus a spot check of 6 samples against
