@@ -271,9 +271,24 @@ def main():
     # ---- timed (N > 1 only): the same steps followed by the one collective of the path, an NCCL all-gather of the
     # output shards.  Shards are double-buffered, so the gather of step i runs beside step i + 1. ----
     gathered = None
-    if world > 1 and not args.no_gather:
-        outs = [out, torch.empty_like(out)]
-        full = torch.empty((world * B, K), dtype=torch.float64, device=dev)
+    gather_on = world > 1 and not args.no_gather
+    if gather_on:
+        # the receive buffer holds the whole global batch (world x 524 MB): skip the leg on every rank if any rank
+        # cannot allocate it
+        try:
+            outs = [out, torch.empty_like(out)]
+            full = torch.empty((world * B, K), dtype=torch.float64, device=dev)
+            have = 1
+        except RuntimeError:
+            outs = full = None
+            have = 0
+        havet = torch.tensor([have], dtype=torch.int32, device=dev)
+        dist.all_reduce(havet, op=dist.ReduceOp.MIN)
+        if not bool(havet.item()):
+            gather_on = False
+            gathered = {"value": None, "unit": "samples/s", "skipped": "receive buffer did not fit"}
+            outs = full = None
+    if gather_on:
         works = [None, None]
 
         def step_gather(i):
