@@ -75,6 +75,7 @@ typedef struct {
     double* pscr;   /* scratch of the fused panel kernel: 16 x 64 doubles (8 x 8 inverse factors) + 17 flags */
     double* linv;   /* n x ld: explicit L^-1 (lower), NULL until htn_factor_make_inverse */
     double* linvt;  /* its transpose */
+    int inv_block;  /* 0: linv / linvt hold all of L^-1; W > 0: only its W x W diagonal blocks (block substitution) */
     int nblk;
     int solves;     /* the factor will be used by the blocked triangular solves (needs every inverse) */
 } htn_factor_t;
@@ -92,6 +93,9 @@ int htn_trsm_right_lt(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t 
 /* X := X * L^-1   (solves X_new L = X); needs fa->u */
 int htn_trsm_right_l(htn_ctx_t* ctx, const htn_factor_t* fa, double* x, size_t ldx, int m);
 int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa);
+/* only the inverses of the W x W diagonal blocks of L (W a multiple of 128): the solves below then substitute block by
+ * block - cheaper than the whole inverse when few rows are solved against a large factor; needs fa->u */
+int htn_factor_make_inverse_blocks(htn_ctx_t* ctx, htn_factor_t* fa, int w);
 int htn_solve_l(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m);
 int htn_solve_lt(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m);
 int htn_solve_spd(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* t, double* y,

@@ -332,6 +332,7 @@ int htn_factor_make_inverse(htn_ctx_t* ctx, htn_factor_t* fa)
     if (!fa->linvt) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linvt, bytes));
     HTN_CUDA(cudaMemsetAsync(fa->linv, 0, bytes, ctx->stream));
     HTN_CUDA(cudaMemsetAsync(fa->linvt, 0, bytes, ctx->stream));
+    fa->inv_block = 0;
     if (fa->dinv && fa->dinvt) {
         const size_t half = htn_round_up((size_t)(fa->n / 2), HTN_NB) + HTN_NB;
         const size_t ldt = htn_round_up(half, 16);
@@ -349,9 +350,89 @@ done:
     return rc;
 }
 
+int htn_factor_make_inverse_blocks(htn_ctx_t* ctx, htn_factor_t* fa, int w)
+{
+    int rc = 0;
+    const size_t bytes = (size_t)fa->n * fa->ld * sizeof(double);
+    double* tt = NULL;
+    if (w <= 0 || w % HTN_NB || !fa->dinv || !fa->dinvt || !fa->u || w >= fa->n) return htn_factor_make_inverse(ctx, fa);
+    if (!fa->linv) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linv, bytes));
+    if (!fa->linvt) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linvt, bytes));
+    HTN_CUDA(cudaMemsetAsync(fa->linv, 0, bytes, ctx->stream));
+    HTN_CUDA(cudaMemsetAsync(fa->linvt, 0, bytes, ctx->stream));
+    {
+        const size_t half = htn_round_up((size_t)(w / 2), HTN_NB) + HTN_NB;
+        const size_t ldt = htn_round_up(half, 16);
+        const int forks = inverse_forks_ready(ctx->device);
+        HTN_TRY(htn_dalloc(ctx, (void**)&tt, 2 * ldt * ldt * sizeof(double))); /* T and T^T */
+        rc = htnk_scatter_diag_blocks(ctx->stream, fa->dinv, fa->dinvt, HTN_NB, fa->n, fa->linv, fa->linvt, fa->ld);
+        for (int lo = 0; lo < fa->n && !rc; lo += w)
+            rc = inverse_rec(ctx, fa, lo, lo + w < fa->n ? lo + w : fa->n, tt, ldt, forks ? 0 : -1);
+        htn_dfree(ctx, tt);
+        if (!rc) fa->inv_block = w;
+    }
+done:
+    return rc;
+}
+
+/* block substitution with the diagonal-block inverses (fa->inv_block = W): per block column one update GEMM with the
+ * columns already solved and one triangular GEMM with the block's inverse */
+static int solve_l_blocks(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
+{
+    int rc = 0;
+    const int n = fa->n, w = fa->inv_block;
+    const size_t ld = fa->ld, ldt = htn_round_up((size_t)w, 16);
+    double* t = NULL;
+    HTN_TRY(htn_dalloc(ctx, (void**)&t, (size_t)m * ldt * sizeof(double)));
+    for (int c0 = (n - 1) / w * w; c0 >= 0; c0 -= w) { /* Y L = X: last block column first */
+        const int wj = n - c0 < w ? n - c0 : w, r1 = c0 + wj, k = n - r1;
+        const double* src = x + c0;
+        size_t lds = ldx;
+        if (k > 0) { /* T = X_j - Y[:, r1:] L[r1:, c0:c0+wj];  B[nn][kk] = L[r1+kk][c0+nn] = U[c0+nn][r1+kk] */
+            HTN_TRY(htnk_copy2d(ctx->stream, x + c0, ldx, m, wj, t, ldt, NULL));
+            HTN_TRY(htnk_gemm_tn(ctx->stream, m, wj, k, -1.0, y + r1, ldy, fa->u + (size_t)c0 * ld + r1, ld, 1.0, t, ldt,
+                                 NULL, HTNK_GEMM_FULL, 0, 0, 0));
+            src = t;
+            lds = ldt;
+        }
+        HTN_TRY(htnk_gemm_tn(ctx->stream, m, wj, wj, 1.0, src, lds, fa->linvt + (size_t)c0 * ld + c0, ld, 0.0, y + c0, ldy,
+                             NULL, HTNK_GEMM_B_UPPER, 0, 0, 0));
+    }
+done:
+    htn_dfree(ctx, t);
+    return rc;
+}
+
+static int solve_lt_blocks(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
+{
+    int rc = 0;
+    const int n = fa->n, w = fa->inv_block;
+    const size_t ld = fa->ld, ldt = htn_round_up((size_t)w, 16);
+    double* t = NULL;
+    HTN_TRY(htn_dalloc(ctx, (void**)&t, (size_t)m * ldt * sizeof(double)));
+    for (int c0 = 0; c0 < n; c0 += w) { /* Y L^T = X: first block column first */
+        const int wj = n - c0 < w ? n - c0 : w;
+        const double* src = x + c0;
+        size_t lds = ldx;
+        if (c0 > 0) { /* T = X_j - Y[:, :c0] L[c0:c0+wj, :c0]^T;  B[nn][kk] = L[c0+nn][kk] */
+            HTN_TRY(htnk_copy2d(ctx->stream, x + c0, ldx, m, wj, t, ldt, NULL));
+            HTN_TRY(htnk_gemm_tn(ctx->stream, m, wj, c0, -1.0, y, ldy, fa->f + (size_t)c0 * ld, ld, 1.0, t, ldt, NULL,
+                                 HTNK_GEMM_FULL, 0, 0, 0));
+            src = t;
+            lds = ldt;
+        }
+        HTN_TRY(htnk_gemm_tn(ctx->stream, m, wj, wj, 1.0, src, lds, fa->linv + (size_t)c0 * ld + c0, ld, 0.0, y + c0, ldy,
+                             NULL, HTNK_GEMM_B_LOWER, wj, wj, 0));
+    }
+done:
+    htn_dfree(ctx, t);
+    return rc;
+}
+
 /* Y (m x n) = X L^-1      (solves Y L = X; the row form of L^T y = x, dtrsv 'L','T') */
 int htn_solve_l(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
 {
+    if (fa->inv_block) return solve_l_blocks(ctx, fa, x, ldx, y, ldy, m);
     return htnk_gemm_tn(ctx->stream, m, fa->n, fa->n, 1.0, x, ldx, fa->linvt, fa->ld, 0.0, y, ldy, NULL,
                         HTNK_GEMM_B_UPPER, 0, 0, 0);
 }
@@ -359,6 +440,7 @@ int htn_solve_l(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t 
 /* Y = X L^-T     (solves Y L^T = X) */
 int htn_solve_lt(htn_ctx_t* ctx, const htn_factor_t* fa, const double* x, size_t ldx, double* y, size_t ldy, int m)
 {
+    if (fa->inv_block) return solve_lt_blocks(ctx, fa, x, ldx, y, ldy, m);
     return htnk_gemm_tn(ctx->stream, m, fa->n, fa->n, 1.0, x, ldx, fa->linv, fa->ld, 0.0, y, ldy, NULL,
                         HTNK_GEMM_B_LOWER, fa->n, fa->n, 0);
 }

@@ -28,8 +28,18 @@ static double identity_factor_garbage(void)
 
 /* stage a dense SPD input: lower triangle into a fresh n x ld buffer, factorise, and build the explicit
  * inverse factor that turns every later many-row solve into one triangular GEMM */
+/* rows: how many rows will be solved against this factor in all.  Few rows against a large factor: only the 2048-wide
+ * diagonal blocks of the inverse are built (cfg4: p = 8192 against 1024 + 256 rows), and the solves substitute block by
+ * block.  HTN_INV_BLOCK (development / tests): 0 = always the whole inverse, W = that block width regardless. */
+static int inverse_block_width(int n, size_t rows)
+{
+    const char* e = getenv("HTN_INV_BLOCK");
+    if (e) return atoi(e);
+    return (n >= 4096 && rows * 3 <= (size_t)n) ? 2048 : 0;
+}
+
 static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src, double** buf, htn_factor_t* fa,
-                        int* d_info)
+                        int* d_info, int wblock)
 {
     int rc = 0;
     const size_t ld = htn_round_up((size_t)n, 16);
@@ -39,7 +49,7 @@ static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src,
     HTN_TRY(htn_factor_init(ctx, fa, *buf, ld, n, 1));
     HTN_TRY(htn_potrf(ctx, fa, d_info));
     HTN_TRY(htn_factor_make_u(ctx, fa));
-    HTN_TRY(htn_factor_make_inverse(ctx, fa));
+    HTN_TRY(htn_factor_make_inverse_blocks(ctx, fa, wblock)); /* wblock = 0: the whole inverse */
 done:
     return rc;
 }
@@ -162,7 +172,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
 
     /* ---- A, Omega: factor (dense) (mvn_rand_prec, src/htnorm_distributions.c:110-123) ---- */
     if (a_id == NORMAL) {
-        HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0));
+        HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0, inverse_block_width(p, (size_t)2 * n_ + nsamples)));
         if (rng_in_flight) { /* L^T y1 = z for chunk 0 (see the loop below), started as soon as L_A^-1 exists */
             const size_t nb0 = nsamples < chunk ? nsamples : chunk;
             htn_ctx_t c2 = *ctx;
@@ -176,7 +186,8 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
             y1_in_flight = 1;
         }
     }
-    if (o_id == NORMAL) HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1));
+    if (o_id == NORMAL) /* Omega^-1 itself is formed from the whole inverse factor below */
+        HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1, 0));
     /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs) */
     if (a_id == IDENTITY) {
         XT = Phip;

@@ -603,6 +603,30 @@ def test_large_batch_chunks_equal_one_chunk(h, monkeypatch):
     monkeypatch.delenv("HTN_CHUNK_BYTES", raising=False)
 
 
+def test_structured_block_inverse_solves(h, oracle, gold, monkeypatch):
+    """Few rows against a large dense A: only the diagonal blocks of L_A^-1 are inverted and the solves substitute
+    block by block (automatic from p = 4096).  HTN_INV_BLOCK forces that path at test size: golden vectors within
+    the tolerance, and a ragged last block (p = 300 with 128-wide blocks)."""
+    import torch
+    monkeypatch.setenv("HTN_INV_BLOCK", "128")
+    for name in ("nd_plain_mid", "nn_struct_mid", "nd_plain_big"):
+        c = cases.sp_case(name)
+        x, info = h.structured_precision_mvnorm_batch(c["nsamples"], c["mean"], c["a"], c["phi"], c["omega"],
+                                                      c["struct_mean"], c["a_type"], c["o_type"], gen=c["gen"],
+                                                      seed0=c["seed0"])
+        assert not info.any()
+        assert rel_err(x, gold["structured"][name + "__x"]) < REL_TOL, name
+    monkeypatch.setenv("HTN_INV_BLOCK", "0")
+    c = cases.sp_case("nn_struct_mid")
+    x0, _ = h.structured_precision_mvnorm_batch(64, c["mean"], c["a"], c["phi"], c["omega"], c["struct_mean"],
+                                                c["a_type"], c["o_type"], gen=c["gen"], seed0=3)
+    monkeypatch.setenv("HTN_INV_BLOCK", "256")
+    x1, _ = h.structured_precision_mvnorm_batch(64, c["mean"], c["a"], c["phi"], c["omega"], c["struct_mean"],
+                                                c["a_type"], c["o_type"], gen=c["gen"], seed0=3)
+    assert rel_err(x1, x0) < 1e-12
+    monkeypatch.delenv("HTN_INV_BLOCK", raising=False)
+
+
 def test_full_size_headline_properties(h, oracle):
     """BASELINE headline size (k = 1000, k2 = 1, 65 536 samples, device-resident): size-independent properties
     (constraint residual, sample mean of the projected distribution) plus a spot check of 6 samples against
