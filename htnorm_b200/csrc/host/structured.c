@@ -59,8 +59,8 @@ done:
 static _Thread_local struct {
     int device;
     cudaStream_t side, side2;
-    cudaEvent_t ev_fork, ev_rng, ev_a, ev_y1;
-} ss = {-1, NULL, NULL, NULL, NULL, NULL, NULL};
+    cudaEvent_t ev_fork, ev_rng, ev_a, ev_y1, ev_o;
+} ss = {-1, NULL, NULL, NULL, NULL, NULL, NULL, NULL};
 
 static int sp_streams_ready(int device)
 {
@@ -72,6 +72,7 @@ static int sp_streams_ready(int device)
         cudaEventDestroy(ss.ev_rng);
         cudaEventDestroy(ss.ev_a);
         cudaEventDestroy(ss.ev_y1);
+        cudaEventDestroy(ss.ev_o);
         ss.device = -1;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking);
@@ -80,6 +81,7 @@ static int sp_streams_ready(int device)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_rng, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_a, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_y1, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ss.ev_o, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         htn_set_error("structured precision: side streams: %s", cudaGetErrorString(e));
         return HTN_E_CUDA;
@@ -112,8 +114,8 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     /* side: the generator - chunk 0 is drawn while A, Omega and M are being factorised; side2: Y1 of chunk 0, one big
      * triangular GEMM that needs only chol(A), beside the chain of small launches that builds X and M */
     cudaStream_t side = NULL, side2 = NULL;
-    cudaEvent_t ev_fork = NULL, ev_rng = NULL, ev_a = NULL, ev_y1 = NULL;
-    int rng_in_flight = 0, y1_in_flight = 0, side2_used = 0;
+    cudaEvent_t ev_fork = NULL, ev_rng = NULL, ev_a = NULL, ev_y1 = NULL, ev_o = NULL;
+    int rng_in_flight = 0, y1_in_flight = 0, side2_used = 0, omega_forked = 0;
     htn_factor_t fa, fo, fm;
     memset(&fa, 0, sizeof(fa));
     memset(&fo, 0, sizeof(fo));
@@ -151,7 +153,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     if (a_id == NORMAL) HTN_TRY(htn_dalloc(ctx, (void**)&Y1, chunk * pp * 8));
     HTN_TRY(sp_streams_ready(ctx->device));
     side = ss.side, side2 = ss.side2;
-    ev_fork = ss.ev_fork, ev_rng = ss.ev_rng, ev_a = ss.ev_a, ev_y1 = ss.ev_y1;
+    ev_fork = ss.ev_fork, ev_rng = ss.ev_rng, ev_a = ss.ev_a, ev_y1 = ss.ev_y1, ev_o = ss.ev_o;
     /* Both runs of normals of chunk 0 are drawn up front (y1's then y2's, from the same stream).  If chol(A)
      * or chol(omega) fails the reference would have stopped earlier: only the single-draw entry cares (it
      * writes the generator back), and it re-checks the codes below before touching the caller's state. */
@@ -171,6 +173,16 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
     }
 
     /* ---- A, Omega: factor (dense) (mvn_rand_prec, src/htnorm_distributions.c:110-123) ---- */
+    if (a_id == NORMAL && o_id == NORMAL) { /* two dense factorisations: Omega's (the smaller one) runs beside A's */
+        htn_ctx_t c2 = *ctx;
+        c2.stream = side2;
+        HTN_CUDA(cudaEventRecord(ev_a, st));
+        HTN_CUDA(cudaStreamWaitEvent(side2, ev_a, 0));
+        side2_used = 1;
+        HTN_TRY(factor_dense(&c2, omega, n, lower_src, &FO, &fo, d_info + 1, 0));
+        HTN_CUDA(cudaEventRecord(ev_o, side2));
+        omega_forked = 1;
+    }
     if (a_id == NORMAL) {
         HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0, inverse_block_width(p, (size_t)2 * n_ + nsamples)));
         if (rng_in_flight) { /* L^T y1 = z for chunk 0 (see the loop below), started as soon as L_A^-1 exists */
@@ -186,7 +198,9 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
             y1_in_flight = 1;
         }
     }
-    if (o_id == NORMAL) /* Omega^-1 itself is formed from the whole inverse factor below */
+    if (omega_forked) /* Omega^-1 itself is formed from the whole inverse factor below */
+        HTN_CUDA(cudaStreamWaitEvent(st, ev_o, 0));
+    else if (o_id == NORMAL)
         HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1, 0));
     /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs) */
     if (a_id == IDENTITY) {
@@ -285,7 +299,7 @@ finish:
     if (d_info_out) rc = htnk_fill_i32(st, d_info_out, nsamples, *first_info);
 done:
     if (rng_in_flight && ev_rng) cudaStreamWaitEvent(st, ev_rng, 0); /* never free under the generator */
-    if (side2_used && (y1_in_flight || rc)) { /* ... nor under the early Y1 product, whatever state it was left in */
+    if (side2_used && (y1_in_flight || omega_forked || rc)) { /* ... nor under the early Y1 product, whatever state it was left in */
         if (cudaEventRecord(ev_y1, side2) != cudaSuccess || cudaStreamWaitEvent(st, ev_y1, 0) != cudaSuccess)
             cudaStreamSynchronize(side2);
     }
