@@ -219,11 +219,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    h.phase_timing(True)                    # on during the warm-up too: the phase-mark events are created there
     for i in range(args.warmup):
         step(i)
     barrier()
     # ---- timed: device-resident inputs ----
-    h.phase_timing(True)
+    h.phase_timing(True)                    # resets the marks
     launches0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gemm_ms = []

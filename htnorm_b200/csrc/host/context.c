@@ -135,7 +135,8 @@ void htn_dfree(htn_ctx_t* ctx, void* p)
 static int g_prof_on = 0;
 static cudaEvent_t g_prof_ev[HTN_PROF_SETS][HTN_PROF_SLOTS];
 static unsigned char g_prof_set[HTN_PROF_SETS][HTN_PROF_SLOTS];
-static int g_prof_created = 0, g_prof_dev = -1, g_prof_cur = -1;
+static unsigned char g_prof_have[HTN_PROF_SETS];
+static int g_prof_dev = -1, g_prof_cur = -1;
 
 void htn_phase_timing_enable(int on)
 {
@@ -147,11 +148,12 @@ void htn_phase_timing_enable(int on)
 void htn_prof_mark(htn_ctx_t* ctx, int slot)
 {
     if (!g_prof_on || slot < 0 || slot >= HTN_PROF_SLOTS) return;
-    if (g_prof_dev != ctx->device || !g_prof_created) { /* events belong to a device: (re)create them here */
+    if (g_prof_dev != ctx->device) { /* events belong to a device: forget the ones of the device used before */
         for (int s = 0; s < HTN_PROF_SETS; s++)
-            for (int i = 0; i < HTN_PROF_SLOTS; i++) cudaEventCreate(&g_prof_ev[s][i]);
+            if (g_prof_have[s])
+                for (int i = 0; i < HTN_PROF_SLOTS; i++) cudaEventDestroy(g_prof_ev[s][i]);
+        memset(g_prof_have, 0, sizeof(g_prof_have));
         memset(g_prof_set, 0, sizeof(g_prof_set));
-        g_prof_created = 1;
         g_prof_dev = ctx->device;
         g_prof_cur = -1;
     }
@@ -160,6 +162,10 @@ void htn_prof_mark(htn_ctx_t* ctx, int slot)
         memset(g_prof_set[g_prof_cur], 0, HTN_PROF_SLOTS);
     }
     if (g_prof_cur < 0) return;
+    if (!g_prof_have[g_prof_cur]) { /* a set's five events are created the first time the ring reaches it */
+        for (int i = 0; i < HTN_PROF_SLOTS; i++) cudaEventCreate(&g_prof_ev[g_prof_cur][i]);
+        g_prof_have[g_prof_cur] = 1;
+    }
     if (cudaEventRecord(g_prof_ev[g_prof_cur][slot], ctx->stream) == cudaSuccess) g_prof_set[g_prof_cur][slot] = 1;
 }
 
