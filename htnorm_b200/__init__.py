@@ -7,7 +7,8 @@ built library raises ImportError: there is no CPU fallback.
 """
 from ._lib import LIB_PATH, PUBLIC_SYMBOLS, lib  # noqa: F401
 from .api import (HTNGenerator, fp64_fma_peak_tflops, fp64_tensor_peak_tflops,  # noqa: F401
-                  hyperplane_truncated_mvnorm, hyperplane_truncated_mvnorm_batch, launch_count, phase_timing,
+                  hyperplane_truncated_mvnorm, hyperplane_truncated_mvnorm_batch, int_issue_peak_gops, launch_count,
+                  phase_timing,
                   raw_streams, standard_normals, structured_precision_mvnorm,
                   structured_precision_mvnorm_batch)
 from .dist import gather_rows, sample_sharded, shard_range, shard_sizes  # noqa: F401

@@ -12,8 +12,8 @@ PUBLIC_SYMBOLS = [
     "rng_free", "rng_pcg64_new", "rng_pcg64_new_seeded", "rng_xrs128p_new", "rng_xrs128p_new_seeded",
     "htn_batch_init", "htn_hyperplane_truncated_mvn_batch", "htn_structured_precision_mvn_batch",
     "htn_rng_raw_fill", "htn_std_normal_fill", "htn_device_count", "htn_last_error", "htn_launch_count",
-    "htn_version", "htn_fp64_tensor_peak_tflops", "htn_fp64_fma_peak_tflops", "htn_phase_timing_enable",
-    "htn_phase_timing_get",
+    "htn_version", "htn_fp64_tensor_peak_tflops", "htn_fp64_fma_peak_tflops", "htn_int_issue_peak_gops",
+    "htn_phase_timing_enable", "htn_phase_timing_get",
 ]
 
 HTNORM_ALLOC_ERROR = -100
@@ -61,6 +61,8 @@ def _load():
     lib.htn_fp64_tensor_peak_tflops.argtypes = [C.c_int, C.c_double]
     lib.htn_fp64_fma_peak_tflops.restype = C.c_double
     lib.htn_fp64_fma_peak_tflops.argtypes = [C.c_int, C.c_double]
+    lib.htn_int_issue_peak_gops.restype = C.c_double
+    lib.htn_int_issue_peak_gops.argtypes = [C.c_int, C.c_double]
     lib.rng_pcg64_new.restype = C.POINTER(RngT)
     lib.rng_pcg64_new_seeded.restype = C.POINTER(RngT)
     lib.rng_pcg64_new_seeded.argtypes = [C.c_uint64]
@@ -83,6 +85,17 @@ def _load():
 
 
 lib = _load()
+
+
+def load_dev():
+    """tests/ and tools/ only: libhtnorm_b200_dev.so = the product objects + csrc/host/debug.c (htn_dbg_*: GEMM,
+    Cholesky and solve hooks with host arrays, latency probes).  The product library does not export them."""
+    path = os.path.join(_HERE, "libhtnorm_b200_dev.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    dev = C.CDLL(path)
+    dev.htn_last_error.restype = C.c_char_p
+    return dev
 
 
 def last_error():

@@ -230,8 +230,13 @@ def _seeds_arg(seeds, nsamples, device):
     if seeds is None:
         return None
     if _is_torch(seeds):
+        import torch
         if device is None:
             raise TypeError("`seeds` is a CUDA tensor but the inputs are host arrays")
+        if not seeds.is_cuda or seeds.device.index != device:
+            raise ValueError("`seeds` must live on the same CUDA device as the inputs")
+        if seeds.dtype not in (torch.int64, torch.uint64):
+            raise TypeError("`seeds` must be a 64-bit integer tensor (int64 or uint64)")
         if seeds.numel() != nsamples:
             raise ValueError("`seeds` must have one entry per sample")
         return seeds.contiguous()
@@ -245,18 +250,64 @@ def _seeds_arg(seeds, nsamples, device):
 
 
 def _alloc(shape, device, dtype="f8"):
+    """Result buffers the wrapper allocates itself.  Device mode: `out` starts as NaN and `info` as 0, so rows a
+    failed factorisation leaves untouched are recognisable (the device path reports failures through `info` only)."""
     if device is None:
         return np.empty(shape, dtype=dtype)
     import torch
-    return torch.empty(shape, dtype={"f8": torch.float64, "i4": torch.int32}[dtype], device=f"cuda:{device}")
+    if dtype == "f8":
+        return torch.full(shape, float("nan"), dtype=torch.float64, device=f"cuda:{device}")
+    return torch.zeros(shape, dtype=torch.int32, device=f"cuda:{device}")
+
+
+def _check_result(x, name, shape, device, dtype):
+    """A caller-supplied `out` / `info` goes to the C ABI as a raw pointer: shape, dtype, contiguity and memory
+    space (host arrays with host inputs, CUDA tensors on the same device with device inputs) are checked here."""
+    want = {"f8": "float64", "i4": "int32"}[dtype]
+    if device is None:
+        if _is_torch(x):
+            raise TypeError(f"`{name}` is a torch tensor but the inputs are host arrays")
+        if not isinstance(x, np.ndarray):
+            raise TypeError(f"`{name}` must be a NumPy array")
+        if x.dtype != np.dtype(dtype) or tuple(x.shape) != tuple(shape) or not x.flags.c_contiguous:
+            raise ValueError(f"`{name}` must be a C-contiguous {want} array of shape {tuple(shape)}")
+        if not x.flags.writeable:
+            raise ValueError(f"`{name}` must be writeable")
+        return x
+    import torch
+    if not _is_torch(x) or not x.is_cuda:
+        raise TypeError(f"`{name}` must be a CUDA tensor when the inputs are CUDA tensors")
+    if x.device.index != device:
+        raise ValueError(f"`{name}` must live on the same CUDA device as the inputs")
+    if x.dtype != {"f8": torch.float64, "i4": torch.int32}[dtype]:
+        raise TypeError(f"`{name}` must be a {want} tensor")
+    if tuple(x.shape) != tuple(shape) or not x.is_contiguous():
+        raise ValueError(f"`{name}` must be a contiguous tensor of shape {tuple(shape)}")
+    return x
+
+
+def _finish(rc, info, device, raise_on_error, what):
+    """Return-code policy.  Host memory: the call is synchronous and returns the first non-zero per-sample code
+    (raised as the reference's ValueError unless raise_on_error is False).  Device memory: the call returns 0 once
+    enqueued and NEVER waits for the GPU by itself; the codes are in `info`.  With raise_on_error=True the wrapper
+    synchronises once and raises on the first non-zero code; the default (None) leaves the device path asynchronous."""
+    if raise_on_error is None:
+        raise_on_error = device is None
+    if rc < 0 or (rc > 0 and raise_on_error):
+        check(rc, what)
+    if device is not None and raise_on_error and info.numel():
+        bad = info[info != 0]               # synchronises
+        if bad.numel():
+            check(int(bad[0].item()), what)
 
 
 def hyperplane_truncated_mvnorm_batch(nsamples, mean, cov, g, r, diag=False, *, gen="pcg64", seeds=None,
                                       seed0=0, independent=False, out=None, info=None, flags=0, stream=None,
-                                      raise_on_error=True):
+                                      raise_on_error=None):
     """``nsamples`` draws in one call.  Sample i == the reference's single draw with a generator freshly
     seeded with ``seeds[i]`` (``seed0 + i`` when seeds is None).  ``independent``: inputs carry one problem
-    per sample (mean: B x k, cov: B x k x k, g: B x k2 x k, r: B x k2).  Returns ``(out, info)``."""
+    per sample (mean: B x k, cov: B x k x k, g: B x k2 x k, r: B x k2).  Returns ``(out, info)``.
+    ``raise_on_error``: None = raise for host arrays, stay asynchronous for CUDA tensors (see ``_finish``)."""
     device, (mean, cov, g, r) = _prep([mean, cov, g, r])
     k2, k = int(g.shape[-2]), int(g.shape[-1])
     lead = (nsamples,) if independent else ()
@@ -265,23 +316,20 @@ def hyperplane_truncated_mvnorm_batch(nsamples, mean, cov, g, r, diag=False, *, 
     if tuple(r.shape) != lead + (k2,) or tuple(g.shape) != lead + (k2, k):
         raise ValueError("`r` and `g` have incompatible shapes")
     seeds = _seeds_arg(seeds, nsamples, device)
-    if out is None:
-        out = _alloc((nsamples, k), device)
-    if info is None:
-        info = _alloc((nsamples,), device, "i4")
+    out = _alloc((nsamples, k), device) if out is None else _check_result(out, "out", (nsamples, k), device, "f8")
+    info = _alloc((nsamples,), device, "i4") if info is None else _check_result(info, "info", (nsamples,), device, "i4")
     conf = HtConfig()
     lib.init_ht_config(C.byref(conf), C.c_size_t(k2), C.c_size_t(k), _ptr(mean), _ptr(cov), _ptr(g), _ptr(r),
                        C.c_bool(bool(diag)))
     b = _batch(nsamples, gen, seeds, seed0, independent, device, flags, stream)
     rc = lib.htn_hyperplane_truncated_mvn_batch(C.byref(b), C.byref(conf), _ptr(out), _ptr(info))
-    if rc < 0 or (rc > 0 and raise_on_error):
-        check(rc, "hyperplane_truncated_mvnorm_batch")
+    _finish(rc, info, device, raise_on_error, "hyperplane_truncated_mvnorm_batch")
     return out, info
 
 
 def structured_precision_mvnorm_batch(nsamples, mean, a, phi, omega, mean_structured=False, a_type=0,
                                       o_type=0, *, gen="pcg64", seeds=None, seed0=0, out=None, info=None,
-                                      flags=0, stream=None, raise_on_error=True):
+                                      flags=0, stream=None, raise_on_error=None):
     """``nsamples`` draws from N(mean, (a + phi^T omega phi)^-1) sharing a, phi, omega."""
     device, (mean, a, phi, omega) = _prep([mean, a, phi, omega])
     n, p = int(phi.shape[0]), int(phi.shape[1])
@@ -291,17 +339,14 @@ def structured_precision_mvnorm_batch(nsamples, mean, a, phi, omega, mean_struct
     if tuple(mean.shape) != ((n,) if mean_structured else (p,)):
         raise ValueError("`mean` has the wrong length")
     seeds = _seeds_arg(seeds, nsamples, device)
-    if out is None:
-        out = _alloc((nsamples, p), device)
-    if info is None:
-        info = _alloc((nsamples,), device, "i4")
+    out = _alloc((nsamples, p), device) if out is None else _check_result(out, "out", (nsamples, p), device, "f8")
+    info = _alloc((nsamples,), device, "i4") if info is None else _check_result(info, "info", (nsamples,), device, "i4")
     conf = SpConfig()
     lib.init_sp_config(C.byref(conf), C.c_size_t(n), C.c_size_t(p), _ptr(mean), _ptr(a), _ptr(phi), _ptr(omega),
                        C.c_bool(bool(mean_structured)), C.c_int(a_type), C.c_int(o_type))
     b = _batch(nsamples, gen, seeds, seed0, False, device, flags, stream)
     rc = lib.htn_structured_precision_mvn_batch(C.byref(b), C.byref(conf), _ptr(out), _ptr(info))
-    if rc < 0 or (rc > 0 and raise_on_error):
-        check(rc, "structured_precision_mvnorm_batch")
+    _finish(rc, info, device, raise_on_error, "structured_precision_mvnorm_batch")
     return out, info
 
 
@@ -334,6 +379,11 @@ def fp64_tensor_peak_tflops(device=-1, ms=50.0):
 
 def fp64_fma_peak_tflops(device=-1, ms=50.0):
     return float(lib.htn_fp64_fma_peak_tflops(device, ms))
+
+
+def int_issue_peak_gops(device=-1, ms=50.0):
+    """integer issue ceiling (giga warp-instructions / s) with the generators' instruction mix"""
+    return float(lib.htn_int_issue_peak_gops(device, ms))
 
 
 def phase_timing(enable=None):

@@ -286,6 +286,9 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
                             const double* B, size_t ldb, double beta, double* C, size_t ldc,
                             const double* bias, int mode, int ktri, int kext0, int bn)
 {
+    // the one-shot guard belongs to THIS call whatever happens next: consume it before any early return
+    const int* const skip = g_next_skip;
+    g_next_skip = nullptr;
     if (M <= 0 || N <= 0) return 0;
     if (K < 0) return -202;
     if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -319,8 +322,7 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     p.A = A; p.B = B; p.C = C; p.bias = bias;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
-    p.skip = g_next_skip;
-    g_next_skip = nullptr;
+    p.skip = skip;
     p.tiles_m = tiles_m;
     const int bn_cols = bn >= 128 ? 128 : (bn >= 64 ? 64 : bn);
     p.tiles_n = (N + bn_cols - 1) / bn_cols;

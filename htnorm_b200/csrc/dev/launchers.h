@@ -151,6 +151,8 @@ int htnk_ht_small_batched(cudaStream_t st, size_t nproblems, int k, int k2, cons
 /* ---- peak microbenchmarks (peak.cu) ---- */
 double htnk_dmma_peak_tflops(cudaStream_t st, double ms);
 double htnk_dfma_peak_tflops(cudaStream_t st, double ms);
+/* integer issue ceiling with the generator's instruction mix, giga warp-instructions per second */
+double htnk_int_issue_peak_gops(cudaStream_t st, double ms);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,27 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters,
     if (s == 123.456) sink[0] = s;
 }
 
+// Integer-issue peak: the generator's own instruction mix - eight independent PCG32 streams per thread (64-bit LCG step
+// = IMAD.WIDE + 2 IMAD, the XSH-RR output = shifts, LOP3, SHF), no memory traffic.  Reported as warp-instructions per
+// second from the EXECUTED instruction count of the unrolled loop body (counted from SASS once: kIntInstrPerIter), i.e. the
+// issue-slot ceiling the ziggurat kernel is bound by (profiles/: normal_fill is issue-bound, not HBM-bound).
+__global__ void __launch_bounds__(256) int_issue_peak_kernel(double* sink, int iters, double seed)
+{
+    unsigned long long st[8], acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = (unsigned long long)(seed * 1e6) + threadIdx.x * 977u + i * 7919u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned long long old = st[i];
+            st[i] = old * 6364136223846793005ULL + (2 * i + 1);
+            const unsigned xs = (unsigned)(((old >> 18) ^ old) >> 27);
+            acc += __funnelshift_r(xs, xs, (unsigned)(old >> 59));
+        }
+    }
+    if (acc == 0x123456789abcdefULL) sink[0] = (double)acc;
+}
+
 template <typename K>
 double time_kernel(cudaStream_t st, K kern, double flops_per_thread_iter_x32, double ms_target)
 {
@@ -95,6 +116,18 @@ extern "C" double htnk_dfma_peak_tflops(cudaStream_t st, double ms)
 {
     // per warp per iteration: 32 lanes * 8 FMA * 2 flops
     return time_kernel(st, dfma_peak_kernel, 32.0 * 8.0 * 2.0, ms);
+}
+
+// giga warp-instructions per second over all SMs.  kIntInstrPerIter: SASS instructions of one loop iteration of
+// int_issue_peak_kernel (8 streams x [IMAD.WIDE.U32, 2 IMAD, IMAD.IADD, 2-3 SHF, LOP3, SHF.R.W, IADD3 + carry] + register moves + loop overhead),
+// counted with `cuobjdump -sass` (tools/count_int_peak_sass.py re-derives it; the count is asserted there).
+#ifndef HTN_INT_INSTR_PER_ITER
+#define HTN_INT_INSTR_PER_ITER 103.0
+#endif
+extern "C" double htnk_int_issue_peak_gops(cudaStream_t st, double ms)
+{
+    // time_kernel returns (grid * 8 warps * iters * x) / time / 1e12: with x = instructions per iteration * 1e3 -> G/s
+    return time_kernel(st, int_issue_peak_kernel, HTN_INT_INSTR_PER_ITER * 1e3, ms);
 }
 
 // ---- latency probes (one warp / one CTA): calibrates the cycle models in DESIGN.md ----

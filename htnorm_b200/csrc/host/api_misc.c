@@ -89,10 +89,12 @@ static double peak(int device, double ms, int tensor)
 {
     htn_ctx_t ctx;
     if (htn_ctx_begin(&ctx, device, NULL, 1)) return -1.0;
-    double v = tensor ? htnk_dmma_peak_tflops(ctx.stream, ms) : htnk_dfma_peak_tflops(ctx.stream, ms);
+    double v = tensor == 2 ? htnk_int_issue_peak_gops(ctx.stream, ms)
+                           : (tensor ? htnk_dmma_peak_tflops(ctx.stream, ms) : htnk_dfma_peak_tflops(ctx.stream, ms));
     htn_ctx_end(&ctx, 1);
     return v;
 }
+double htn_int_issue_peak_gops(int device, double ms) { return peak(device, ms > 0 ? ms : 50.0, 2); }
 
 double htn_fp64_tensor_peak_tflops(int device, double ms) { return peak(device, ms > 0 ? ms : 50.0, 1); }
 double htn_fp64_fma_peak_tflops(int device, double ms) { return peak(device, ms > 0 ? ms : 50.0, 0); }

@@ -24,7 +24,14 @@ size_t htn_chunk_budget(void)
     if (e && atoll(e) >= 4096) return (size_t)atoll(e);
     return (size_t)3 << 30;
 }
-const char* htn_version(void) { return "htnorm-b200 0.1 (sm_100a)"; }
+const char* htn_version(void)
+{
+#ifdef HTNORM_COLMAJOR
+    return "htnorm-b200 0.2 (sm_100a, column-major build)";
+#else
+    return "htnorm-b200 0.2 (sm_100a)";
+#endif
+}
 unsigned long long htn_launch_count(void) { return htnk_launch_count(); }
 
 int htn_device_count(void)
@@ -68,12 +75,12 @@ int htn_ctx_begin(htn_ctx_t* ctx, int device, void* stream, int host_mode)
         return HTN_E_ARG;
     }
     if (ctx->device != ctx->prev_device) HTN_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->device < 64 && !pool_configured[ctx->device]) {
+    if (ctx->device < 64 && !__atomic_load_n(&pool_configured[ctx->device], __ATOMIC_ACQUIRE)) {
         cudaMemPool_t pool;
         unsigned long long keep = ~0ULL; /* never trim: workspaces are reused call after call */
         HTN_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
         HTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_configured[ctx->device] = 1;
+        __atomic_store_n(&pool_configured[ctx->device], 1, __ATOMIC_RELEASE); /* idempotent: a racing thread repeats it */
     }
     if (host_mode) {
         /* the library's own stream for host-memory calls: one per host thread and device, created once and kept
@@ -129,14 +136,17 @@ void htn_dfree(htn_ctx_t* ctx, void* p)
 /* ---- optional phase timing (CUDA events on the caller's stream; off by default) ----
  * Every call of the shared-covariance hyperplane path records one SET of marks; up to HTN_PROF_SETS sets are
  * kept since the facility was enabled, so a benchmark loop can run without synchronising per step and read
- * the per-phase averages afterwards. */
+ * the per-phase averages afterwards.
+ * The state is PER HOST THREAD (thread-local): a thread sees only the marks of its own calls, enabling the
+ * facility in one thread neither slows nor races with sampler calls of another - the library keeps no mutable
+ * state that is shared between threads (SURVEY 8b threading contract). */
 #define HTN_PROF_SLOTS 5
 #define HTN_PROF_SETS 256
-static int g_prof_on = 0;
-static cudaEvent_t g_prof_ev[HTN_PROF_SETS][HTN_PROF_SLOTS];
-static unsigned char g_prof_set[HTN_PROF_SETS][HTN_PROF_SLOTS];
-static unsigned char g_prof_have[HTN_PROF_SETS];
-static int g_prof_dev = -1, g_prof_cur = -1;
+static _Thread_local int g_prof_on = 0;
+static _Thread_local cudaEvent_t g_prof_ev[HTN_PROF_SETS][HTN_PROF_SLOTS];
+static _Thread_local unsigned char g_prof_set[HTN_PROF_SETS][HTN_PROF_SLOTS];
+static _Thread_local unsigned char g_prof_have[HTN_PROF_SETS];
+static _Thread_local int g_prof_dev = -1, g_prof_cur = -1;
 
 void htn_phase_timing_enable(int on)
 {

@@ -14,6 +14,15 @@
 
 #define HTN_NB 128 /* panel width of the blocked factorisation = N tile of the GEMM */
 
+/* Layout default of THIS build of the library.  The reference selects the layout at compile time
+ * (src/htnorm.c:5-10, -DHTNORM_COLMAJOR in src/Makevars:1 for the R binding); libhtnorm_b200_colmajor.so is this
+ * library compiled the same way: every entry point then behaves as if HTN_FLAG_COLMAJOR were set. */
+#ifdef HTNORM_COLMAJOR
+#define HTN_DEFAULT_FLAGS HTN_FLAG_COLMAJOR
+#else
+#define HTN_DEFAULT_FLAGS 0u
+#endif
+
 typedef struct {
     int device;
     int prev_device;
@@ -120,7 +129,7 @@ void htn_foreign_draw(rng_t* rng, size_t n, double* z);
 int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int independent, unsigned flags,
                   size_t k2, size_t k, const double* mean, const double* cov, const double* g,
                   const double* r, int diag, double* out, int* d_info_out, int* first_info);
-int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info);
+int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, unsigned flags, int* info);
 int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsigned flags, size_t n, size_t p,
                   const double* mean, const double* a, const double* phi, const double* omega,
                   int struct_mean, int a_id, int o_id, double* out, int* d_info_out, int* first_info);

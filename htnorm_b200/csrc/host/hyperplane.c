@@ -84,6 +84,12 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     cudaEvent_t ev_sym = NULL, ev_sbranch = NULL;
     cudaEvent_t ev_fork = NULL, ev_rng[2] = {NULL, NULL}, ev_gemm[2] = {NULL, NULL}, ev_sub = NULL;
     int rng_pending = -1; /* buffer whose generator launch the main stream has not yet waited for */
+    int side2_used = 0, copy_used = 0;
+    /* A caller's own generator object (single draw, `states`) must be left untouched when chol(cov) fails, as the
+     * reference leaves it (src/htnorm_distributions.c:77-79 returns before any draw): its normals are drawn only
+     * after the factorisation's code is known.  Seeded batch streams have no caller-visible state and are drawn
+     * up front, beside the factorisation. */
+    const int defer_draw = s->states != NULL;
     htn_factor_t fa, fs;
     memset(&fa, 0, sizeof(fa));
     memset(&fs, 0, sizeof(fs));
@@ -163,9 +169,11 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     htn_prof_mark(ctx, 0);
     HTN_CUDA(cudaEventRecord(ev_fork, st));
     HTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    HTN_TRY(ht_draw_chunk(side, s, 0, nsamples < chunk ? nsamples : chunk, k, ldz, Z[0]));
-    HTN_CUDA(cudaEventRecord(ev_rng[0], side));
-    rng_pending = 0;
+    if (!defer_draw) {
+        HTN_TRY(ht_draw_chunk(side, s, 0, nsamples < chunk ? nsamples : chunk, k, ldz, Z[0]));
+        HTN_CUDA(cudaEventRecord(ev_rng[0], side));
+        rng_pending = 0;
+    }
 
     /* ---- once per batch: everything that depends on (cov, G, r, mean) only ---- */
     /* symmetric copy of cov (as the reference's uplo='L' calls see it) and its lower triangle in F */
@@ -178,6 +186,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     /* ---- branch on side2 (needs cov and G only, runs under the factorisation): cov G^T, G cov G^T and
      * its Cholesky, r - G mean ---- */
     HTN_CUDA(cudaStreamWaitEvent(side2, ev_sym, 0));
+    side2_used = 1;
     /* cov G^T -> F[:, kp : kp+k2]   (dsymm, src/htnorm.c:154; dsymv :73).  Disjoint from L's columns. */
     HTN_TRY(htnk_gemm_tn(side2, k, k2, k, 1.0, Sfull, kp, Gp, kp, 0.0, F + kp, ldz, NULL, HTNK_GEMM_FULL, 0, 0, 0));
     HTN_TRY(htnk_transpose(side2, F + kp, ldz, k, k2, CG, kp));
@@ -220,7 +229,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     }
 
     int h_info[2] = {0, 0};
-    const int async = k2 <= ALPHA_K2_MAX && ctx->async_info_out != NULL;
+    const int async = !defer_draw && k2 <= ALPHA_K2_MAX && ctx->async_info_out != NULL;
     if (!async) {
         HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
         HTN_CUDA(cudaStreamSynchronize(st));
@@ -231,6 +240,10 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
         goto done;
     }
     *first_info = h_info[1]; /* G cov G^T not PD: the unprojected y is returned (src/htnorm.c:169-177) */
+    if (defer_draw) { /* chol(cov) succeeded (the code was read above: a `states` call is never asynchronous) */
+        HTN_TRY(ht_draw_chunk(st, s, 0, nsamples < chunk ? nsamples : chunk, k, ldz, Z[0]));
+        HTN_CUDA(cudaEventRecord(ev_rng[0], st));
+    }
     htn_prof_mark(ctx, 1);
 
     /* ---- per chunk of samples ---- */
@@ -280,6 +293,7 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
             if (sink) { /* ship this sub-chunk home while the next one is being computed */
                 HTN_CUDA(cudaEventRecord(ev_sub, st));
                 HTN_CUDA(cudaStreamWaitEvent(copy_st, ev_sub, 0));
+                copy_used = 1;
                 HTN_CUDA(cudaMemcpyAsync(sink + (b0 + s0) * (size_t)k, outs, sn * (size_t)k * 8, cudaMemcpyDeviceToHost,
                                          copy_st));
             }
@@ -288,20 +302,27 @@ static int ht_shared_dense(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsampl
     }
     if (sink) {
         HTN_CUDA(cudaStreamSynchronize(copy_st));
+        copy_used = 0;
         ctx->host_sink_used = 1;
     }
     if (async) HTN_TRY(htnk_fill_info(st, ctx->async_info_out, nsamples, d_info));
 done:
-    /* never free a buffer the side stream may still be writing */
-    if (rng_pending >= 0 && ev_rng[rng_pending]) cudaStreamWaitEvent(st, ev_rng[rng_pending], 0);
+    /* Never free a buffer another stream may still be using.  The frees below are ordered on the main stream, so
+     * whatever is queued on the side streams - in whatever state an error exit left them - is joined first: a FRESH
+     * event per stream (a stale one from an earlier call would be a no-op), a full synchronisation if that fails. */
+    if (rng_pending >= 0 && ev_rng[rng_pending] &&
+        (cudaEventRecord(ev_rng[rng_pending], side) != cudaSuccess ||
+         cudaStreamWaitEvent(st, ev_rng[rng_pending], 0) != cudaSuccess))
+        cudaStreamSynchronize(side);
+    if (side2_used && (cudaEventRecord(ev_sbranch, side2) != cudaSuccess ||
+                       cudaStreamWaitEvent(st, ev_sbranch, 0) != cudaSuccess))
+        cudaStreamSynchronize(side2);
+    if (copy_used) cudaStreamSynchronize(copy_st); /* error exit with device -> host copies of d_out in flight */
     htn_factor_free(ctx, &fa);
     htn_factor_free(ctx, &fs);
     htn_dfree(ctx, Z[0]);
     htn_dfree(ctx, Z[1]);
     htn_dfree(ctx, D);
-    if (ev_sbranch) { /* the branch may still be running if we bailed out early */
-        cudaStreamWaitEvent(st, ev_sbranch, 0);
-    }
     /* (streams and events belong to the per-thread cache) */
     htn_dfree(ctx, c0);
     htn_dfree(ctx, Sm);
@@ -448,7 +469,7 @@ done:
 }
 
 /* LAPACK status of chol(cov) alone (used to decide whether a foreign generator may be advanced) */
-int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info)
+int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, unsigned flags, int* info)
 {
     int rc = 0;
     const size_t kp = htn_round_up((size_t)k, 16);
@@ -460,7 +481,7 @@ int htn_ht_cov_info(htn_ctx_t* ctx, int k, const double* cov, int* info)
     HTN_TRY(htn_dalloc(ctx, (void**)&d_info, sizeof(int)));
     HTN_CUDA(cudaMemsetAsync(F, 0, (size_t)k * kp * 8, ctx->stream));
     HTN_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-    HTN_TRY(htnk_sym_expand(ctx->stream, cov, (size_t)k, k, 0, NULL, 0, F, kp));
+    HTN_TRY(htnk_sym_expand(ctx->stream, cov, (size_t)k, k, (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, NULL, 0, F, kp));
     HTN_TRY(htn_factor_init(ctx, &fa, F, kp, k, 0));
     HTN_TRY(htn_potrf(ctx, &fa, d_info));
     HTN_CUDA(cudaMemcpyAsync(info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -491,6 +512,7 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     }
     const size_t B = b->nsamples, k = conf->gncol, k2 = conf->gnrow;
     const size_t np = b->independent ? B : 1;
+    const unsigned flags = b->flags | HTN_DEFAULT_FLAGS;
     htn_ctx_t ctx;
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, b->mem == HTN_MEM_HOST);
     if (rc) return rc;
@@ -499,7 +521,7 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
     if (b->mem == HTN_MEM_DEVICE) {
         /* asynchronous: nothing in this branch waits for the device (shared dense inputs, k2 <= 16, info given) */
         ctx.async_info_out = (!b->independent && !conf->diag && k2 <= ALPHA_K2_MAX) ? info : NULL;
-        rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
+        rc = htn_ht_device(&ctx, &s, B, b->independent, flags, k2, k, conf->mean, conf->cov, conf->g, conf->r,
                            conf->diag, out, info, &first);
         int rc2 = htn_ctx_end(&ctx, 0);
         return rc ? rc : rc2;
@@ -527,7 +549,7 @@ int htn_hyperplane_truncated_mvn_batch(const htn_batch_t* b, const ht_config_t* 
         HTN_CUDA(cudaMemcpyAsync(d_out, out, B * k * 8, cudaMemcpyHostToDevice, ctx.stream));
     ctx.host_sink = (!b->independent && !conf->diag) ? out : NULL;
     ctx.host_sink_used = 0;
-    rc = htn_ht_device(&ctx, &s, B, b->independent, b->flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
+    rc = htn_ht_device(&ctx, &s, B, b->independent, flags, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
                        d_info, &first);
     ctx.host_sink = NULL;
     if (rc) goto done;
@@ -586,12 +608,13 @@ int htn_hyperplane_truncated_mvn(rng_t* rng, const ht_config_t* conf, double* HT
     if (kind >= 0) {
         HTN_TRY(upload(&ctx, &d_state, h_state, sizeof(h_state)));
         htn_streams_t s = {kind, NULL, 0, (uint64_t*)d_state, NULL};
-        HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, 0, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL, &first));
+        HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, HTN_DEFAULT_FLAGS, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL,
+                              &first));
     } else {
         /* foreign generator: its callbacks run on the host.  The reference draws only after a
          * successful factorisation (src/htnorm_distributions.c:78), so factorise first with no draw ... */
         if (!conf->diag) {
-            HTN_TRY(htn_ht_cov_info(&ctx, (int)k, d_cov, &first));
+            HTN_TRY(htn_ht_cov_info(&ctx, (int)k, d_cov, HTN_DEFAULT_FLAGS, &first));
         }
         if (first == 0) { /* ... then draw k normals through the callbacks and run the device path on them */
             h_z = malloc(k * sizeof(double));
@@ -599,8 +622,8 @@ int htn_hyperplane_truncated_mvn(rng_t* rng, const ht_config_t* conf, double* HT
             htn_foreign_draw(rng, k, h_z);
             HTN_TRY(upload(&ctx, &d_z, h_z, k * 8));
             htn_streams_t s = {0, NULL, 0, NULL, (const double*)d_z};
-            HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, 0, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out, NULL,
-                                  &first));
+            HTN_TRY(htn_ht_device(&ctx, &s, 1, 0, HTN_DEFAULT_FLAGS, k2, k, d_mean, d_cov, d_g, d_r, conf->diag, d_out,
+                                  NULL, &first));
         }
     }
     HTN_CUDA(cudaMemcpyAsync(out, d_out, k * 8, cudaMemcpyDeviceToHost, ctx.stream));

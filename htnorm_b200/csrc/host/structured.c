@@ -368,12 +368,12 @@ static int sp_host(const sp_config_t* conf, int gen, const uint64_t* seeds, uint
         /* foreign generator: the reference draws y1's normals only after chol(A) succeeded and
          * y2's only after chol(omega) did (src/htnorm.c:245-246): check both, then draw on the host */
         int ia = 0, io = 0;
-        if (conf->a_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)p, d_a, &ia));
+        if (conf->a_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)p, d_a, flags, &ia));
         if (ia) { first = ia; goto done; }
         h_z = malloc((p + n) * sizeof(double));
         if (!h_z) { rc = HTNORM_ALLOC_ERROR; goto done; }
         htn_foreign_draw(foreign, p, h_z);
-        if (conf->o_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)n, d_om, &io));
+        if (conf->o_id == NORMAL) HTN_TRY(htn_ht_cov_info(&ctx, (int)n, d_om, flags, &io));
         if (io) { first = io; goto done; }
         htn_foreign_draw(foreign, n, h_z + p);
         HTN_TRY(upload(&ctx, &d_z, h_z, (p + n) * 8));
@@ -417,13 +417,14 @@ int htn_structured_precision_mvn_batch(const htn_batch_t* b, const sp_config_t* 
         return HTN_E_ARG;
     }
     if (b->mem == HTN_MEM_HOST)
-        return sp_host(conf, (int)b->gen, b->seeds, b->seed0, NULL, b->nsamples, b->flags, b->device, out, info, NULL);
+        return sp_host(conf, (int)b->gen, b->seeds, b->seed0, NULL, b->nsamples, b->flags | HTN_DEFAULT_FLAGS, b->device, out,
+                       info, NULL);
     htn_ctx_t ctx;
     int rc = htn_ctx_begin(&ctx, b->device, b->stream, 0);
     if (rc) return rc;
     int first = 0;
     htn_streams_t s = {(int)b->gen, b->seeds, b->seed0, NULL, NULL};
-    rc = htn_sp_device(&ctx, &s, b->nsamples, b->flags, conf->pnrow, conf->pncol, conf->mean, conf->a, conf->phi,
+    rc = htn_sp_device(&ctx, &s, b->nsamples, b->flags | HTN_DEFAULT_FLAGS, conf->pnrow, conf->pncol, conf->mean, conf->a, conf->phi,
                        conf->omega, conf->struct_mean, conf->a_id, conf->o_id, out, info, &first);
     int rc2 = htn_ctx_end(&ctx, 0);
     return rc ? rc : rc2;
@@ -437,10 +438,10 @@ int htn_structured_precision_mvn(rng_t* rng, const sp_config_t* conf, double* HT
     }
     const int kind = htn_rng_kind(rng);
     if (kind < 0) /* foreign generator: host draws through its callbacks, device algebra */
-        return sp_host(conf, 0, NULL, 0, NULL, 1, 0, -1, out, NULL, rng);
+        return sp_host(conf, 0, NULL, 0, NULL, 1, HTN_DEFAULT_FLAGS, -1, out, NULL, rng);
     uint64_t h_state[4] = {0, 0, 0, 0};
     memcpy(h_state, rng->base, kind == HTN_GEN_PCG64 ? 32 : 16);
-    int rc = sp_host(conf, kind, NULL, 0, h_state, 1, 0, -1, out, NULL, NULL);
+    int rc = sp_host(conf, kind, NULL, 0, h_state, 1, HTN_DEFAULT_FLAGS, -1, out, NULL, NULL);
     if (rc >= 0 || rc == HTNORM_ALLOC_ERROR) memcpy(rng->base, h_state, kind == HTN_GEN_PCG64 ? 32 : 16);
     return rc;
 }

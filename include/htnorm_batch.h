@@ -100,6 +100,10 @@ int htn_phase_timing_get(double* ms, int n);
 double htn_fp64_tensor_peak_tflops(int device, double ms);
 /* Same for plain DFMA (FP64 FMA pipe), for comparison. */
 double htn_fp64_fma_peak_tflops(int device, double ms);
+/* Measured integer ISSUE throughput of `device` with the bit generators' own instruction mix (64-bit LCG steps,
+ * xorshift / rotate outputs, no memory traffic), in giga warp-instructions per second over all SMs.  The ziggurat
+ * generator is bound by issue slots, not by HBM: this is the denominator of its second roofline. */
+double htn_int_issue_peak_gops(int device, double ms);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,8 @@ def test_ziggurat_large_property(h):
 # ------------------------------------------------------------------ dense building blocks
 
 def _dbg(h):
-    lib = h.lib
+    """kernel-level hooks (htn_dbg_*) live in the DEV build of the library only; the product does not export them"""
+    lib = _dbg.lib = getattr(_dbg, "lib", None) or h._lib.load_dev()
     lib.htn_dbg_gemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
                                     C.c_size_t, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int]
@@ -84,7 +85,7 @@ def test_gemm_tn(h, M, N, K, bn):
         want[:, :N] = 0.5 * A[:, :K] @ B[:, :K].T + 2.0 * Cm[:, :N] + bias
         rc = lib.htn_dbg_gemm_tn(M, N, K, 0.5, A.ctypes.data, lda, B.ctypes.data, ldb, 2.0, Cm.ctypes.data, ldc,
                                  bias.ctypes.data, 0, 0, 0, bn)
-        assert rc == 0, h._lib.last_error()
+        assert rc == 0, lib.htn_last_error().decode()
         assert np.abs(Cm - want).max() < 1e-11 * max(1, K)
 
 
@@ -121,7 +122,7 @@ def test_potrf_and_solves(h, oracle, n):
     for op in (1, 2, 3):
         x = x0.copy()
         rc = lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, op, 5, x.ctypes.data)
-        assert rc == 0, h._lib.last_error()
+        assert rc == 0, lib.htn_last_error().decode()
         assert np.abs(l - want_l).max() < 1e-12
         linv = np.linalg.inv(want_l)
         want = {1: x0 @ linv.T, 2: x0 @ linv, 3: x0 @ linv.T @ linv}[op]
@@ -432,7 +433,7 @@ def test_potrf_wide_panels(h, n):
     x0 = rng.standard_normal((3, n))
     x = x0.copy()
     rc = lib.htn_dbg_potrf_solve(n, a.ctypes.data, l.ctypes.data, 3, 3, x.ctypes.data)
-    assert rc == 0, h._lib.last_error()
+    assert rc == 0, lib.htn_last_error().decode()
     assert np.abs(l @ l.T - a).max() < 2e-11
     assert np.abs(np.triu(l, 1)).max() == 0.0
     assert np.abs(x @ a - x0).max() < 1e-9          # x = x0 A^-1
@@ -694,3 +695,43 @@ def test_full_size_structured_spot_check(h, oracle):
     xo = oracle.structured("pcg64", len(spot), mu, a, phi, om, False, 0, 1,
                            seeds=(12345 + spot).astype(np.uint64))[0]
     assert rel_err(x[spot], xo) < REL_TOL
+
+
+def test_failed_cov_leaves_the_callers_generator_untouched(h, oracle):
+    """the reference draws nothing when chol(cov) fails (src/htnorm_distributions.c:77-79), so the
+    caller's generator must come back unchanged and its NEXT draw must be the stream's first."""
+    c = cases.ht_case("k4_dense_64")
+    for gen in ("pcg64", "xrs128p"):
+        g = h.HTNGenerator(77, gen)
+        before = g.state
+        bad = c["cov"].copy()
+        bad[10, 10] = -1.0
+        out = np.full(64, 7.0)
+        with pytest.raises(ValueError, match="leading minor"):
+            g.hyperplane_truncated_mvnorm(c["mean"], bad, c["g"], c["r"], out=out)
+        assert g.state == before and (out == 7.0).all()
+        x = g.hyperplane_truncated_mvnorm(c["mean"], c["cov"], c["g"], c["r"])
+        xo, _, _ = oracle.hyperplane(gen, 1, c["mean"], c["cov"], c["g"], c["r"], seed0=77)
+        assert rel_err(x[None], xo) < REL_TOL
+        assert g.state != before
+
+
+def test_device_mode_raise_on_error_and_result_validation(h):
+    """with CUDA tensors the call returns 0 once enqueued; raise_on_error=True synchronises once and
+    raises the reference's ValueError; buffers the wrapper allocates start as NaN / 0."""
+    import torch
+    dev = "cuda:0"
+    k = 40
+    z = lambda *s_: torch.zeros(*s_, dtype=torch.float64, device=dev)
+    ones = torch.ones(2, k, dtype=torch.float64, device=dev)
+    with pytest.raises(ValueError, match="leading minor"):
+        h.hyperplane_truncated_mvnorm_batch(3, z(k), z(k, k), ones, z(2), raise_on_error=True)
+    x, info = h.hyperplane_truncated_mvnorm_batch(3, z(k), z(k, k), ones, z(2))      # default: asynchronous, no raise
+    torch.cuda.synchronize()
+    assert info.cpu().tolist() == [1, 1, 1] and bool(torch.isnan(x).all())
+    with pytest.raises(TypeError):
+        h.hyperplane_truncated_mvnorm_batch(3, z(k), torch.eye(k, dtype=torch.float64, device=dev), ones, z(2),
+                                            out=np.empty((3, k)))
+    with pytest.raises(TypeError):
+        h.hyperplane_truncated_mvnorm_batch(3, z(k), torch.eye(k, dtype=torch.float64, device=dev), ones, z(2),
+                                            seeds=torch.zeros(3, dtype=torch.int32, device=dev))

@@ -165,3 +165,33 @@ def test_sharded_sampling_is_independent_of_world_size_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_batch_result_buffers_are_validated(h):
+    """`out` / `info` reach the C ABI as raw pointers, so shape, dtype, contiguity and memory space are
+    checked in the wrapper - before any device work (this runs without a GPU)."""
+    k = 8
+    args = (np.zeros(k), np.eye(k), np.ones((1, k)), np.zeros(1))
+    for bad in (np.empty((4, k), dtype=np.float32), np.empty((3, k)), np.empty((4, k + 1)),
+                np.empty((k, 4)).T, np.empty((4, 2 * k))[:, ::2]):
+        with pytest.raises(ValueError, match="`out`"):
+            h.hyperplane_truncated_mvnorm_batch(4, *args, out=bad)
+    with pytest.raises(ValueError, match="`info`"):
+        h.hyperplane_truncated_mvnorm_batch(4, *args, info=np.empty(4, dtype=np.int64))
+    with pytest.raises(ValueError, match="`info`"):
+        h.structured_precision_mvnorm_batch(4, np.zeros(k), np.eye(k), np.ones((2, k)), np.eye(2),
+                                            info=np.empty(3, dtype=np.int32))
+    with pytest.raises(TypeError):
+        h.hyperplane_truncated_mvnorm_batch(4, *args, out=[[0.0] * k] * 4)
+    with pytest.raises(ValueError, match="seeds"):
+        h.hyperplane_truncated_mvnorm_batch(4, *args, seeds=np.arange(3, dtype=np.uint64))
+
+
+def test_product_library_exports_only_the_declared_boundary(h):
+    """W7 / ADVICE r1: the release library exports the symbols include/*.h declares and nothing else; the kernel-level
+    test hooks (htn_dbg_*) and the host layer's internals live in libhtnorm_b200_dev.so only."""
+    out = subprocess.run(["nm", "-D", "--defined-only", h.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split()[1] in "TDBR"}
+    assert exported == declared_functions(), exported ^ declared_functions()
+    dev = h._lib.load_dev()
+    assert hasattr(dev, "htn_dbg_gemm_tn") and not hasattr(h.lib, "htn_dbg_gemm_tn")
