@@ -39,50 +39,103 @@ def make_inputs(np):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), time-stamped by arrival so that the
-    samples that fall inside the timed region can be picked out."""
+    """SM clock and throttle reasons DURING the timed region.  NVML (nvidia_ml_py) polled every 2 ms from a thread -
+    the timed region of the default run is a few tens of milliseconds, shorter than one period of `nvidia-smi -lms` -
+    with `nvidia-smi -lms 50` (B200_PROFILING.md recipe) as the fallback.  Samples are time-stamped so that those
+    inside [t0, t1] can be picked out."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.nvml, self.stop_flag, self.src = gpu, [], None, None, False, None
+        self.sm_max = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.src = pynvml, "nvml, 2 ms period"
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:       # noqa: BLE001  (no NVML: fall back to the CLI)
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self._physical_index())], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi -lms 50"
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:   # noqa: BLE001  (older binding name)
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), ("nvml", sm, mask)))
+            except Exception:       # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    @property
+    def active(self):
+        return self.nvml is not None or self.proc is not None
+
     def count_since(self, t0):
         return sum(1 for t, _ in self.rows if t >= t0)
 
     def stop(self, t0, t1, note=None):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) > 8]
-
-        def num(x):
-            try:
-                return float(x)
-            except ValueError:
-                return None
-        sm = sorted(v for v in (num(r[1]) for r in rows) if v is not None)
-        mx = [v for v in (num(r[2]) for r in rows) if v is not None]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
         reasons = set()
-        for r in rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if self.nvml is not None:
+            sm = sorted(r[1] for r in rows)
+            mx = [self.sm_max] if self.sm_max else []
+            for r in rows:
+                for name, bit in self.REASONS:
+                    if r[2] & bit:
+                        reasons.add(name)
+        else:
+            rows = [r for r in rows if len(r) > 8]
+
+            def num(x):
+                try:
+                    return float(x)
+                except ValueError:
+                    return None
+            sm = sorted(v for v in (num(r[1]) for r in rows) if v is not None)
+            mx = [v for v in (num(r[2]) for r in rows) if v is not None]
+            for r in rows:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
         out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-               "reasons": sorted(reasons), "samples": len(sm)}
+               "reasons": sorted(reasons), "samples": len(sm), "source": self.src}
         if note:
             out["note"] = note
         return out
@@ -166,6 +219,173 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, steps, first_buffer=None, warm=2):
+    """`steps` sampler steps, each followed by the all-gather of the rows x k output shards, double-buffered so that
+    the gather of step i runs beside step i + 1.  Transport: copy-engine pushes into peer-mapped buffers
+    (htnorm_b200.dist.PeerGather - no kernel, no SM taken from the sampling GEMM); NCCL all_gather_into_tensor when
+    the peer mapping cannot be set up.  Device-timed, max over ranks.  Checks: every received shard has the checksum
+    its owner computed, and a slice of the LAST rank's shard equals the same rows drawn locally (bit for bit)."""
+    res = {"value": None}
+    ok_local = 1
+    outs = pg = full = None
+    try:
+        outs = [first_buffer if first_buffer is not None else torch.empty((rows, k), dtype=torch.float64, device=dev),
+                torch.empty((rows, k), dtype=torch.float64, device=dev)]
+    except RuntimeError:
+        ok_local = 0
+    flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not bool(flag.item()):
+        return {"value": None, "skipped": "shard buffers did not fit"}
+    transport = "copy engines: one cudaMemcpyAsync per peer shard on dedicated streams into peer-mapped (CUDA IPC) buffers"
+    try:
+        if os.environ.get("HTN_BENCH_GATHER", "peer") != "peer":
+            raise RuntimeError("NCCL requested")
+        pg = h.PeerGather(rows, k, dev)
+        full = pg.full
+        ok_local = 1
+    except Exception as ex:     # noqa: BLE001
+        ok_local = 0
+        res["peer_gather_error"] = repr(ex)[:200]
+    flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not bool(flag.item()):
+        if pg is not None:
+            pg = None
+        transport = "ncclAllGather (all_gather_into_tensor) on NCCL's stream"
+        try:
+            full = torch.empty((world * rows, k), dtype=torch.float64, device=dev)
+            ok_local = 1
+        except RuntimeError:
+            ok_local = 0
+        flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            return {"value": None, "skipped": "receive buffer did not fit"}
+    pend = [None, None]
+
+    def step(i):
+        o = outs[i & 1]
+        if pend[i & 1] is not None:             # this shard buffer has left for the peers
+            if pg is not None:
+                pg.wait(pend[i & 1])
+            else:
+                pend[i & 1].wait()
+        sample_into(i, o)
+        if pg is not None:
+            pend[i & 1] = pg.push(o)
+        else:
+            pend[i & 1] = dist.all_gather_into_tensor(full.view(-1), o.view(-1), async_op=True)
+
+    def drain():                                # the current stream has seen every copy / collective of this rank
+        for w in pend:
+            if w is not None:
+                if pg is not None:
+                    pg.wait(w)
+                else:
+                    w.wait()
+
+    def everywhere():
+        if pg is not None:
+            pg.finish()
+        else:
+            torch.cuda.synchronize()
+            dist.barrier()
+    for i in range(warm):
+        step(i)
+    drain()
+    everywhere()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(steps):
+        step(warm + i)
+    drain()
+    g1.record()
+    everywhere()
+    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    last_i = warm + steps - 1
+    last = outs[last_i & 1]
+    # checks on the last step's batch
+    own = bool(torch.equal(full[rank * rows:(rank + 1) * rows], last))
+    sums = torch.zeros(world, dtype=torch.float64, device=dev)
+    sums[rank] = last.sum()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    got = torch.stack([full[q * rows:(q + 1) * rows].sum() for q in range(world)])
+    sums_ok = bool(torch.equal(got, sums))
+    q, n = world - 1, min(128, rows)
+    lo = rows - n
+    sub_ok = bool(torch.equal(redraw(last_i, q, lo, n), full[q * rows + lo:q * rows + lo + n]))
+    okt = torch.tensor([int(own), int(sums_ok), int(sub_ok)], dtype=torch.int32, device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    res.update({"seconds": float(t.item()) * 1e-3, "ms_per_step": float(t.item()) / steps, "transport": transport,
+                "collective": "all-gather of the output shards over NVLink, overlapped with the next step "
+                              "(double-buffered shards); every rank ends with all %d samples" % (rows * world),
+                "own_shard_intact": bool(okt[0].item()), "peer_shards_match_owner_checksums": bool(okt[1].item()),
+                "slice_of_last_rank_equals_local_redraw": bool(okt[2].item())})
+    if pg is not None:
+        pg.close()
+    return res
+
+
+def cfg5_over_gpus(torch, dist, h, world, rank, dev, peak_tf, steps, no_gather):
+    """BASELINE configs[4] as north_star states it: ONE 16384 x 16384 covariance, k2 = 64, 65 536 samples sharded over
+    the N GPUs (8192 per rank at N = 8), the set-up (factorisation) replicated on every rank, no data-path collective;
+    then the same with the output gather.  Inputs are broadcast from rank 0 (untimed) so that every rank factorises
+    the same bits."""
+    import bench_configs as bc
+    total, k = 65536, 16384
+    rows = total // world
+    mu, cov, g, r = bc.cfg5_inputs(torch, dev)
+    for t in (mu, cov, g, r):
+        dist.broadcast(t, src=0)
+    out = torch.empty((rows, k), dtype=torch.float64, device=dev)
+    info = torch.empty(rows, dtype=torch.int32, device=dev)
+    s0 = 12345 + rank * rows
+
+    def sample(i, o):
+        h.hyperplane_truncated_mvnorm_batch(rows, mu, cov, g, r, gen="pcg64", seed0=s0 + i * total, out=o, info=info)
+
+    def redraw(i, q, lo, n):
+        o = torch.empty((n, k), dtype=torch.float64, device=dev)
+        h.hyperplane_truncated_mvnorm_batch(n, mu, cov, g, r, gen="pcg64", seed0=12345 + q * rows + i * total + lo, out=o)
+        return o
+    sample(0, out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sample(1 + i, out)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    bad = torch.tensor([int((info != 0).sum().item())], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+    resid = ((out[:256] @ g.T - r).norm(dim=1) / r.norm()).max().reshape(1)
+    dist.all_reduce(resid, op=dist.ReduceOp.MAX)
+    flops_rank = bc.cfg5_flops(rows)
+    tf = flops_rank / (ms * 1e-3) / 1e12
+    res = {"workload": "hyperplane-truncated MVN k=16384, k2=64: one covariance, 65 536 samples over %d GPUs (%d per "
+                       "rank), factorisation replicated per rank, no data-path collective" % (world, rows),
+           "ms_per_step": ms, "samples_per_s": total / (ms * 1e-3), "steps": steps,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s per GPU",
+                        "frac": tf / peak_tf if peak_tf and peak_tf > 0 else None, "algorithmic_flops_per_rank": flops_rank,
+                        "algorithmic_flops_unreplicated": bc.cfg5_flops(total)},
+           "failed_samples": int(bad.item()), "rel_constraint_residual_f64_first_256_per_rank": float(resid.item())}
+    if not no_gather:
+        gl = gather_leg(torch, dist, h, world, rank, dev, rows, k, sample, redraw, steps, first_buffer=out, warm=1)
+        if gl.get("seconds"):
+            gl["samples_per_s"] = total * steps / gl.pop("seconds")
+            gl["bytes_per_rank_per_step"] = 8 * rows * k
+        gl.pop("value", None)
+        res["gathered"] = gl
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +394,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the figure that includes the NCCL all-gather")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the figures that include the output gather")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the `configs` object (cfg2 ... cfg5, generator alone; N = 1) and cfg5 over N GPUs (N > 1)")
+    ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5_shard,normal_fill", help="which entries of `configs` to run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -244,7 +467,7 @@ def main():
     clk = None
     if rank == 0:
         note = None
-        if clocks.count_since(t_wall0) < 3 and clocks.proc is not None:
+        if clocks.count_since(t_wall0) < 3 and clocks.active:
             # the timed region is shorter than the sampler's period: keep the SAME steps running (untimed)
             # until a few samples have arrived, and report those
             note = ("timed region (%.0f ms) shorter than the nvidia-smi sampling period; clocks sampled over an "
@@ -269,64 +492,23 @@ def main():
     # parity spot check inside the bench: constraint residual of the last batch (sum-to-zero)
     resid = float((out @ d_in[2].T - d_in[3]).abs().max().item())
 
-    # ---- timed (N > 1 only): the same steps followed by the one collective of the path, an NCCL all-gather of the
+    # ---- timed (N > 1 only): the same steps followed by the one collective of the path, the all-gather of the
     # output shards.  Shards are double-buffered, so the gather of step i runs beside step i + 1. ----
     gathered = None
-    gather_on = world > 1 and not args.no_gather
-    if gather_on:
-        # the receive buffer holds the whole global batch (world x 524 MB): skip the leg on every rank if any rank
-        # cannot allocate it
-        try:
-            outs = [out, torch.empty_like(out)]
-            full = torch.empty((world * B, K), dtype=torch.float64, device=dev)
-            have = 1
-        except RuntimeError:
-            outs = full = None
-            have = 0
-        havet = torch.tensor([have], dtype=torch.int32, device=dev)
-        dist.all_reduce(havet, op=dist.ReduceOp.MIN)
-        if not bool(havet.item()):
-            gather_on = False
-            gathered = {"value": None, "unit": "samples/s", "skipped": "receive buffer did not fit"}
-            outs = full = None
-    if gather_on:
-        works = [None, None]
-
-        def step_gather(i):
-            o = outs[i & 1]
-            if works[i & 1] is not None:
-                works[i & 1].wait()          # this shard buffer has left for the peers
+    if world > 1 and not args.no_gather:
+        def sample_headline(i, o):
             h.hyperplane_truncated_mvnorm_batch(B, *d_in, gen="pcg64", seed0=seed0 + i * B * world, out=o, info=info)
-            works[i & 1] = dist.all_gather_into_tensor(full.view(-1), o.view(-1), async_op=True)
 
-        def drain():
-            for w in works:
-                if w is not None:
-                    w.wait()
-        for i in range(2):
-            step_gather(i)
-        drain()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for i in range(args.steps):
-            step_gather(2 + i)
-        drain()
-        g1.record()
-        barrier()
-        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        last = outs[(2 + args.steps - 1) & 1]
-        ok = bool(torch.equal(full[rank * B:(rank + 1) * B], last))
-        okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        gathered = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": "samples/s",
-                    "ms_per_step": float(t.item()) / args.steps, "bytes_per_rank_per_step": 8 * B * K,
-                    "collective": "ncclAllGather of the output shards over NVLink, overlapped with the next step "
-                                  "(double-buffered shards); every rank ends with all %d samples" % (B * world),
-                    "own_shard_intact": bool(okt.item())}
-        del full, outs
-        out = last
+        def redraw_headline(i, q, lo, n):      # rows [lo, lo + n) of rank q's shard of step i, drawn on THIS rank
+            o = torch.empty((n, K), dtype=torch.float64, device=dev)
+            h.hyperplane_truncated_mvnorm_batch(n, *d_in, gen="pcg64", seed0=12345 + q * B + i * B * world + lo, out=o)
+            return o
+        gathered = gather_leg(torch, dist, h, world, rank, dev, B, K, sample_headline, redraw_headline, args.steps,
+                              first_buffer=out)
+        if gathered.get("seconds"):
+            gathered["value"] = B * world * args.steps / gathered.pop("seconds")
+            gathered["unit"] = "samples/s"
+            gathered["bytes_per_rank_per_step"] = 8 * B * K
 
     # ---- timed: end to end through the C ABI with HOST buffers (pinned), copies inside ----
     h_in = [torch.from_numpy(x).pin_memory() for x in (mean, cov, g, r)]
@@ -352,11 +534,41 @@ def main():
     e2e_value = B * world * e2e_steps / float(t.item())
     h2d = 8 * (K * K + K2 * K + K + K2)
     d2h = 8 * B * K + 4 * B
+    # the ceiling of that figure on THIS box: every rank copies one shard-sized buffer device -> pinned host at the same
+    # time, nothing else running (N = 1: the bare PCIe rate; N > 1: what the host side absorbs from N GPUs at once)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_out.copy_(out, non_blocking=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    d2h_ceiling_gbs = world * 8.0 * B * K / float(t.item()) / 1e9
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    measured = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    dmma_peak = h.fp64_tensor_peak_tflops(local, 100.0)         # in-run FP64 tensor (DMMA) peak
+    dfma_peak = h.fp64_fma_peak_tflops(local, 50.0) if rank == 0 else None
+    # ---- the other BASELINE configurations (not the headline): N = 1 -> cfg2, cfg3, cfg4, cfg5's shard, the generator
+    # alone; N > 1 -> cfg5 as north_star states it, sharded over the N GPUs, without and with the output gather ----
+    configs = None
+    if not args.no_configs:
+        import bench_configs
+        del out, info
+        torch.cuda.empty_cache()
+        if world == 1:
+            hbm = float(measured.get("hbm_gbs", bench_configs.HBM_FALLBACK_GBS))
+            configs = bench_configs.run_all(h, torch, dev, dmma_peak, hbm, tuple(args.configs.split(",")))
+            configs["peaks"] = {"fp64_tensor_tflops": dmma_peak, "hbm_gbs": hbm,
+                                "hbm_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in measured
+                                else "B200_PROFILING.md fallback (of fallback)"}
+        else:
+            try:
+                configs = {"cfg5": cfg5_over_gpus(torch, dist, h, world, rank, dev, dmma_peak, 2, args.no_gather)}
+            except Exception as ex:     # noqa: BLE001  (reported in place; the headline stands)
+                configs = {"cfg5": {"error": repr(ex)[:300]}}
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        measured = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
-        dmma_peak = h.fp64_tensor_peak_tflops(local, 100.0)     # in-run FP64 tensor (DMMA) peak
         alg_flops = B * (K * K + 2.0 * K * K2)                  # per launch of the sampling GEMM
         gemm_avg = sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
         achieved = alg_flops / (gemm_avg * 1e-3) / 1e12 if gemm_avg else None
@@ -366,12 +578,16 @@ def main():
                 "traffic": None,
                 "peak_source": "in-run DMMA (mma.sync m8n8k4 f64) microbenchmark, htn_fp64_tensor_peak_tflops; "
                                "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs=%s)" % measured.get("hbm_gbs"),
+                "fp64_fma_peak_tflops": dfma_peak,
                 "kernel_ms": gemm_avg,
                 "step_phases_ms": {k_: v for k_, v in phases[0].items() if k_ != "calls"},
                 "kernel_launches_timed": phases[0]["calls"]}
         traffic_path = os.path.join(ROOT, "profiles", "gemm_traffic_bytes.json")
         if os.path.exists(traffic_path):
-            roof["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+            tj = json.load(open(traffic_path))
+            roof["traffic"] = tj.get("dram_bytes_per_launch")
+            roof["traffic_source"] = "one `ncu --set full` capture of this kernel, not this run: " + str(tj.get("source"))
+            roof["algorithmic_bytes"] = tj.get("algorithmic_bytes")
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -381,11 +597,17 @@ def main():
                            "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "output (524 MB per step at the default batch) and Z~ exceed the 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "d2h_gbs": e2e_value * 8.0 * K / 1e9, "d2h_ceiling_gbs": d2h_ceiling_gbs,
+                        "frac_of_d2h_ceiling": e2e_value * 8.0 * K / 1e9 / d2h_ceiling_gbs,
+                        "d2h_ceiling_how": "all %d ranks copy one 524 MB shard device -> pinned host concurrently, "
+                                           "3 repetitions, max over ranks" % world},
                 "gpu_launches": launches, "roofline": roof, "clocks": clk,
                 "max_abs_constraint_residual": resid}
         if gathered is not None:
             line["gathered"] = gathered
+        if configs is not None:
+            line["configs"] = configs
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()

@@ -11,6 +11,6 @@ from .api import (HTNGenerator, fp64_fma_peak_tflops, fp64_tensor_peak_tflops,  
                   phase_timing,
                   raw_streams, standard_normals, structured_precision_mvnorm,
                   structured_precision_mvnorm_batch)
-from .dist import gather_rows, sample_sharded, shard_range, shard_sizes  # noqa: F401
+from .dist import PeerGather, gather_rows, sample_sharded, shard_range, shard_sizes  # noqa: F401
 
 __version__ = "0.1.0"

@@ -65,3 +65,76 @@ def gather_rows(local, nsamples, group=None, dst=None):
     for q in range(world):
         full[offs[q]:offs[q + 1]] = buf[q, :sizes[q]]
     return full
+
+
+class PeerGather:
+    """All-gather of equal-sized row shards by COPY-ENGINE pushes into peer-mapped receive buffers - no NCCL kernel,
+    hence no CTA taken from the sampling GEMM that owns every SM while the previous step's shard is in flight.
+
+    One process per GPU (torch.distributed for the plumbing only): every rank allocates its receive buffer
+    ``full`` [world * rows, k], exports it as a CUDA IPC handle (torch.multiprocessing's reductions), and all ranks
+    exchange the handles once (``all_gather_object``).  ``push(shard, event)`` then enqueues, on one dedicated stream per
+    peer, a plain ``cudaMemcpyAsync`` (``Tensor.copy_``: device-to-device, peer access enabled) of this rank's shard
+    into rows [rank * rows, (rank + 1) * rows) of EVERY rank's buffer, NVLink / NVSwitch carrying each copy at the
+    copy engine's rate.  ``wait_sent()`` makes the compute stream wait until this rank's shard buffer may be reused;
+    ``finish()`` (copy streams drained on every rank, then one barrier) makes ``full`` complete everywhere.
+    Single-node only (CUDA IPC); callers fall back to ``gather_rows`` (NCCL) when construction fails."""
+
+    def __init__(self, rows, k, device, group=None, dtype=None):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows, self.k, self.device = rows, k, torch.device(device)
+        dtype = dtype or torch.float64
+        self.full = torch.empty((self.world * rows, k), dtype=dtype, device=self.device)
+        handle = reduce_tensor(self.full)                     # (rebuild function, picklable arguments)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peers = []
+        for q in range(self.world):
+            if q == self.rank:
+                self.peers.append(self.full)
+            else:
+                fn, args = handles[q]
+                self.peers.append(fn(*args))                  # the peer's buffer, mapped into this process
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.world)]
+        self.sent = None
+        lo = self.rank * rows
+        self.dst = [p[lo:lo + rows] for p in self.peers]
+        dist.barrier(group=group)
+
+    def push(self, shard):
+        """enqueue the copies of `shard` (ready on the current stream at this point) to every rank, own buffer included"""
+        torch = self.torch
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        done = []
+        order = [(self.rank + 1 + i) % self.world for i in range(self.world)]   # ring order: spread the targets
+        for q in order:
+            st = self.streams[q]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                self.dst[q].copy_(shard, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
+        return done
+
+    def wait(self, done):
+        """the current stream waits until the copies of an earlier push() have read their source"""
+        cur = self.torch.cuda.current_stream(self.device)
+        for ev in done:
+            cur.wait_event(ev)
+
+    def finish(self):
+        """every push of every rank has landed: local copy streams drained, then a barrier"""
+        for st in self.streams:
+            st.synchronize()
+        self.dist.barrier(group=self.group)
+
+    def close(self):
+        self.dist.barrier(group=self.group)                   # nobody may still be writing into a buffer about to go
+        self.dst = self.peers = None
+        self.full = None

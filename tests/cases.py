@@ -117,3 +117,40 @@ SP_CASES = ["pytest_fixture", "nn_plain", "nn_struct", "dd_plain", "id_struct", 
             "nd_plain_big"]
 
 RNG_SEEDS = [0, 1, 10, 12345, 2**32 - 1, 2**63 + 5, 2**64 - 1]
+
+
+# ---- BASELINE.json configs at FULL size (configs[3], configs[4]) ------------------------------------------------
+# Inputs must be rebuilt identically on the GPU box from a seed, cheaply (no O(d^3) BLAS on the host): SPD matrices of
+# the form  diag(U(1,2)) + V V^T / d  with V d x 64 - dense, kappa ~ 3, 2 * 64 * d^2 flops to build.  The golden rows
+# come from the unmodified reference on the same arrays (tools/make_golden_fullsize.py -> tests/golden/fullsize.npz).
+
+def spd_lowrank(rng, d, rank=64):
+    v = rng.standard_normal((d, rank))
+    s = v @ v.T
+    s /= d
+    s[np.diag_indices(d)] += rng.uniform(1.0, 2.0, d)
+    return s
+
+
+def cfg4_inputs():
+    """configs[3]: structured precision + structured mean, p = 8192, n = 1024, dense A and Omega."""
+    rng = np.random.default_rng(404)
+    p, n = 8192, 1024
+    a = spd_lowrank(rng, p)
+    omega = spd_lowrank(rng, n)
+    phi = rng.standard_normal((n, p)) / np.sqrt(p)
+    t = rng.standard_normal(n)
+    return dict(mean=t, a=a, phi=phi, omega=omega, struct_mean=True, a_type=0, o_type=0, gen="pcg64", seed0=12345,
+                spot=np.array([0, 1, 128, 255]))
+
+
+def cfg5_inputs():
+    """configs[4], one GPU's shard: hyperplane-truncated MVN k = 16384, k2 = 64.  G is scaled by 1/sqrt(k) so that
+    G x is O(1) and the constraint residual can be evaluated to ~1e-16 in float64."""
+    rng = np.random.default_rng(505)
+    k, k2 = 16384, 64
+    cov = spd_lowrank(rng, k)
+    g = rng.standard_normal((k2, k)) / np.sqrt(k)
+    r = rng.standard_normal(k2)
+    mean = rng.standard_normal(k)
+    return dict(mean=mean, cov=cov, g=g, r=r, gen="pcg64", seed0=12345, spot=np.array([0, 8191]))

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import cases
-from conftest import REL_TOL, RESID_TOL, rel_err
+from conftest import REL_TOL, RESID_TOL, constraint_violation, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -167,10 +167,14 @@ def test_hyperplane_golden(h, gold, name):
     assert np.array_equal(info, g[name + "__info"])
     tol = 1e-6 if name == "readme_k1000" else REL_TOL   # README cov = t t^T: kappa ~ 1e9
     assert rel_err(x, g[name + "__x"]) < tol
-    resid = np.abs(x @ c["g"].T - c["r"]).max(axis=1)
-    scale = np.linalg.norm(c["r"]) if np.linalg.norm(c["r"]) > 0 else 1.0
-    if name != "readme_k1000":
-        assert (resid / scale).max() < RESID_TOL * 10 * max(1.0, np.abs(x).max())
+    # the north_star bar: ||G x - r|| <= 1e-12 ||r|| (absolute when r = 0), residual evaluated in extended precision.
+    # On the two ill-conditioned inputs the REFERENCE's own output misses that bar (its pytest fixture, kappa 6e3:
+    # 1.5e-11; the README cov = t t^T, kappa 6e9: 2.5e-12 - measured on the golden rows): there the bar is the
+    # reference's own violation, with a factor 4 for a different summation order.
+    viol = constraint_violation(x, c["g"], c["r"])
+    ref_viol = constraint_violation(g[name + "__x"], c["g"], c["r"])
+    bar = RESID_TOL if name not in ("pytest_fixture", "readme_k1000") else max(RESID_TOL, 4 * ref_viol)
+    assert viol < bar, (name, viol, ref_viol)
 
 
 def test_hyperplane_independent_golden(h, gold):
@@ -205,7 +209,7 @@ def test_hyperplane_vs_oracle_fresh_inputs(h, oracle):
         xo, io, _ = oracle.hyperplane(gen, B, mu, cov, g, r, seeds=seeds)
         assert np.array_equal(info, io)
         assert rel_err(x, xo) < REL_TOL
-        assert (np.abs(x @ g.T - r).max(axis=1) / np.linalg.norm(r)).max() < RESID_TOL * 50
+        assert constraint_violation(x, g, r) < RESID_TOL
 
 
 def test_error_codes_and_nan(h):
@@ -300,7 +304,7 @@ def test_reference_properties_on_device(h):
     rng = np.random.default_rng(5)
     cov = cases.spd(rng, k)
     x, _ = h.hyperplane_truncated_mvnorm_batch(64, rng.standard_normal(k), cov, np.ones((1, k)), np.zeros(1))
-    assert np.abs(x.sum(axis=1)).max() < RESID_TOL * 100
+    assert constraint_violation(x, np.ones((1, k)), np.zeros(1)) < RESID_TOL      # r = 0: absolute
     s = cases.sp_case("dd_plain")
     a, _ = h.structured_precision_mvnorm_batch(8, s["mean"], s["a"], s["phi"], s["omega"], False, 1, 1, seed0=2)
     b, _ = h.structured_precision_mvnorm_batch(8, s["mean"], s["a"], s["phi"], s["omega"], False, 0, 0, seed0=2)
@@ -454,8 +458,7 @@ def test_independent_problems_all_shapes(h, oracle, k, k2, diag):
                                   seed0=5)
     assert np.array_equal(info, io) and not info.any()
     assert rel_err(x, xo) < REL_TOL
-    resid = np.abs(np.einsum("bck,bk->bc", c["g"], x) - c["r"]).max()
-    assert resid < RESID_TOL * 50 * max(1.0, np.abs(c["r"]).max())
+    assert constraint_violation(x, c["g"], c["r"]) < RESID_TOL
 
 
 def test_independent_problems_failures_and_layouts(h, oracle):
@@ -641,8 +644,8 @@ def test_full_size_headline_properties(h, oracle):
     x, info = h.hyperplane_truncated_mvnorm_batch(B, *t, seed0=12345)
     torch.cuda.synchronize()
     assert int((info != 0).sum()) == 0
-    resid = (x @ t[2].T - t[3]).abs().max().item()
-    assert resid < 1e-12 * max(1.0, x.abs().max().item()) * 10          # sum-to-zero constraint
+    # sum-to-zero constraint, r = 0: absolute bar, every one of the 65 536 samples, extended-precision row sums
+    assert constraint_violation(x.cpu().numpy(), g, r) < RESID_TOL
     # E[x] = mean + cov g^T (g cov g^T)^-1 (r - g mean)
     cg = cov @ g.T
     want = mean + (cg @ np.linalg.solve(g @ cg, r - g @ mean))
@@ -670,8 +673,7 @@ def test_full_size_small_problems_properties(h, oracle):
     x, info = h.hyperplane_truncated_mvnorm_batch(B, mu, cov, g, r, independent=True, seed0=12345)
     torch.cuda.synchronize()
     assert int((info != 0).sum()) == 0
-    resid = (torch.einsum("bck,bk->bc", g, x) - r).abs().max().item()
-    assert resid < 1e-11
+    assert constraint_violation(x.cpu().numpy(), g.cpu().numpy(), r.cpu().numpy()) < RESID_TOL   # every problem
     spot = np.array([0, 1, 127, 128, 4097, 30000, 65534, 65535])
     sel = torch.from_numpy(spot).to(dev)
     xo, io, _ = oracle.hyperplane("pcg64", len(spot), mu[sel].cpu().numpy(), cov[sel].cpu().numpy(),
@@ -735,3 +737,60 @@ def test_device_mode_raise_on_error_and_result_validation(h):
     with pytest.raises(TypeError):
         h.hyperplane_truncated_mvnorm_batch(3, z(k), torch.eye(k, dtype=torch.float64, device=dev), ones, z(2),
                                             seeds=torch.zeros(3, dtype=torch.int32, device=dev))
+
+
+# ------------------------------------------------------------------ BASELINE configs[3] / configs[4] at FULL size
+
+def _fullsize_gold():
+    import os
+    from conftest import GOLD
+    return np.load(os.path.join(GOLD, "fullsize.npz"))
+
+
+def test_full_size_cfg4_structured_mean_block_inverse_path(h):
+    """BASELINE configs[3]: p = 8192, n = 1024, dense A and Omega, structured mean, batch 256.  At this size the host
+    layer takes - BY DEFAULT, nothing forced - the diagonal-block inverse of L_A (structured.c inverse_block_width,
+    linalg.c solve_*_blocks) and the wide-super-panel Cholesky: 4 samples against golden rows of the unmodified
+    reference (tools/make_golden_fullsize.py), all 256 finite, codes zero.  Reference: src/htnorm.c:217-356."""
+    import os
+    assert "HTN_INV_BLOCK" not in os.environ
+    c = cases.cfg4_inputs()
+    gold = _fullsize_gold()
+    B = 256
+    x, info = h.structured_precision_mvnorm_batch(B, c["mean"], c["a"], c["phi"], c["omega"], c["struct_mean"],
+                                                  c["a_type"], c["o_type"], gen=c["gen"], seed0=c["seed0"])
+    assert not info.any() and np.isfinite(x).all()
+    spot = gold["cfg4__spot"]
+    assert np.array_equal(spot, c["spot"])
+    err = rel_err(x[spot], gold["cfg4__x"])
+    assert err < REL_TOL, err
+
+
+def test_full_size_cfg5_shard(h):
+    """BASELINE configs[4], one GPU's shard: k = 16384, k2 = 64, one factorisation, 8192 samples (device-resident).
+    Every sample satisfies ||G x - r|| <= 1e-12 ||r|| (extended-precision residual), and the two samples at the ends
+    of the shard match golden rows of the unmodified reference (one 16384 x 16384 dpotrf per row there).
+    Reference: src/htnorm.c:85-187 (dposv k2 = 64 at :169), src/htnorm_distributions.c:75-83."""
+    import torch
+    c = cases.cfg5_inputs()
+    gold = _fullsize_gold()
+    dev = "cuda:0"
+    t = [torch.from_numpy(c[n_]).to(dev) for n_ in ("mean", "cov", "g", "r")]
+    B = 8192
+    x, info = h.hyperplane_truncated_mvnorm_batch(B, *t, gen=c["gen"], seed0=c["seed0"])
+    torch.cuda.synchronize()
+    assert int((info != 0).sum()) == 0
+    xh = x.cpu().numpy()
+    del x, t
+    torch.cuda.empty_cache()
+    viol = constraint_violation(xh, c["g"], c["r"])
+    assert viol < RESID_TOL, viol
+    spot = gold["cfg5__spot"]
+    assert np.array_equal(spot, c["spot"])
+    err = rel_err(xh[spot], gold["cfg5__x"])
+    assert err < REL_TOL, err
+    # a second, single-sample shard drawn with the offset seed is the same row, bit for bit (the 8-GPU sharding rule)
+    t = [torch.from_numpy(c[n_]).to(dev) for n_ in ("mean", "cov", "g", "r")]
+    y, _ = h.hyperplane_truncated_mvnorm_batch(128, *t, gen=c["gen"], seed0=c["seed0"] + 8064)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), xh[8064:])
