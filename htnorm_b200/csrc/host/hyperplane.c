@@ -436,9 +436,15 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
                 htnk_segment_t seg = {k, zs, k, NULL, NULL, NULL};
                 rc = htnk_normal_fill(ctx->stream, &sv, nsamples, 1, &seg, NULL);
             }
-            if (!rc)
-                rc = htnk_ht_small_batched(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, diag,
-                                           (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
+            if (!rc) {
+                /* the warp-per-problem kernel for the shapes it is specialised for, else the generic CTA-per-problem one */
+                rc = (diag || (flags & HTN_FLAG_COLMAJOR))
+                         ? 1
+                         : htnk_ht_small_warp(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, out, info_dev);
+                if (rc == 1)
+                    rc = htnk_ht_small_batched(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, diag,
+                                               (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
+            }
             htn_dfree(ctx, zs);
             htn_dfree(ctx, tmp);
             *first_info = 0; /* per-problem codes live in the device array */

@@ -1,26 +1,9 @@
-"""cfg2 in miniature: independent small problems (k = 64, k2 = 4), device-resident, timed with CUDA events."""
+"""cfg2-shaped run for profiling: P problems k = 64, k2 = 4 (default 2^18), a few launches"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import htnorm_b200 as h
-import cases
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
-k, k2 = 64, 4
-dev = "cuda:0"
-rng = np.random.default_rng(1)
-base = torch.from_numpy(np.stack([cases.spd(rng, k) for _ in range(64)])).to(dev)
-cov = base.repeat(B // 64, 1, 1).contiguous()
-g = torch.randn(B, k2, k, dtype=torch.float64, device=dev); r = torch.randn(B, k2, dtype=torch.float64, device=dev)
-mu = torch.randn(B, k, dtype=torch.float64, device=dev)
-out = torch.empty((B, k), dtype=torch.float64, device=dev); info = torch.empty(B, dtype=torch.int32, device=dev)
-f = lambda: h.hyperplane_truncated_mvnorm_batch(B, mu, cov, g, r, seed0=1, independent=True, out=out, info=info)
-for _ in range(3): f()
-torch.cuda.synchronize()
-ts = []
-for _ in range(5):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); f(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-best = min(ts)
-bytes_ = B * 8 * (k * k + k2 * k + 2 * k + k2)
-print(f"B={B} ms={best:.3f} problems/s={B/(best*1e-3):.3e} GB/s={bytes_/(best*1e-3)/1e9:.0f} (HBM roofline 6535) resid={float((torch.einsum('bck,bk->bc', g, out) - r).abs().max()):.2e} info_nonzero={int((info != 0).sum())}")
+import bench_configs as bc
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+r = bc.cfg2(h, torch, "cuda:0", 6535.1, P)
+print(r["ms"], r["samples_per_s"], r["roofline"]["frac"])
