@@ -25,6 +25,7 @@
 // the generic kernel (small_batched.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "launchers.h"
@@ -81,11 +82,19 @@ struct Geo {
     static constexpr int TOTAL = SCR + 128;
 };
 
-template <int NT>
+// PROF (HTN_SMALL_PROF=1, development only): lane 0 of every warp adds the clock64() span of each phase to prof[]
+#define PHASE(i)                                                                       \
+    if (PROF) {                                                                        \
+        const long long t_now = clock64();                                             \
+        if (lane == 0) atomicAdd((unsigned long long*)&prof[i], (unsigned long long)(t_now - t_prev)); \
+        t_prev = t_now;                                                                \
+    }
+
+template <int NT, bool PROF>
 __global__ void __launch_bounds__(32, 9)
 ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const double* __restrict__ cov,
                const double* __restrict__ gm, const double* __restrict__ rv, const double* __restrict__ zs,
-               double* __restrict__ out, int* __restrict__ info)
+               double* __restrict__ out, int* __restrict__ info, long long* prof)
 {
     using G = Geo<NT>;
     constexpr int K = G::K, RS = G::RS;
@@ -115,6 +124,7 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
     for (int idx = lane; idx < G::TOTAL; idx += 32) sm[idx] = 0.0;
     __syncwarp();
 
+    long long t_prev = PROF ? clock64() : 0;
     for (size_t pb = blockIdx.x; pb < nproblems; pb += gridDim.x) {
         const double* covp = cov + pb * (size_t)K * K;
         const double* gp = gm + pb * (size_t)k2 * K;
@@ -156,8 +166,10 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
         for (int c = 0; c < 4; c++)
             if (c < k2) rreg[c] = rv[pb * (size_t)k2 + c];
         asm volatile("cp.async.commit_group;\n" ::);
+        PHASE(0)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncwarp();
+        PHASE(1)
 
         // ---- c0 = r - G mean: one tensor-core pass W^T W over W = GM (entries (a, 4) = G[a] . mean) ----
         double gmean[4];
@@ -177,17 +189,22 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             for (int a = 0; a < 4; a++) gmean[a] = sm[G::SCR + a * 8 + (4 ^ (4 * ((a >> 1) & 1)))];
         }
 
+        PHASE(2)
         // ---- Cholesky cov = L L^T, panel by panel, with look-ahead inside the single instruction stream: the
         // rank-8 update of step p is split into the URGENT tiles (block column p + 1: all that the elimination of panel
         // p + 1 reads) and the DEFERRED ones (block columns >= p + 2), which are issued a few at a time BETWEEN the
         // pivots of that elimination - independent tensor-core work in the stalls of the 8-pivot dependency chain ----
         int fail = 0;
-        double fa[NT][2];  // fragments (row pattern) of the tiles of the panel factorised last
+        // fragments (row pattern) of the tiles of the panel factorised last: fa = L, fad = -L D (cov = L D L^T: the rank-8
+        // update is C -= (L D) L^T)
+        double fa[NT][2], fad[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; t++) fa[t][0] = fa[t][1] = fad[t][0] = fad[t][1] = 0.0;
         auto tile_update = [&](int ti, int tj) {
             double2* cp = reinterpret_cast<double2*>(&sm[G::off(tj) + 64 * (ti - tj) + (cf >> 3)]);
             double2 c = *cp;
-            dmma(c.x, c.y, -fa[ti][0], fa[tj][0]);
-            dmma(c.x, c.y, -fa[ti][1], fa[tj][1]);
+            dmma(c.x, c.y, fad[ti][0], fa[tj][0]);
+            dmma(c.x, c.y, fad[ti][1], fa[tj][1]);
             *cp = c;
         };
 #pragma unroll
@@ -236,10 +253,11 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
                     }
                 }
                 if (ajj <= 0.0 && fail == 0) fail = 8 * p + j + 1;  // NaN passes
-                const double rinv = fast_rsqrt(ajj);               // off the chain: only scales the finished column
+                // square-root free: column j of the UNIT lower factor is a[i][j] / d_j = t, the pivot d_j goes to DV
 #pragma unroll
                 for (int rs = 0; rs < RS; rs++)
-                    if (32 * rs + 31 >= 8 * p) v[rs][j] *= rinv;
+                    if (32 * rs + 31 >= 8 * p) v[rs][j] = t[rs];
+                if (lane == ((8 * p + j) & 31)) sm[G::WV + 8 * p + j] = ajj;
                 // deferred tiles of step p - 1 (block columns >= p + 1), an eighth of them after every pivot
                 if (p >= 1) {
                     const int q = p - 1;
@@ -261,10 +279,12 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             for (int rs = 0; rs < RS; rs++) {
                 if (32 * rs + 31 >= 8 * p) {
                     const int i = lane + 32 * rs;
-                    const int r = i - 8 * p;
+                    if (rs == rsd) {  // compile-time: only this row set holds rows of the diagonal block
+                        const int r = i - 8 * p;
 #pragma unroll
-                    for (int c = 1; c < 8; c++)
-                        if (r >= 0 && r < c) v[rs][c] = 0.0;
+                        for (int c = 1; c < 8; c++)
+                            if (r >= 0 && r < c) v[rs][c] = 0.0;
+                    }
                     if (i >= 8 * p && i < K) {
                         const int cb = G::off(p) - 64 * p;
                         *reinterpret_cast<double2*>(&sm[cb + (row_lo[rs] >> 3)]) = make_double2(v[rs][0], v[rs][1]);
@@ -275,26 +295,31 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
                 }
             }
             __syncwarp();
+            PHASE(3)
             if (p + 1 < NT) {
                 // fragments of panel p, then the urgent tiles (block column p + 1): all loads, then two rounds of
                 // independent DMMAs, then the stores
+                const double ds0 = -sm[G::WV + 8 * p + t4], ds1 = -sm[G::WV + 8 * p + 4 + t4];  // -d of the fragment's columns
 #pragma unroll
                 for (int t = p + 1; t < NT; t++) {
                     fa[t][0] = sm[G::off(p) + 64 * (t - p) + (rf0 >> 3)];
                     fa[t][1] = sm[G::off(p) + 64 * (t - p) + (rf1 >> 3)];
+                    fad[t][0] = fa[t][0] * ds0;
+                    fad[t][1] = fa[t][1] * ds1;
                 }
                 double2 cu[NT];
 #pragma unroll
                 for (int ti = p + 1; ti < NT; ti++)
                     cu[ti] = *reinterpret_cast<const double2*>(&sm[G::off(p + 1) + 64 * (ti - p - 1) + (cf >> 3)]);
 #pragma unroll
-                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, -fa[ti][0], fa[p + 1][0]);
+                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, fad[ti][0], fa[p + 1][0]);
 #pragma unroll
-                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, -fa[ti][1], fa[p + 1][1]);
+                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, fad[ti][1], fa[p + 1][1]);
 #pragma unroll
                 for (int ti = p + 1; ti < NT; ti++)
                     *reinterpret_cast<double2*>(&sm[G::off(p + 1) + 64 * (ti - p - 1) + (cf >> 3)]) = cu[ti];
                 __syncwarp();
+                PHASE(4)
             }
         }
         if (fail) {  // the reference returns before drawing (src/htnorm_distributions.c:78): out untouched
@@ -302,8 +327,22 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             continue;
         }
 
-        // ---- V = L^T G^T on the tensor cores: one accumulator per 8 rows of V, all eight chains interleaved; written
-        // over G^T at the end ----
+        // cov = L D L^T with L unit lower: the Cholesky factor is L sqrt(D).  sd = sqrt(d), lane = row; DV then holds sd
+        double sdreg[RS];
+#pragma unroll
+        for (int rs = 0; rs < RS; rs++) {
+            const int i = lane + 32 * rs;
+            sdreg[rs] = i < K ? sqrt(sm[G::WV + i]) : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rs = 0; rs < RS; rs++) {
+            const int i = lane + 32 * rs;
+            if (i < K) sm[G::WV + i] = sdreg[rs];
+        }
+        __syncwarp();
+        // ---- V = sqrt(D) L^T G^T on the tensor cores: one accumulator per 8 rows of V, all eight chains interleaved;
+        // written over G^T at the end ----
         {
             double2 va[NT];
 #pragma unroll
@@ -327,10 +366,14 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             __syncwarp();  // every lane has read G^T
             if (t4 < 2) {
 #pragma unroll
-                for (int tb = 0; tb < NT; tb++) *reinterpret_cast<double2*>(&sm[G::GM + 64 * tb + (cf >> 3)]) = va[tb];
+                for (int tb = 0; tb < NT; tb++) {
+                    const double sdr = sm[G::WV + 8 * tb + g];
+                    *reinterpret_cast<double2*>(&sm[G::GM + 64 * tb + (cf >> 3)]) = make_double2(va[tb].x * sdr, va[tb].y * sdr);
+                }
             }
             __syncwarp();
         }
+        PHASE(5)
         // ---- S = V^T V and V^T z in one pass W^T W over W = [V | mean | z]: entries (a, b) and (a, 5) ----
         {
             double2 acc[4];
@@ -400,6 +443,7 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
                 for (int i = 0; i < 4; i++) al[i] = f2 ? 0.0 : bv[i];  // G cov G^T not PD: the unprojected y (src/htnorm.c:170)
             }
         }
+        PHASE(6)
         // ---- w = z + V alpha (lane = row) ----
 #pragma unroll
         for (int rs = 0; rs < RS; rs++) {
@@ -412,11 +456,11 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
                 w = fma(v01.y, al[1], w);
                 w = fma(v23.x, al[2], w);
                 w = fma(v23.y, al[3], w);
-                sm[G::WV + i] = w;
+                sm[G::WV + i] = w * sdreg[rs];  // Cholesky factor times w = L (sqrt(D) w)
             }
         }
         __syncwarp();
-        // ---- x = mean + L w: row dot products, lane = row, panel by panel ----
+        // ---- x = mean + L (sqrt(D) w): row dot products, lane = row, panel by panel ----
         double acc[RS];
 #pragma unroll
         for (int rs = 0; rs < RS; rs++) acc[rs] = mreg[rs];
@@ -453,8 +497,10 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
         }
         if (lane == 0 && info) info[pb] = f2;
         __syncwarp();  // the next problem's asynchronous copies overwrite what this one was still reading
+        PHASE(7)
     }
 }
+#undef PHASE
 
 }  // namespace
 
@@ -468,7 +514,8 @@ extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int 
     static const bool off = getenv("HTN_SMALL_IMPL") != nullptr && atoi(getenv("HTN_SMALL_IMPL")) == 0;
     if (off) return 1;
     if ((((uintptr_t)mean | (uintptr_t)cov | (uintptr_t)g | (uintptr_t)r | (uintptr_t)zs | (uintptr_t)out) & 7) != 0) return 1;
-    auto kern = ht_warp_kernel<8>;
+    static const bool want_prof = getenv("HTN_SMALL_PROF") != nullptr;
+    auto kern = want_prof ? ht_warp_kernel<8, true> : ht_warp_kernel<8, false>;
     const size_t smem = (size_t)Geo<8>::TOTAL * sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
     int dev = 0, sms = 148, per_sm = 1;
@@ -479,7 +526,23 @@ extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int 
     if (const char* e = getenv("HTN_SMALL_CTAS")) per_sm = atoi(e) < per_sm ? (atoi(e) > 0 ? atoi(e) : 1) : per_sm;
     size_t grid = (size_t)sms * per_sm;
     if (grid > nproblems) grid = nproblems;
-    kern<<<(unsigned)grid, 32, smem, st>>>(nproblems, k2, mean, cov, g, r, zs, out, info);
+    long long* prof = nullptr;
+    if (want_prof) {
+        if (cudaMalloc(&prof, 16 * sizeof(long long)) != cudaSuccess) return -201;
+        cudaMemsetAsync(prof, 0, 16 * sizeof(long long), st);
+    }
+    kern<<<(unsigned)grid, 32, smem, st>>>(nproblems, k2, mean, cov, g, r, zs, out, info, prof);
     htnk_count_launch();
+    if (want_prof) {  // development aid: synchronous on purpose
+        long long hp[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost);
+        cudaFree(prof);
+        static const char* names[8] = {"issue-stage", "wait-stage", "c0", "elim(+deferred)", "urgent", "V", "S+solve", "w+x+out"};
+        fprintf(stderr, "[ht_warp] %d warps/SM (%zu B smem), clk per problem:", per_sm, smem);
+        double tot = 0;
+        for (int i = 0; i < 8; i++) { fprintf(stderr, " %s %.0f", names[i], (double)hp[i] / (double)nproblems); tot += (double)hp[i] / (double)nproblems; }
+        fprintf(stderr, " | total %.0f\n", tot);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }
