@@ -149,9 +149,10 @@ int htnk_ht_small_batched(cudaStream_t st, size_t nproblems, int k, int k2, cons
                           int lower_src, double* out, int* info);
 
 /* One WARP per problem, k = 64, k2 <= 4, dense row-major cov (small_warp.cu): same contract as above.  Returns 1 when the
- * shape is not one it is built for (the caller then takes htnk_ht_small_batched). */
+ * shape is not one it is built for (the caller then takes htnk_ht_small_batched).  counter: one zero-initialised device
+ * unsigned, the kernel's dynamic problem queue. */
 int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int k2, const double* mean, const double* cov,
-                       const double* g, const double* r, const double* zs, double* out, int* info);
+                       const double* g, const double* r, const double* zs, double* out, int* info, unsigned* counter);
 
 /* ---- peak microbenchmarks (peak.cu) ---- */
 double htnk_dmma_peak_tflops(cudaStream_t st, double ms);

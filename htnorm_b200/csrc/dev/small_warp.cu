@@ -1,28 +1,33 @@
-// Many small independent problems, round-2 design: ONE WARP PER PROBLEM, everything warp-synchronous, every
-// address a compile-time constant (BASELINE.json configs[1]: k = 64, k2 = 4, 2^20 problems).
+// Many small independent problems, round-2 design: ONE WARP PER PROBLEM, the trailing matrix in REGISTERS, everything
+// warp-synchronous, every address a compile-time constant (BASELINE.json configs[1]: k = 64, k2 = 4, 2^20 problems).
 //
-// Why (profiles/r1_small_batched_v7_summary.txt): the round-1 kernel (small_batched.cu: one 64-thread CTA per problem,
-// factor warp + update warp, generic k) spent 12.8 k warp-instructions per problem - a quarter of them address
-// arithmetic (IMAD / LEA / ISETP), 42 block barriers - and 2.9 k cycles of the SM's FP64 datapath on padded or
-// redundant work (all-lanes 8 x 8 factor, k2 and z padded to 8 on the tensor cores); it reached 22 % of the HBM
-// roofline.  Here:
+// Why (profiles/r1_small_batched_v7_summary.txt, profiles/r2_small_warp_*): the round-1 kernel (small_batched.cu: one
+// 64-thread CTA per problem, factor warp + update warp, generic k) spent 12.8 k warp-instructions per problem - a quarter
+// of them address arithmetic, 42 block barriers - and 2.9 k cycles of the SM's FP64 datapath on padded or redundant
+// work; it reached 22 % of the HBM roofline.  A first warp-per-problem version that kept the trailing matrix in shared
+// memory turned out bound by the shared-memory DATA PIPE (3.3 k wavefronts per problem, 66 % of its peak: 8-byte
+// asynchronous copies scattered with bank conflicts, an LDS + STS round trip per tile update).  Here:
 //   * the whole of src/htnorm.c:85-187 + mvn_rand_cov (src/htnorm_distributions.c:58-88) for one problem runs in one
-//     warp out of 23 KB of shared memory: no block barrier, no role hand-off, 9 independent problems per SM;
-//   * k is a template parameter (k = 8 NT): loops are fully unrolled and every shared-memory offset is an immediate;
-//   * cov = L L^T in LOWER form on 8-wide column panels.  The panel step is done with the LANE = ROW layout: lane i
-//     holds row i of the panel in registers, the 8 pivots of a panel are eliminated by row operations whose only
-//     communication is a warp shuffle of the pivot row (no 8 x 8 factor replicated in all lanes, no explicit inverse,
-//     no tensor-core panel solve); the update of a pivot uses 1 / a_jj (reciprocal seed + Newton), so the rsqrt that
-//     scales the column is off the critical path;
-//   * the rank-8 trailing update stays on the FP64 tensor cores (DMMA m8n8k4), fragments read conflict-free through
-//     an XOR swizzle of the dense 8-double panel rows (no padding: 18 KB for the factor instead of 27);
+//     warp: no block barrier, no role hand-off, 9 independent problems per SM;
+//   * cov goes straight from HBM into REGISTERS as the 36 upper-triangle 8 x 8 tiles in the tensor-core accumulator
+//     layout (one 16-byte load per tile and lane: the upper triangle of the row-major matrix is what the reference
+//     reads) and the rank-8 trailing updates (DMMA m8n8k4) never touch memory;
+//   * k is a template parameter (k = 8 NT): loops are fully unrolled, every shared-memory offset is an immediate;
+//   * cov = U~^T D U~ (square-root free, U~ unit upper) on 8-row panels.  A finished panel is written to shared memory
+//     once (it is needed there as tensor-core fragments anyway) and read back in the LANE = COLUMN layout: lane j holds
+//     column j of the panel, the 8 pivots are eliminated by row operations whose only communication is a warp shuffle
+//     of the pivot row - no 8 x 8 factor replicated in all lanes, no explicit inverse, no tensor-core panel solve, no
+//     rsqrt on the chain (the update of a pivot uses 1 / d: reciprocal seed + two Newton steps);
+//   * look-ahead inside the single instruction stream: the update of step p is split into the tile row the next
+//     elimination needs and the rest, which is issued a few tiles at a time between the pivots of that elimination;
+//   * 8 x 8 tiles are stored dense (64 doubles) with an XOR swizzle of the rows and a row swap in odd tile columns:
+//     accumulator, fragment, transposed-fragment and lane = column accesses are all bank-conflict free without padding;
 //   * the projection is reformulated around the factor so that cov G^T (2 k^2 k2 flops) is never formed:
-//         V = L^T G^T,  G cov G^T = V^T V,  G y = G mean + V^T z,  x = mean + L (z + V alpha)
-//     (same algebra as the shared-covariance path's W = G L, hyperplane.c) - V on the tensor cores, x by row dot products.
+//         V = sqrt(D) U~ G^T,  G cov G^T = V^T V,  G y = G mean + V^T z,  x = mean + U~^T sqrt(D) (z + V alpha)
+//     (same algebra as the shared-covariance path's W = G L, hyperplane.c) - V on the tensor cores, x by column dot products.
 // Error codes follow the reference: cov not PD -> pivot index, out untouched; G cov G^T not PD -> its
-// pivot index and the unprojected y = mean + L z.
-// Handles k in {64} (NT = 8), k2 <= 4, dense row-major cov (upper triangle read); every other shape keeps
-// the generic kernel (small_batched.cu).
+// pivot index and the unprojected y.  Handles k = 64 (NT = 8), k2 <= 4, dense row-major cov, 16-byte aligned; every
+// other shape keeps the generic kernel (small_batched.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -67,104 +72,116 @@ __device__ __forceinline__ double fast_rcp(double x)
 }
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// Shared-memory map of one problem (doubles).  Panel p holds L[8p.., 8p..8p+7] as dense 8-double rows; element
-// (row i, column c of the panel) sits at row * 8 + (c ^ sw(i)), sw(i) = 4 * ((i >> 1) & 1): with that XOR the
-// tensor-core fragment patterns (row g / column t4, and the transposed one) touch 16 distinct 8-byte bank pairs per
-// half-warp, and the 16-byte accumulator accesses 8 distinct 16-byte slots per quarter-warp.
+// Shared-memory map of one problem (doubles).  Tile (p, tj), p <= tj, of the factor is a dense block of 64 doubles at
+// 64 * tid(p, tj); its element (r, c) sits at pr * 8 + (c ^ sw(pr)) with pr = r ^ (tj & 1) and sw(pr) = 4 * ((pr >> 1) & 1).
 template <int NT>
 struct Geo {
     static constexpr int K = 8 * NT;
-    static constexpr int RS = (K + 31) / 32;  // rows per lane
-    static __host__ __device__ constexpr int off(int p) { return 8 * (K * p - 4 * p * (p - 1)); }
-    static constexpr int GM = 8 * (K * NT - 4 * NT * (NT - 1));  // [K][8]: G^T (cols 0-3) | mean (4) | z (5) | 0 0, later V in 0-3
-    static constexpr int WV = GM + 8 * K;                        // [K]   w = z + V alpha
-    static constexpr int SCR = WV + K;                           // [2][64] two 8 x 8 result tiles
+    static constexpr int CS = (K + 31) / 32;  // columns per lane
+    static __host__ __device__ constexpr int tid(int p, int tj) { return p * NT - p * (p - 1) / 2 + (tj - p); }
+    static constexpr int NTILES = NT * (NT + 1) / 2;
+    static constexpr int GM = 64 * NTILES;  // [K][8]: G^T (cols 0-3) | mean (4) | z (5) | 0 0, later V in cols 0-3
+    static constexpr int WV = GM + 8 * K;   // [K]    d, then sqrt(d), then sqrt(d) w
+    static constexpr int SCR = WV + K;      // [2][64] two 8 x 8 result tiles
     static constexpr int TOTAL = SCR + 128;
 };
 
 // PROF (HTN_SMALL_PROF=1, development only): lane 0 of every warp adds the clock64() span of each phase to prof[]
-#define PHASE(i)                                                                       \
-    if (PROF) {                                                                        \
-        const long long t_now = clock64();                                             \
-        if (lane == 0) atomicAdd((unsigned long long*)&prof[i], (unsigned long long)(t_now - t_prev)); \
-        t_prev = t_now;                                                                \
+#define PHASE(i)                                                                                              \
+    if (PROF) {                                                                                               \
+        const long long t_now = clock64();                                                                    \
+        if (lane == 0) atomicAdd((unsigned long long*)&prof[i], (unsigned long long)(t_now - t_prev));        \
+        t_prev = t_now;                                                                                       \
     }
 
 template <int NT, bool PROF>
-__global__ void __launch_bounds__(32, 9)
+__global__ void __launch_bounds__(32, 8)
 ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const double* __restrict__ cov,
                const double* __restrict__ gm, const double* __restrict__ rv, const double* __restrict__ zs,
-               double* __restrict__ out, int* __restrict__ info, long long* prof)
+               double* __restrict__ out, int* __restrict__ info, unsigned* __restrict__ next, long long* prof)
 {
     using G = Geo<NT>;
-    constexpr int K = G::K, RS = G::RS;
+    constexpr int K = G::K, CS = G::CS;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x;
     const int g = lane >> 2, t4 = lane & 3;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
 
-    // ---- lane constants (byte offsets) ----
-    // fragment "row pattern": element (row g, column t4 + 4 s) of an 8 x 8 tile
-    const int swg = 4 * ((g >> 1) & 1);
-    const unsigned rf0 = 8u * (unsigned)(g * 8 + (t4 ^ swg)), rf1 = 8u * (unsigned)(g * 8 + ((t4 + 4) ^ swg));
-    // fragment "transposed pattern": element (row t4 + 4 s, column g); s = 1 is 4 rows = 256 bytes further
-    const unsigned tf0 = 8u * (unsigned)(t4 * 8 + (g ^ (4 * ((t4 >> 1) & 1))));
-    // accumulator pattern: elements (row g, columns 2 t4, 2 t4 + 1), one 16-byte access
-    const unsigned cf = 8u * (unsigned)(g * 8 + ((2 * t4) ^ swg));
-    // row pattern of the elimination: lane = row i = lane + 32 rs; columns 0-3 at lo, 4-7 at hi (swizzled halves)
-    unsigned row_lo[RS], row_hi[RS];
+    // ---- lane constants (offsets in doubles inside a tile), for even [0] and odd [1] tile columns ----
+    const int swg = 4 * ((g >> 1) & 1), swt = 4 * ((t4 >> 1) & 1);
+    int cf[2], tf[2], rf0[2], rf1[2];
 #pragma unroll
-    for (int rs = 0; rs < RS; rs++) {
+    for (int e = 0; e < 2; e++) {
+        cf[e] = (g ^ e) * 8 + ((2 * t4) ^ swg);        // accumulator pattern: (row g, columns 2 t4, 2 t4 + 1), 16 bytes
+        tf[e] = (t4 ^ e) * 8 + (g ^ swt);              // transposed fragment: (row t4 + 4 s, column g); s = 1: + 32
+        rf0[e] = (g ^ e) * 8 + (t4 ^ swg);             // row fragment: (row g, column t4 + 4 s)
+        rf1[e] = (g ^ e) * 8 + ((t4 + 4) ^ swg);
+    }
+    // lane = column layout: column j = lane + 32 cs lives in tile column tj = j >> 3 (parity ej), column cj = j & 7.
+    // Row c of that tile: (c ^ ej) * 8 + (cj ^ sw(c)); four lane constants per column set cover the eight rows:
+    // colA[cs][2 * ((c >> 1) & 1) + (c & 1)] + 8 * (c & ~1)... kept simple: one offset per row, 8 registers per set.
+    int col[CS][8];
+#pragma unroll
+    for (int cs = 0; cs < CS; cs++) {
+        const int j = lane + 32 * cs, ej = (j >> 3) & 1, cj = j & 7;
+#pragma unroll
+        for (int c = 0; c < 8; c++) col[cs][c] = 64 * (j >> 3) + (c ^ ej) * 8 + (cj ^ (4 * ((c >> 1) & 1)));
+    }
+    // GM (row = variable i, 8 columns, swizzled by the row): lane = row i = lane + 32 rs: columns 0-3 at lo, 4-7 at hi
+    int row_lo[CS], row_hi[CS];
+#pragma unroll
+    for (int rs = 0; rs < CS; rs++) {
         const int i = lane + 32 * rs;
         const int sw = 4 * ((i >> 1) & 1);
-        row_lo[rs] = 8u * (unsigned)(i * 8 + sw);
-        row_hi[rs] = 8u * (unsigned)(i * 8 + (4 - sw));
+        row_lo[rs] = i * 8 + sw;
+        row_hi[rs] = i * 8 + (4 - sw);
     }
+    const int gtf = t4 * 8 + (g ^ swt);  // transposed fragment of GM rows (no tile parity there)
+    const int gcf = g * 8 + ((2 * t4) ^ swg);
     // zero the region once: GM columns that are never written must read as zero for the tensor-core passes
     for (int idx = lane; idx < G::TOTAL; idx += 32) sm[idx] = 0.0;
     __syncwarp();
 
     long long t_prev = PROF ? clock64() : 0;
-    for (size_t pb = blockIdx.x; pb < nproblems; pb += gridDim.x) {
+    for (;;) {
+        // dynamic distribution: the SM's schedulers hold 3 / 2 / 2 / 2 of the nine warps, a static deal would leave the
+        // partitions with two warps idle at the end
+        unsigned pbu = 0;
+        if (lane == 0) pbu = atomicAdd(next, 1u);
+        pbu = __shfl_sync(0xffffffffu, pbu, 0);
+        if ((size_t)pbu >= nproblems) break;
+        const size_t pb = pbu;
         const double* covp = cov + pb * (size_t)K * K;
         const double* gp = gm + pb * (size_t)k2 * K;
-        // ---- stage: cov[i][j], j >= i (the upper triangle of the row-major matrix) lands at L position
-        // (row j, column i): lane = j, one 8-byte asynchronous copy per element, 256 contiguous bytes per warp request
+        // ---- cov: the 36 upper tiles straight into registers, accumulator layout, 16 bytes per tile and lane ----
+        double2 c[NT][NT];
+        {
+            const double* src = covp + g * K + 2 * t4;
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
-            const int j = lane + 32 * rs;
-            const double* src = covp + j;
+            for (int ti = 0; ti < NT; ti++)
 #pragma unroll
-            for (int i = 0; i < K; i++) {
-                if (i <= 32 * rs + 31) {  // compile-time: this row set has elements j >= i
-                    const int p = i >> 3, c = i & 7;
-                    // (c ^ sw(j)) = c + sw for c < 4, c - sw for c >= 4
-                    const unsigned dst = sbase + (c < 4 ? row_lo[rs] : row_hi[rs]) +
-                                         8u * (unsigned)(G::off(p) - 64 * p + (c & 3));
-                    if (j >= i && j < K) cp_async8(dst, src + (size_t)i * K);
-                }
-            }
+                for (int tj = ti; tj < NT; tj++) c[ti][tj] = __ldg(reinterpret_cast<const double2*>(src + 8 * ti * K + 8 * tj));
         }
-        // G^T -> GM columns 0..k2-1, mean -> column 4, z -> column 5 (lane = row)
-        double mreg[RS];
+        // G^T -> GM columns 0..k2-1, mean -> column 4, z -> column 5 (lane = row), asynchronous 8-byte copies
+        double mreg[CS];
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
+        for (int rs = 0; rs < CS; rs++) {
             const int i = lane + 32 * rs;
             mreg[rs] = 0.0;
             if (i < K) {
                 const unsigned rowb = sbase + 8u * (unsigned)G::GM;
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if (c < k2) cp_async8(rowb + row_lo[rs] + 8u * c, gp + (size_t)c * K + i);
-                cp_async8(rowb + row_hi[rs], mean + pb * (size_t)K + i);          // column 4
-                cp_async8(rowb + row_hi[rs] + 8u, zs + pb * (size_t)K + i);       // column 5
+                for (int cc = 0; cc < 4; cc++)
+                    if (cc < k2) cp_async8(rowb + 8u * (unsigned)(row_lo[rs] + cc), gp + (size_t)cc * K + i);
+                cp_async8(rowb + 8u * (unsigned)row_hi[rs], mean + pb * (size_t)K + i);        // column 4
+                cp_async8(rowb + 8u * (unsigned)(row_hi[rs] + 1), zs + pb * (size_t)K + i);    // column 5
                 mreg[rs] = mean[pb * (size_t)K + i];
             }
         }
         double rreg[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < k2) rreg[c] = rv[pb * (size_t)k2 + c];
+        for (int cc = 0; cc < 4; cc++)
+            if (cc < k2) rreg[cc] = rv[pb * (size_t)k2 + cc];
         asm volatile("cp.async.commit_group;\n" ::);
         PHASE(0)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -179,146 +196,124 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             for (int u = 0; u < 4; u++) acc[u] = make_double2(0.0, 0.0);
 #pragma unroll
             for (int q = 0; q < K / 4; q++) {  // four independent accumulator chains
-                const double f = sm[G::GM + 32 * q + (tf0 >> 3)];
+                const double f = sm[G::GM + 32 * q + gtf];
                 dmma(acc[q & 3].x, acc[q & 3].y, f, f);
             }
-            *reinterpret_cast<double2*>(&sm[G::SCR + (cf >> 3)]) =
+            *reinterpret_cast<double2*>(&sm[G::SCR + gcf]) =
                 make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
             __syncwarp();
 #pragma unroll
             for (int a = 0; a < 4; a++) gmean[a] = sm[G::SCR + a * 8 + (4 ^ (4 * ((a >> 1) & 1)))];
         }
-
         PHASE(2)
-        // ---- Cholesky cov = L L^T, panel by panel, with look-ahead inside the single instruction stream: the
-        // rank-8 update of step p is split into the URGENT tiles (block column p + 1: all that the elimination of panel
-        // p + 1 reads) and the DEFERRED ones (block columns >= p + 2), which are issued a few at a time BETWEEN the
-        // pivots of that elimination - independent tensor-core work in the stalls of the 8-pivot dependency chain ----
+
+        // ---- cov = U~^T D U~, panel by panel ----
         int fail = 0;
-        // fragments (row pattern) of the tiles of the panel factorised last: fa = L, fad = -L D (cov = L D L^T: the rank-8
-        // update is C -= (L D) L^T)
+        // transposed fragments of the tiles of the panel factorised last: fa = U~, fad = -D U~ (the rank-8 update is
+        // C(ti, tj) -= U~(p, ti)^T D U~(p, tj))
         double fa[NT][2], fad[NT][2];
 #pragma unroll
         for (int t = 0; t < NT; t++) fa[t][0] = fa[t][1] = fad[t][0] = fad[t][1] = 0.0;
-        auto tile_update = [&](int ti, int tj) {
-            double2* cp = reinterpret_cast<double2*>(&sm[G::off(tj) + 64 * (ti - tj) + (cf >> 3)]);
-            double2 c = *cp;
-            dmma(c.x, c.y, fad[ti][0], fa[tj][0]);
-            dmma(c.x, c.y, fad[ti][1], fa[tj][1]);
-            *cp = c;
-        };
 #pragma unroll
         for (int p = 0; p < NT; p++) {
-            // elimination of panel p in the lane = row layout
-            double v[RS][8];
+            // the panel's tiles leave the registers (accumulator layout) ...
 #pragma unroll
-            for (int rs = 0; rs < RS; rs++) {
-                if (32 * rs + 31 >= 8 * p) {  // compile-time: the row set reaches into the panel
-                    const int i = lane + 32 * rs;
-                    const bool in = i >= 8 * p && i < K;
-                    const int cb = G::off(p) - 64 * p;
-                    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
-                    if (in) {
-                        a0 = *reinterpret_cast<const double2*>(&sm[cb + (row_lo[rs] >> 3)]);
-                        a1 = *reinterpret_cast<const double2*>(&sm[cb + (row_lo[rs] >> 3) + 2]);
-                        a2 = *reinterpret_cast<const double2*>(&sm[cb + (row_hi[rs] >> 3)]);
-                        a3 = *reinterpret_cast<const double2*>(&sm[cb + (row_hi[rs] >> 3) + 2]);
+            for (int tj = p; tj < NT; tj++)
+                *reinterpret_cast<double2*>(&sm[64 * G::tid(p, tj) + cf[tj & 1]]) = c[p][tj];
+            __syncwarp();
+            // ... and come back in the lane = column layout: v[cs][r] = A[8 p + r][j]
+            double v[CS][8];
+#pragma unroll
+            for (int cs = 0; cs < CS; cs++) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[cs][r] = 0.0;
+                if (32 * cs + 31 >= 8 * p) {  // compile-time: the column set reaches into the panel
+                    const int j = lane + 32 * cs;
+                    if (j >= 8 * p && j < K) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) v[cs][r] = sm[64 * (G::tid(p, p) - p) + col[cs][r]];
                     }
-                    v[rs][0] = a0.x; v[rs][1] = a0.y; v[rs][2] = a1.x; v[rs][3] = a1.y;
-                    v[rs][4] = a2.x; v[rs][5] = a2.y; v[rs][6] = a3.x; v[rs][7] = a3.y;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) v[rs][c] = 0.0;
                 }
             }
-            const int rsd = (8 * p) >> 5;  // row set that holds the diagonal block (compile-time after unrolling)
+            const int csd = (8 * p) >> 5;  // column set that holds the diagonal tile (compile-time after unrolling)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                // the chain first: pivot, its reciprocal, the update of the NEXT pivot's column in the diagonal rows
-                const double ajj = shfl(v[rsd][j], (8 * p + j) & 31);
+                // the chain first: pivot, its reciprocal, the update of the NEXT pivot's row in the diagonal columns
+                const double ajj = shfl(v[csd][j], (8 * p + j) & 31);
                 double bc[8];
 #pragma unroll
-                for (int c = j + 1; c < 8; c++) bc[c] = shfl(v[rsd][j], (8 * p + c) & 31);  // a[c][j], unscaled
+                for (int r = j + 1; r < 8; r++) bc[r] = shfl(v[csd][j], (8 * p + r) & 31);  // a[j][8p + r], unscaled
                 const double rcp = fast_rcp(ajj);
-                double t[RS];
+                double t[CS];
 #pragma unroll
-                for (int rs = 0; rs < RS; rs++) t[rs] = v[rs][j] * rcp;
-                if (j + 1 < 8) v[rsd][j + 1] = fma(-t[rsd], bc[j + 1], v[rsd][j + 1]);
+                for (int cs = 0; cs < CS; cs++) t[cs] = v[cs][j] * rcp;
+                if (j + 1 < 8) v[csd][j + 1] = fma(-t[csd], bc[j + 1], v[csd][j + 1]);
 #pragma unroll
-                for (int rs = 0; rs < RS; rs++) {
-                    if (32 * rs + 31 >= 8 * p) {
+                for (int cs = 0; cs < CS; cs++) {
+                    if (32 * cs + 31 >= 8 * p) {
 #pragma unroll
-                        for (int c = j + 1; c < 8; c++)
-                            if (!(rs == rsd && c == j + 1)) v[rs][c] = fma(-t[rs], bc[c], v[rs][c]);
+                        for (int r = j + 1; r < 8; r++)
+                            if (!(cs == csd && r == j + 1)) v[cs][r] = fma(-t[cs], bc[r], v[cs][r]);
                     }
                 }
                 if (ajj <= 0.0 && fail == 0) fail = 8 * p + j + 1;  // NaN passes
-                // square-root free: column j of the UNIT lower factor is a[i][j] / d_j = t, the pivot d_j goes to DV
+                // square-root free: row j of the UNIT upper factor is a[j][.] / d_j = t, the pivot d_j goes to WV
 #pragma unroll
-                for (int rs = 0; rs < RS; rs++)
-                    if (32 * rs + 31 >= 8 * p) v[rs][j] = t[rs];
+                for (int cs = 0; cs < CS; cs++)
+                    if (32 * cs + 31 >= 8 * p) v[cs][j] = t[cs];
                 if (lane == ((8 * p + j) & 31)) sm[G::WV + 8 * p + j] = ajj;
-                // deferred tiles of step p - 1 (block columns >= p + 1), an eighth of them after every pivot
+                // deferred tiles of step p - 1 (tile rows >= p + 1), an eighth of them after every pivot: registers only
                 if (p >= 1) {
                     const int q = p - 1;
                     const int nd = (NT - 2 - q) * (NT - 1 - q) / 2;
                     const int lo = j * nd / 8, hi = (j + 1) * nd / 8;
                     int idx = 0;
 #pragma unroll
-                    for (int tj = q + 2; tj < NT; tj++) {
+                    for (int ti = q + 2; ti < NT; ti++) {
 #pragma unroll
-                        for (int ti = tj; ti < NT; ti++) {
-                            if (idx >= lo && idx < hi) tile_update(ti, tj);
+                        for (int tj = ti; tj < NT; tj++) {
+                            if (idx >= lo && idx < hi) {
+                                dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][0], fa[tj][0]);
+                                dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][1], fa[tj][1]);
+                            }
                             idx++;
                         }
                     }
                 }
             }
-            // rows of the diagonal block: nothing above the diagonal (the products below read whole tiles)
+            // columns of the diagonal tile: nothing below the diagonal (the products below read whole tiles)
 #pragma unroll
-            for (int rs = 0; rs < RS; rs++) {
-                if (32 * rs + 31 >= 8 * p) {
-                    const int i = lane + 32 * rs;
-                    if (rs == rsd) {  // compile-time: only this row set holds rows of the diagonal block
-                        const int r = i - 8 * p;
+            for (int cs = 0; cs < CS; cs++) {
+                if (32 * cs + 31 >= 8 * p) {
+                    const int j = lane + 32 * cs;
+                    if (cs == csd) {  // compile-time: only this column set holds columns of the diagonal tile
+                        const int cc = j - 8 * p;
 #pragma unroll
-                        for (int c = 1; c < 8; c++)
-                            if (r >= 0 && r < c) v[rs][c] = 0.0;
+                        for (int r = 1; r < 8; r++)
+                            if (cc >= 0 && cc < r) v[cs][r] = 0.0;
                     }
-                    if (i >= 8 * p && i < K) {
-                        const int cb = G::off(p) - 64 * p;
-                        *reinterpret_cast<double2*>(&sm[cb + (row_lo[rs] >> 3)]) = make_double2(v[rs][0], v[rs][1]);
-                        *reinterpret_cast<double2*>(&sm[cb + (row_lo[rs] >> 3) + 2]) = make_double2(v[rs][2], v[rs][3]);
-                        *reinterpret_cast<double2*>(&sm[cb + (row_hi[rs] >> 3)]) = make_double2(v[rs][4], v[rs][5]);
-                        *reinterpret_cast<double2*>(&sm[cb + (row_hi[rs] >> 3) + 2]) = make_double2(v[rs][6], v[rs][7]);
+                    if (j >= 8 * p && j < K) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) sm[64 * (G::tid(p, p) - p) + col[cs][r]] = v[cs][r];
                     }
                 }
             }
             __syncwarp();
             PHASE(3)
             if (p + 1 < NT) {
-                // fragments of panel p, then the urgent tiles (block column p + 1): all loads, then two rounds of
-                // independent DMMAs, then the stores
-                const double ds0 = -sm[G::WV + 8 * p + t4], ds1 = -sm[G::WV + 8 * p + 4 + t4];  // -d of the fragment's columns
+                // fragments of panel p, then the urgent tile row p + 1 (all that the next elimination reads)
+                const double ds0 = -sm[G::WV + 8 * p + t4], ds1 = -sm[G::WV + 8 * p + 4 + t4];  // -d of the fragment's rows
 #pragma unroll
                 for (int t = p + 1; t < NT; t++) {
-                    fa[t][0] = sm[G::off(p) + 64 * (t - p) + (rf0 >> 3)];
-                    fa[t][1] = sm[G::off(p) + 64 * (t - p) + (rf1 >> 3)];
+                    fa[t][0] = sm[64 * G::tid(p, t) + tf[t & 1]];
+                    fa[t][1] = sm[64 * G::tid(p, t) + 32 + tf[t & 1]];
                     fad[t][0] = fa[t][0] * ds0;
                     fad[t][1] = fa[t][1] * ds1;
                 }
-                double2 cu[NT];
 #pragma unroll
-                for (int ti = p + 1; ti < NT; ti++)
-                    cu[ti] = *reinterpret_cast<const double2*>(&sm[G::off(p + 1) + 64 * (ti - p - 1) + (cf >> 3)]);
+                for (int tj = p + 1; tj < NT; tj++) dmma(c[p + 1][tj].x, c[p + 1][tj].y, fad[p + 1][0], fa[tj][0]);
 #pragma unroll
-                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, fad[ti][0], fa[p + 1][0]);
-#pragma unroll
-                for (int ti = p + 1; ti < NT; ti++) dmma(cu[ti].x, cu[ti].y, fad[ti][1], fa[p + 1][1]);
-#pragma unroll
-                for (int ti = p + 1; ti < NT; ti++)
-                    *reinterpret_cast<double2*>(&sm[G::off(p + 1) + 64 * (ti - p - 1) + (cf >> 3)]) = cu[ti];
-                __syncwarp();
+                for (int tj = p + 1; tj < NT; tj++) dmma(c[p + 1][tj].x, c[p + 1][tj].y, fad[p + 1][1], fa[tj][1]);
                 PHASE(4)
             }
         }
@@ -327,48 +322,48 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             continue;
         }
 
-        // cov = L D L^T with L unit lower: the Cholesky factor is L sqrt(D).  sd = sqrt(d), lane = row; DV then holds sd
-        double sdreg[RS];
+        // the Cholesky factor is sqrt(D) U~.  sd = sqrt(d), lane = row; WV then holds sd
+        double sdreg[CS];
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
+        for (int rs = 0; rs < CS; rs++) {
             const int i = lane + 32 * rs;
             sdreg[rs] = i < K ? sqrt(sm[G::WV + i]) : 0.0;
         }
         __syncwarp();
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
+        for (int rs = 0; rs < CS; rs++) {
             const int i = lane + 32 * rs;
             if (i < K) sm[G::WV + i] = sdreg[rs];
         }
         __syncwarp();
-        // ---- V = sqrt(D) L^T G^T on the tensor cores: one accumulator per 8 rows of V, all eight chains interleaved;
-        // written over G^T at the end ----
+        // ---- V = sqrt(D) U~ G^T on the tensor cores: one accumulator per 8 rows of V, all chains interleaved; written
+        // over G^T at the end ----
         {
             double2 va[NT];
 #pragma unroll
             for (int tb = 0; tb < NT; tb++) va[tb] = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int ti = 0; ti < NT; ti++) {
-                // A[m][kk] = L[8 ti + kk][8 tb + m] (transposed pattern on panel tb), B[kk][n] = G[n][8 ti + kk]
-                const double b0 = sm[G::GM + 64 * ti + (tf0 >> 3)];
-                const double b1 = sm[G::GM + 64 * ti + 32 + (tf0 >> 3)];
+            for (int tj = 0; tj < NT; tj++) {
+                // A[m][kk] = U~[8 tb + m][8 tj + kk] (row fragment of tile (tb, tj)), B[kk][n] = G[n][8 tj + kk]
+                const double b0 = sm[G::GM + 64 * tj + gtf];
+                const double b1 = sm[G::GM + 64 * tj + 32 + gtf];
                 double a0[NT], a1[NT];
 #pragma unroll
-                for (int tb = 0; tb <= ti; tb++) {
-                    a0[tb] = sm[G::off(tb) + 64 * (ti - tb) + (tf0 >> 3)];
-                    a1[tb] = sm[G::off(tb) + 64 * (ti - tb) + 32 + (tf0 >> 3)];
+                for (int tb = 0; tb <= tj; tb++) {
+                    a0[tb] = sm[64 * G::tid(tb, tj) + rf0[tj & 1]];
+                    a1[tb] = sm[64 * G::tid(tb, tj) + rf1[tj & 1]];
                 }
 #pragma unroll
-                for (int tb = 0; tb <= ti; tb++) dmma(va[tb].x, va[tb].y, a0[tb], b0);
+                for (int tb = 0; tb <= tj; tb++) dmma(va[tb].x, va[tb].y, a0[tb], b0);
 #pragma unroll
-                for (int tb = 0; tb <= ti; tb++) dmma(va[tb].x, va[tb].y, a1[tb], b1);
+                for (int tb = 0; tb <= tj; tb++) dmma(va[tb].x, va[tb].y, a1[tb], b1);
             }
             __syncwarp();  // every lane has read G^T
             if (t4 < 2) {
 #pragma unroll
                 for (int tb = 0; tb < NT; tb++) {
                     const double sdr = sm[G::WV + 8 * tb + g];
-                    *reinterpret_cast<double2*>(&sm[G::GM + 64 * tb + (cf >> 3)]) = make_double2(va[tb].x * sdr, va[tb].y * sdr);
+                    *reinterpret_cast<double2*>(&sm[G::GM + 64 * tb + gcf]) = make_double2(va[tb].x * sdr, va[tb].y * sdr);
                 }
             }
             __syncwarp();
@@ -381,10 +376,10 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             for (int u = 0; u < 4; u++) acc[u] = make_double2(0.0, 0.0);
 #pragma unroll
             for (int q = 0; q < K / 4; q++) {
-                const double f = sm[G::GM + 32 * q + (tf0 >> 3)];
+                const double f = sm[G::GM + 32 * q + gtf];
                 dmma(acc[q & 3].x, acc[q & 3].y, f, f);
             }
-            *reinterpret_cast<double2*>(&sm[G::SCR + 64 + (cf >> 3)]) =
+            *reinterpret_cast<double2*>(&sm[G::SCR + 64 + gcf]) =
                 make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
             __syncwarp();
         }
@@ -420,8 +415,8 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            if (i > j && c > j && c <= i) s[i][c] = fma(-s[i][j], s[c][j], s[i][c]);
+                        for (int cc = 0; cc < 4; cc++)
+                            if (i > j && cc > j && cc <= i) s[i][cc] = fma(-s[i][j], s[cc][j], s[i][cc]);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -444,56 +439,50 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
             }
         }
         PHASE(6)
-        // ---- w = z + V alpha (lane = row) ----
+        // ---- w = sqrt(D) (z + V alpha) (lane = row) ----
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
+        for (int rs = 0; rs < CS; rs++) {
             const int i = lane + 32 * rs;
             if (i < K) {
-                const double2 v01 = *reinterpret_cast<const double2*>(&sm[G::GM + (row_lo[rs] >> 3)]);
-                const double2 v23 = *reinterpret_cast<const double2*>(&sm[G::GM + (row_lo[rs] >> 3) + 2]);
-                double w = sm[G::GM + (row_hi[rs] >> 3) + 1];  // z, column 5
+                const double2 v01 = *reinterpret_cast<const double2*>(&sm[G::GM + row_lo[rs]]);
+                const double2 v23 = *reinterpret_cast<const double2*>(&sm[G::GM + row_lo[rs] + 2]);
+                double w = sm[G::GM + row_hi[rs] + 1];  // z, column 5
                 w = fma(v01.x, al[0], w);
                 w = fma(v01.y, al[1], w);
                 w = fma(v23.x, al[2], w);
                 w = fma(v23.y, al[3], w);
-                sm[G::WV + i] = w * sdreg[rs];  // Cholesky factor times w = L (sqrt(D) w)
+                sm[G::WV + i] = w * sdreg[rs];
             }
         }
         __syncwarp();
-        // ---- x = mean + L (sqrt(D) w): row dot products, lane = row, panel by panel ----
-        double acc[RS];
+        // ---- x = mean + U~^T w: column dot products, lane = column, panel by panel ----
+        double acc[CS];
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) acc[rs] = mreg[rs];
+        for (int cs = 0; cs < CS; cs++) acc[cs] = mreg[cs];
 #pragma unroll
         for (int p = 0; p < NT; p++) {
             const double2 w01 = *reinterpret_cast<const double2*>(&sm[G::WV + 8 * p]);
             const double2 w23 = *reinterpret_cast<const double2*>(&sm[G::WV + 8 * p + 2]);
             const double2 w45 = *reinterpret_cast<const double2*>(&sm[G::WV + 8 * p + 4]);
             const double2 w67 = *reinterpret_cast<const double2*>(&sm[G::WV + 8 * p + 6]);
+            const double wv[8] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y};
 #pragma unroll
-            for (int rs = 0; rs < RS; rs++) {
-                if (32 * rs + 31 >= 8 * p) {
-                    const int i = lane + 32 * rs;
-                    if (i >= 8 * p && i < K) {
-                        const int cb = G::off(p) - 64 * p;
-                        const double2 a0 = *reinterpret_cast<const double2*>(&sm[cb + (row_lo[rs] >> 3)]);
-                        const double2 a1 = *reinterpret_cast<const double2*>(&sm[cb + (row_lo[rs] >> 3) + 2]);
-                        const double2 a2 = *reinterpret_cast<const double2*>(&sm[cb + (row_hi[rs] >> 3)]);
-                        const double2 a3 = *reinterpret_cast<const double2*>(&sm[cb + (row_hi[rs] >> 3) + 2]);
-                        double t = acc[rs];
-                        t = fma(a0.x, w01.x, t); t = fma(a0.y, w01.y, t);
-                        t = fma(a1.x, w23.x, t); t = fma(a1.y, w23.y, t);
-                        t = fma(a2.x, w45.x, t); t = fma(a2.y, w45.y, t);
-                        t = fma(a3.x, w67.x, t); t = fma(a3.y, w67.y, t);
-                        acc[rs] = t;
+            for (int cs = 0; cs < CS; cs++) {
+                if (32 * cs + 31 >= 8 * p) {
+                    const int j = lane + 32 * cs;
+                    if (j >= 8 * p && j < K) {
+                        double t = acc[cs];
+#pragma unroll
+                        for (int r = 0; r < 8; r++) t = fma(sm[64 * (G::tid(p, p) - p) + col[cs][r]], wv[r], t);
+                        acc[cs] = t;
                     }
                 }
             }
         }
 #pragma unroll
-        for (int rs = 0; rs < RS; rs++) {
-            const int i = lane + 32 * rs;
-            if (i < K) out[pb * (size_t)K + i] = acc[rs];
+        for (int cs = 0; cs < CS; cs++) {
+            const int j = lane + 32 * cs;
+            if (j < K) out[pb * (size_t)K + j] = acc[cs];
         }
         if (lane == 0 && info) info[pb] = f2;
         __syncwarp();  // the next problem's asynchronous copies overwrite what this one was still reading
@@ -504,16 +493,18 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
 
 }  // namespace
 
-// returns 1 when the shape is not one this kernel is built for (the caller falls back to the generic kernel)
+// returns 1 when the shape is not one this kernel is built for (the caller falls back to the generic kernel).
+// counter: one zero-initialised unsigned on the device (the kernel's dynamic problem queue)
 extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int k2, const double* mean,
                                   const double* cov, const double* g, const double* r, const double* zs, double* out,
-                                  int* info)
+                                  int* info, unsigned* counter)
 {
     if (nproblems == 0) return 0;
-    if (k != 64 || k2 < 1 || k2 > 4) return 1;
+    if (k != 64 || k2 < 1 || k2 > 4 || nproblems > 0xfffffff0u || counter == nullptr) return 1;
     static const bool off = getenv("HTN_SMALL_IMPL") != nullptr && atoi(getenv("HTN_SMALL_IMPL")) == 0;
     if (off) return 1;
-    if ((((uintptr_t)mean | (uintptr_t)cov | (uintptr_t)g | (uintptr_t)r | (uintptr_t)zs | (uintptr_t)out) & 7) != 0) return 1;
+    if ((((uintptr_t)mean | (uintptr_t)g | (uintptr_t)r | (uintptr_t)zs | (uintptr_t)out) & 7) != 0 || ((uintptr_t)cov & 15) != 0)
+        return 1;
     static const bool want_prof = getenv("HTN_SMALL_PROF") != nullptr;
     auto kern = want_prof ? ht_warp_kernel<8, true> : ht_warp_kernel<8, false>;
     const size_t smem = (size_t)Geo<8>::TOTAL * sizeof(double);
@@ -531,17 +522,20 @@ extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int 
         if (cudaMalloc(&prof, 16 * sizeof(long long)) != cudaSuccess) return -201;
         cudaMemsetAsync(prof, 0, 16 * sizeof(long long), st);
     }
-    kern<<<(unsigned)grid, 32, smem, st>>>(nproblems, k2, mean, cov, g, r, zs, out, info, prof);
+    kern<<<(unsigned)grid, 32, smem, st>>>(nproblems, k2, mean, cov, g, r, zs, out, info, counter, prof);
     htnk_count_launch();
     if (want_prof) {  // development aid: synchronous on purpose
         long long hp[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost);
         cudaFree(prof);
-        static const char* names[8] = {"issue-stage", "wait-stage", "c0", "elim(+deferred)", "urgent", "V", "S+solve", "w+x+out"};
+        static const char* names[8] = {"load+stage", "wait", "c0", "panel store+elim(+deferred)", "frags+urgent", "sd+V", "S+solve", "w+x+out"};
         fprintf(stderr, "[ht_warp] %d warps/SM (%zu B smem), clk per problem:", per_sm, smem);
         double tot = 0;
-        for (int i = 0; i < 8; i++) { fprintf(stderr, " %s %.0f", names[i], (double)hp[i] / (double)nproblems); tot += (double)hp[i] / (double)nproblems; }
+        for (int i = 0; i < 8; i++) {
+            fprintf(stderr, " %s %.0f", names[i], (double)hp[i] / (double)nproblems);
+            tot += (double)hp[i] / (double)nproblems;
+        }
         fprintf(stderr, " | total %.0f\n", tot);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -201;

@@ -438,9 +438,16 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
             }
             if (!rc) {
                 /* the warp-per-problem kernel for the shapes it is specialised for, else the generic CTA-per-problem one */
-                rc = (diag || (flags & HTN_FLAG_COLMAJOR))
-                         ? 1
-                         : htnk_ht_small_warp(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, out, info_dev);
+                unsigned* ctr = NULL;
+                rc = 1;
+                if (!diag && !(flags & HTN_FLAG_COLMAJOR) && k == 64 && k2 <= 4) {
+                    rc = htn_dalloc(ctx, (void**)&ctr, sizeof(unsigned));
+                    if (!rc && cudaMemsetAsync(ctr, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = HTN_E_CUDA;
+                    if (!rc)
+                        rc = htnk_ht_small_warp(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, out, info_dev,
+                                                ctr);
+                    htn_dfree(ctx, ctr);
+                }
                 if (rc == 1)
                     rc = htnk_ht_small_batched(ctx->stream, nsamples, (int)k, (int)k2, mean, cov, g, r, zs, diag,
                                                (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
