@@ -80,6 +80,11 @@ struct Geo {
     static constexpr int CS = (K + 31) / 32;  // columns per lane
     static __host__ __device__ constexpr int tid(int p, int tj) { return p * NT - p * (p - 1) / 2 + (tj - p); }
     static constexpr int NTILES = NT * (NT + 1) / 2;
+    // position of tile (ti, tj) among the deferred tiles of step q (tile rows q + 2 .. NT - 1, row by row)
+    static __host__ __device__ constexpr int didx(int q, int ti, int tj)
+    {
+        return (ti - q - 2) * NT - ((ti - 1) * ti - (q + 1) * (q + 2)) / 2 + (tj - ti);
+    }
     static constexpr int GM = 64 * NTILES;  // [K][8]: G^T (cols 0-3) | mean (4) | z (5) | 0 0, later V in cols 0-3
     static constexpr int WV = GM + 8 * K;   // [K]    d, then sqrt(d), then sqrt(d) w
     static constexpr int SCR = WV + K;      // [2][64] two 8 x 8 result tiles
@@ -143,14 +148,17 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
     __syncwarp();
 
     long long t_prev = PROF ? clock64() : 0;
+    // Dynamic distribution (a static deal would leave the less loaded scheduler partitions idle at the end), one problem
+    // AHEAD: the index of the next problem is drawn while the current one is being loaded, so that the atomic's round trip
+    // is never waited for and the next problem's covariance can be prefetched into L2 behind the current one's loads.
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(next, 1u);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
     for (;;) {
-        // dynamic distribution: the SM's schedulers hold 3 / 2 / 2 / 2 of the nine warps, a static deal would leave the
-        // partitions with two warps idle at the end
-        unsigned pbu = 0;
-        if (lane == 0) pbu = atomicAdd(next, 1u);
-        pbu = __shfl_sync(0xffffffffu, pbu, 0);
+        const unsigned pbu = nxt;
         if ((size_t)pbu >= nproblems) break;
         const size_t pb = pbu;
+        if (lane == 0) nxt = atomicAdd(next, 1u);  // consumed (shuffled) only after this problem's loads are in flight
         const double* covp = cov + pb * (size_t)K * K;
         const double* gp = gm + pb * (size_t)k2 * K;
         // ---- cov: the 36 upper tiles straight into registers, accumulator layout, 16 bytes per tile and lane ----
@@ -183,6 +191,21 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
         for (int cc = 0; cc < 4; cc++)
             if (cc < k2) rreg[cc] = rv[pb * (size_t)k2 + cc];
         asm volatile("cp.async.commit_group;\n" ::);
+        // the next problem: its index, and its upper triangle into L2 (lane = rows lane and lane + 32, 128-byte lines)
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        if ((size_t)nxt < nproblems) {
+            const char* nb = reinterpret_cast<const char*>(cov + (size_t)nxt * K * K);
+#pragma unroll
+            for (int rs = 0; rs < CS; rs++) {
+                const int i = lane + 32 * rs;
+                if (i < K) {
+                    const char* rowp = nb + (size_t)i * K * 8;
+#pragma unroll
+                    for (int ln = 0; ln < K * 8 / 128; ln++)
+                        if (128 * ln + 127 >= i * 8) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(rowp + 128 * ln));
+                }
+            }
+        }
         PHASE(0)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncwarp();
@@ -267,16 +290,21 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
                     const int q = p - 1;
                     const int nd = (NT - 2 - q) * (NT - 1 - q) / 2;
                     const int lo = j * nd / 8, hi = (j + 1) * nd / 8;
-                    int idx = 0;
+                    // the chunk's first k-steps, then its second ones: no DMMA waits for the one before it
 #pragma unroll
                     for (int ti = q + 2; ti < NT; ti++) {
 #pragma unroll
                         for (int tj = ti; tj < NT; tj++) {
-                            if (idx >= lo && idx < hi) {
-                                dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][0], fa[tj][0]);
-                                dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][1], fa[tj][1]);
-                            }
-                            idx++;
+                            const int idx = G::didx(q, ti, tj);
+                            if (idx >= lo && idx < hi) dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][0], fa[tj][0]);
+                        }
+                    }
+#pragma unroll
+                    for (int ti = q + 2; ti < NT; ti++) {
+#pragma unroll
+                        for (int tj = ti; tj < NT; tj++) {
+                            const int idx = G::didx(q, ti, tj);
+                            if (idx >= lo && idx < hi) dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][1], fa[tj][1]);
                         }
                     }
                 }
@@ -327,7 +355,8 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
 #pragma unroll
         for (int rs = 0; rs < CS; rs++) {
             const int i = lane + 32 * rs;
-            sdreg[rs] = i < K ? sqrt(sm[G::WV + i]) : 0.0;
+            const double dv = i < K ? sm[G::WV + i] : 1.0;
+            sdreg[rs] = dv * fast_rsqrt(dv);  // sqrt(d), d > 0 here
         }
         __syncwarp();
 #pragma unroll
