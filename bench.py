@@ -228,32 +228,29 @@ def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, s
     res = {"value": None}
     ok_local = 1
     outs = pg = full = None
-    try:
-        outs = [first_buffer if first_buffer is not None else torch.empty((rows, k), dtype=torch.float64, device=dev),
-                torch.empty((rows, k), dtype=torch.float64, device=dev)]
-    except RuntimeError:
-        ok_local = 0
-    flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if not bool(flag.item()):
-        return {"value": None, "skipped": "shard buffers did not fit"}
-    transport = "copy engines: one cudaMemcpyAsync per peer shard on dedicated streams into peer-mapped (CUDA IPC) buffers"
+    transport = ("copy engines: one cudaMemcpyAsync per peer shard on dedicated streams into peer-mapped, double-buffered "
+                 "receive buffers (torch symmetric memory); the sampler writes its shard in place; no kernel, no SM "
+                 "taken from the sampling GEMM")
     try:
         if os.environ.get("HTN_BENCH_GATHER", "peer") != "peer":
             raise RuntimeError("NCCL requested")
-        pg = h.PeerGather(rows, k, dev)
-        full = pg.full
+        pg = h.PeerGather(rows, k, dev, nbuf=2)
         ok_local = 1
     except Exception as ex:     # noqa: BLE001
         ok_local = 0
         res["peer_gather_error"] = repr(ex)[:200]
     flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if not bool(flag.item()):
-        if pg is not None:
-            pg = None
+    if bool(flag.item()):
+        # the sampler writes its shard straight into its slice of the (double-buffered) receive buffer: no local copy
+        outs = [pg.own(0), pg.own(1)]
+        fulls = [pg.full[0], pg.full[1]]
+    else:
+        pg = None
         transport = "ncclAllGather (all_gather_into_tensor) on NCCL's stream"
         try:
+            outs = [first_buffer if first_buffer is not None else torch.empty((rows, k), dtype=torch.float64, device=dev),
+                    torch.empty((rows, k), dtype=torch.float64, device=dev)]
             full = torch.empty((world * rows, k), dtype=torch.float64, device=dev)
             ok_local = 1
         except RuntimeError:
@@ -261,7 +258,8 @@ def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, s
         flag = torch.tensor([ok_local], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if not bool(flag.item()):
-            return {"value": None, "skipped": "receive buffer did not fit"}
+            return {"value": None, "skipped": "shard / receive buffers did not fit"}
+        fulls = [full, full]
     pend = [None, None]
 
     def step(i):
@@ -273,7 +271,7 @@ def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, s
                 pend[i & 1].wait()
         sample_into(i, o)
         if pg is not None:
-            pend[i & 1] = pg.push(o)
+            pend[i & 1] = pg.push(i & 1)
         else:
             pend[i & 1] = dist.all_gather_into_tensor(full.view(-1), o.view(-1), async_op=True)
 
@@ -306,6 +304,7 @@ def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, s
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     last_i = warm + steps - 1
     last = outs[last_i & 1]
+    full = fulls[last_i & 1]
     # checks on the last step's batch
     own = bool(torch.equal(full[rank * rows:(rank + 1) * rows], last))
     sums = torch.zeros(world, dtype=torch.float64, device=dev)
