@@ -58,9 +58,13 @@ done:
     return rc;
 }
 
+/* side stream of the super-panel look-ahead (one per host thread and device, kept) */
+static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_chain, ev_b; } sl = {-1, NULL, NULL, NULL};
+
 int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
 {
     int rc = 0;
+    int sla_used = 0; /* work was queued on the look-ahead side stream: join it before returning, whatever happened */
     const int n = fa->n;
     const size_t ld = fa->ld;
     /* Two-level blocking.  Super-panels of W columns are factorised left-looking INSIDE the panel (block
@@ -142,6 +146,36 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
         if (fa->solves) HTN_TRY(htnk_trtri_batched(ctx->stream, fa->f, ld, n, fa->dinv, fa->dinvt));
         goto done;
     }
+    /* Super-panel LOOK-AHEAD (n >= HTN_POTRF_SLA, default 4097): the rank-W update of super-panel J is split into (a) the
+     * columns of super-panel J + 1 - all that its factorisation chain reads - on the caller's stream, and (b) the rest
+     * of the trailing matrix on a LOW-PRIORITY side stream.  The chain of super-panel J + 1 (64 fused panel launches of
+     * ~50 us at n = 8192: 3.5 ms of latency-bound work on a few SMs) then runs BESIDE (b), the one kernel that can fill the
+     * device.  (a) of J + 1 writes what (b) of J writes, so it waits for it; nothing else is shared. */
+    static int sla_min = -1;
+    if (sla_min < 0) {
+        const char* e = getenv("HTN_POTRF_SLA");
+        sla_min = e ? atoi(e) : 4097;
+    }
+    int use_sla = n >= sla_min && n > 2 * W;
+    if (use_sla && sl.device != ctx->device) {
+        if (sl.device >= 0) {
+            cudaEventDestroy(sl.ev_chain);
+            cudaEventDestroy(sl.ev_b);
+            cudaStreamDestroy(sl.side);
+            sl.device = -1;
+        }
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio); /* numerically largest = lowest priority */
+        if (cudaStreamCreateWithPriority(&sl.side, cudaStreamNonBlocking, lo_prio) == cudaSuccess &&
+            cudaEventCreateWithFlags(&sl.ev_chain, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&sl.ev_b, cudaEventDisableTiming) == cudaSuccess)
+            sl.device = ctx->device;
+        else {
+            cudaGetLastError();
+            use_sla = 0; /* no side stream: the plain order below */
+        }
+    }
+    int pending_b = 0;
     for (int J0 = 0; J0 < n; J0 += W) {
         const int J1 = J0 + W < n ? J0 + W : n;
         for (int j0 = J0; j0 < J1; j0 += HTN_NB) {
@@ -161,14 +195,44 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
                                        fa->rdiag + j0));
         }
         const int R = n - J1;
-        if (R > 0) /* trailing update: A[J1:, J1:] -= L[J1:, J0:J1] * L[J1:, J0:J1]^T on the lower tiles (DMMA) */
-            HTN_TRY(htnk_gemm_tn(ctx->stream, R, R, J1 - J0, -1.0, fa->f + (size_t)J1 * ld + J0, ld,
-                                 fa->f + (size_t)J1 * ld + J0, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld, NULL,
+        if (R <= 0) break;
+        const double* pan = fa->f + (size_t)J1 * ld + J0; /* L[J1:, J0:J1] */
+        if (!use_sla) { /* trailing update: A[J1:, J1:] -= L[J1:, J0:J1] * L[J1:, J0:J1]^T on the lower tiles (DMMA) */
+            HTN_TRY(htnk_gemm_tn(ctx->stream, R, R, J1 - J0, -1.0, pan, ld, pan, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld, NULL,
                                  HTNK_GEMM_C_LOWER, 0, 0, 0));
+            continue;
+        }
+        const int J2 = J1 + W < n ? J1 + W : n, R2 = n - J2;
+        if (R2 > 0) HTN_CUDA(cudaEventRecord(sl.ev_chain, ctx->stream));
+        if (pending_b) { /* (b) of the previous super-panel wrote the block (a) is about to update */
+            HTN_CUDA(cudaStreamWaitEvent(ctx->stream, sl.ev_b, 0));
+            pending_b = 0;
+        }
+        /* (a) A[J1:, J1:J2] -= L[J1:, J] L[J1:J2, J]^T: the rows from J1 on, the next super-panel's columns */
+        HTN_TRY(htnk_gemm_tn(ctx->stream, R, J2 - J1, J1 - J0, -1.0, pan, ld, pan, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld, NULL,
+                             HTNK_GEMM_C_LOWER, 0, 0, 0));
+        if (R2 > 0) { /* (b) A[J2:, J2:] -= L[J2:, J] L[J2:, J]^T, beside the next chain */
+            const double* pan2 = fa->f + (size_t)J2 * ld + J0;
+            HTN_CUDA(cudaStreamWaitEvent(sl.side, sl.ev_chain, 0));
+            sla_used = 1;
+            rc = htnk_gemm_tn(sl.side, R2, R2, J1 - J0, -1.0, pan2, ld, pan2, ld, 1.0, fa->f + (size_t)J2 * ld + J2, ld, NULL,
+                              HTNK_GEMM_C_LOWER, 0, 0, 0);
+            if (!rc && cudaEventRecord(sl.ev_b, sl.side) != cudaSuccess) rc = HTN_E_CUDA;
+            pending_b = 1; /* joined below even on failure: the side stream may have work queued */
+            if (rc) break;
+        }
     }
+    if (rc) goto done;
     /* inverses of the diagonal blocks, all at once, only when blocked solves will follow */
+    if (sla_used) { /* the factor is complete on the caller's stream only once (b) of the last super-panels has landed */
+        if (cudaEventRecord(sl.ev_b, sl.side) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, sl.ev_b, 0) != cudaSuccess)
+            cudaStreamSynchronize(sl.side);
+        sla_used = 0;
+    }
     if (fa->solves) HTN_TRY(htnk_trtri_batched(ctx->stream, fa->f, ld, n, fa->dinv, fa->dinvt));
 done:
+    if (sla_used && (cudaEventRecord(sl.ev_b, sl.side) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, sl.ev_b, 0) != cudaSuccess))
+        cudaStreamSynchronize(sl.side); /* error exit: never leave the side stream running under buffers about to be freed */
     return rc;
 }
 
