@@ -137,6 +137,121 @@ normal_fill_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size
     }  // groups
 }
 
+// ---- warp-cooperative SINGLE-STREAM ziggurat (few streams: structured precision with a small batch, the
+// single-sample API) ----
+// One warp draws ONE stream: lane l decodes the stream's word pos + l.  PCG64 here is two 64-bit LCGs
+// (src/htnorm_pcg32_minimal.h:19-29), so lane l JUMPS AHEAD by l steps with a precomputed (multiplier, increment
+// factor) pair: state_l = A_l * state + C_l * inc, A_l = M^l, C_l = 1 + M + ... + M^(l-1).  Xoroshiro128+ has no cheap
+// jump: every lane steps the generator 32 times and keeps the word and the state of its own step.
+// The 32 candidates run the table-lookup fast path together; a ballot finds the FIRST rejecting lane f (1.5 % of words):
+// the normals of lanes < f stand, lane f's wedge / tail test is resolved by the whole warp on the (uniform) state after
+// word f - it consumes further words exactly as src/htnorm_distributions.c:38-52 does - and the warp re-bases on the
+// state it leaves.  The sequence of generator calls and every accept / reject decision are those of the reference's
+// sequential loop (bit-exact, including the per-stream call count).
+template <int GEN>
+__device__ __forceinline__ void coop_words(const GenState& S, int lane, uint64_t jmul, uint64_t jinc, uint64_t& r, GenState& after)
+{
+    if (GEN == 0) {
+        after.s[1] = S.s[1];
+        after.s[3] = S.s[3];
+        after.s[0] = jmul * S.s[0] + jinc * S.s[1];   // the state BEFORE word `lane`
+        after.s[2] = jmul * S.s[2] + jinc * S.s[3];
+        r = gen_next<0>(after);                        // word `lane`; `after` is now the state after it
+    } else {
+        GenState t = S;
+        after = S;
+        r = 0;
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+            const uint64_t w = gen_next<1>(t);
+            if (i == lane) { r = w; after = t; }
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
+{
+    return ((uint64_t)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)v, src);
+}
+
+template <int GEN>
+__global__ void __launch_bounds__(128)
+normal_fill_coop_kernel(const uint64_t* seeds, uint64_t seed0, uint64_t* states, size_t nstreams, int nseg, Seg seg0,
+                        Seg seg1, uint32_t* ndraws)
+{
+    __shared__ uint64_t s_ki[256];
+    __shared__ double s_wi[256], s_fi[256];
+    zig_stage_tables(s_ki, s_wi, s_fi);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nstreams) return;
+    // jump-ahead pair of this lane: (M^lane, 1 + M + ... + M^(lane-1)) mod 2^64
+    uint64_t jmul = 1, jinc = 0;
+    if (GEN == 0) {
+        for (int i = 0; i < lane; i++) {
+            jinc = jinc * 6364136223846793005ULL + 1;
+            jmul *= 6364136223846793005ULL;
+        }
+    }
+    GenState S;
+    stream_begin<GEN>(S, seeds, seed0, states, b);
+    uint32_t ncalls = 0;
+    const size_t n0 = seg0.n, total = n0 + (nseg > 1 ? seg1.n : 0);
+    size_t produced = 0;
+    auto store = [&](size_t j, double z) {  // the j-th normal of the stream (draw order): reverse fill inside its segment
+        const bool first_seg = j < n0;
+        const Seg& sg = first_seg ? seg0 : seg1;
+        const size_t i = sg.n - 1 - (first_seg ? j : j - n0);
+        double v = z;
+        if (sg.div) v = __ddiv_rn(v, sg.div[i]);
+        if (sg.mul) v = __dmul_rn(v, sg.mul[i]);
+        if (sg.add) v = __dadd_rn(sg.add[i], v);
+        sg.out[b * sg.ld + i] = v;
+    };
+    while (produced < total) {
+        uint64_t r;
+        GenState after;
+        coop_words<GEN>(S, lane, jmul, jinc, r, after);
+        ZigDraw d;
+        const bool ok = zig_fast(r, s_ki, s_wi, d);
+        const unsigned rej = __ballot_sync(0xffffffffu, !ok);
+        const int first = rej ? __ffs(rej) - 1 : 32;
+        const size_t remaining = total - produced;
+        const int m = (size_t)first < remaining ? first : (int)remaining;
+        if (lane < m) store(produced + lane, d.x);
+        if ((size_t)first >= remaining || first == 32) {
+            // no rejecting word among the m >= 1 words used (all 32 accepted, or the run ends before the first rejection)
+            S.s[0] = shfl_u64(after.s[0], m - 1);
+            if (GEN == 0) S.s[2] = shfl_u64(after.s[2], m - 1);
+            else S.s[1] = shfl_u64(after.s[1], m - 1);
+            ncalls += (uint32_t)m;
+            produced += (size_t)m;
+            continue;
+        }
+        // word `first` failed the fast test: resolve it on the state after that word, every lane alike (uniform)
+        S.s[0] = shfl_u64(after.s[0], first);
+        if (GEN == 0) S.s[2] = shfl_u64(after.s[2], first);
+        else S.s[1] = shfl_u64(after.s[1], first);
+        const uint64_t rf = shfl_u64(r, first);
+        ZigDraw df;
+        zig_fast(rf, s_ki, s_wi, df);
+        ncalls += (uint32_t)first + 1;
+        double z = 0.0;
+        const bool got = zig_slow<GEN>(S, df, z, ncalls, s_fi);
+        if (got) {
+            if (lane == 0) store(produced + (size_t)first, z);
+            produced += (size_t)first + 1;
+        } else {
+            produced += (size_t)first;
+        }
+    }
+    if (lane == 0) {
+        stream_end<GEN>(S, states, b);
+        if (ndraws) ndraws[b] = ncalls;
+    }
+}
+
 // normals drawn elsewhere (foreign generator, host side): zpre[b * total + off + j] is the j-th draw of
 // stream b; same placement and transforms as normal_fill_kernel's write-out
 __global__ void __launch_bounds__(256)
@@ -218,6 +333,24 @@ extern "C" int htnk_normal_fill(cudaStream_t st, const htnk_streams_t* s, size_t
     Seg a[2] = {{0, nullptr, 0, nullptr, nullptr, nullptr}, {0, nullptr, 0, nullptr, nullptr, nullptr}};
     for (int i = 0; i < nseg && i < 2; i++)
         a[i] = Seg{seg[i].n, seg[i].out, seg[i].ld, seg[i].div, seg[i].mul, seg[i].add};
+    // few streams: one WARP per stream (jump-ahead / ballot / re-base), else one thread per stream.  HTN_RNG_COOP: the
+    // largest stream count that takes the warp-cooperative kernel (0 = never)
+    // (measured, B200: PCG64 256 x 9216 normals 1560 -> 166 us, 4096 x 2500 442 -> 112 us, 1 x 1000 94 -> 25 us, break-even
+    // near 16 k streams; Xoroshiro128+ - 32 sequential steps per round - breaks even near 3 k streams)
+    static long coop_max = -1;
+    if (coop_max < 0) {
+        const char* e = getenv("HTN_RNG_COOP");
+        coop_max = e ? atol(e) : -2;
+    }
+    const long coop_lim = coop_max >= 0 ? coop_max : (s->gen == 0 ? 12288 : 2048);
+    if ((long)nstreams <= coop_lim) {
+        const unsigned grid = (unsigned)((nstreams + 3) / 4);
+        if (s->gen == 0)
+            normal_fill_coop_kernel<0><<<grid, 128, 0, st>>>(s->seeds, s->seed0, s->states, nstreams, nseg, a[0], a[1], ndraws);
+        else
+            normal_fill_coop_kernel<1><<<grid, 128, 0, st>>>(s->seeds, s->seed0, s->states, nstreams, nseg, a[0], a[1], ndraws);
+        return launch_status();
+    }
     static int cfg = -1;  // HTN_RNG_CFG (experiments): 0 = 16 warps x 32-wide tiles, 1 = 24 x 32, 2 = 32 x 16
     if (cfg < 0) {
         const char* e = getenv("HTN_RNG_CFG");
