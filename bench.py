@@ -228,7 +228,7 @@ def gather_leg(torch, dist, h, world, rank, dev, rows, k, sample_into, redraw, s
     res = {"value": None}
     ok_local = 1
     outs = pg = full = None
-    transport = ("copy engines: one cudaMemcpyAsync per peer shard on dedicated streams into peer-mapped, double-buffered "
+    transport = ("copy engines: one cudaMemcpyAsync per peer shard, ring order on one copy stream, into peer-mapped, double-buffered "
                  "receive buffers (torch symmetric memory); the sampler writes its shard in place; no kernel, no SM "
                  "taken from the sampling GEMM")
     try:
