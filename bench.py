@@ -176,7 +176,7 @@ def cpu_baseline(target_seconds=12.0):
     cores = os.cpu_count() or 1
     probe = cpu_reference_run(cores, cores)
     per_round = max(probe["seconds"], 1e-3)
-    rounds = max(1, min(200, int(target_seconds / per_round)))
+    rounds = max(1, min(5000, int(target_seconds / per_round)))
     res = cpu_reference_run(cores * rounds, cores)
     n = res["nsamples"]
     if res["kind"] == "port":
