@@ -26,8 +26,8 @@
 //         V = sqrt(D) U~ G^T,  G cov G^T = V^T V,  G y = G mean + V^T z,  x = mean + U~^T sqrt(D) (z + V alpha)
 //     (same algebra as the shared-covariance path's W = G L, hyperplane.c) - V on the tensor cores, x by column dot products.
 // Error codes follow the reference: cov not PD -> pivot index, out untouched; G cov G^T not PD -> its
-// pivot index and the unprojected y.  Handles k = 64 (NT = 8), k2 <= 4, dense row-major cov, 16-byte aligned; every
-// other shape keeps the generic kernel (small_batched.cu).
+// pivot index and the unprojected y.  Handles k = 8, 16, ..., 64 (one instantiation per NT = k / 8; cfg2 is NT = 8), k2 <= 4,
+// dense row-major cov, 16-byte aligned; every other shape keeps the generic kernel (small_batched.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -529,14 +529,27 @@ extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int 
                                   int* info, unsigned* counter)
 {
     if (nproblems == 0) return 0;
-    if (k != 64 || k2 < 1 || k2 > 4 || nproblems > 0xfffffff0u || counter == nullptr) return 1;
+    if (k < 8 || k > 64 || (k & 7) || k2 < 1 || k2 > 4 || nproblems > 0xfffffff0u || counter == nullptr) return 1;
     static const bool off = getenv("HTN_SMALL_IMPL") != nullptr && atoi(getenv("HTN_SMALL_IMPL")) == 0;
     if (off) return 1;
     if ((((uintptr_t)mean | (uintptr_t)g | (uintptr_t)r | (uintptr_t)zs | (uintptr_t)out) & 7) != 0 || ((uintptr_t)cov & 15) != 0)
         return 1;
     static const bool want_prof = getenv("HTN_SMALL_PROF") != nullptr;
-    auto kern = want_prof ? ht_warp_kernel<8, true> : ht_warp_kernel<8, false>;
-    const size_t smem = (size_t)Geo<8>::TOTAL * sizeof(double);
+    // one instantiation per k = 8 NT (every address in the kernel is a compile-time constant)
+    void (*kern)(size_t, int, const double*, const double*, const double*, const double*, const double*, double*, int*,
+                 unsigned*, long long*) = nullptr;
+    size_t smem = 0;
+    switch (k >> 3) {
+        case 1: kern = ht_warp_kernel<1, false>; smem = Geo<1>::TOTAL; break;
+        case 2: kern = ht_warp_kernel<2, false>; smem = Geo<2>::TOTAL; break;
+        case 3: kern = ht_warp_kernel<3, false>; smem = Geo<3>::TOTAL; break;
+        case 4: kern = ht_warp_kernel<4, false>; smem = Geo<4>::TOTAL; break;
+        case 5: kern = ht_warp_kernel<5, false>; smem = Geo<5>::TOTAL; break;
+        case 6: kern = ht_warp_kernel<6, false>; smem = Geo<6>::TOTAL; break;
+        case 7: kern = ht_warp_kernel<7, false>; smem = Geo<7>::TOTAL; break;
+        default: kern = want_prof ? ht_warp_kernel<8, true> : ht_warp_kernel<8, false>; smem = Geo<8>::TOTAL; break;
+    }
+    smem *= sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -547,13 +560,13 @@ extern "C" int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int 
     size_t grid = (size_t)sms * per_sm;
     if (grid > nproblems) grid = nproblems;
     long long* prof = nullptr;
-    if (want_prof) {
+    if (want_prof && k == 64) {
         if (cudaMalloc(&prof, 16 * sizeof(long long)) != cudaSuccess) return -201;
         cudaMemsetAsync(prof, 0, 16 * sizeof(long long), st);
     }
     kern<<<(unsigned)grid, 32, smem, st>>>(nproblems, k2, mean, cov, g, r, zs, out, info, counter, prof);
     htnk_count_launch();
-    if (want_prof) {  // development aid: synchronous on purpose
+    if (prof) {  // development aid: synchronous on purpose
         long long hp[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost);

@@ -440,7 +440,7 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
                 /* the warp-per-problem kernel for the shapes it is specialised for, else the generic CTA-per-problem one */
                 unsigned* ctr = NULL;
                 rc = 1;
-                if (!diag && !(flags & HTN_FLAG_COLMAJOR) && k == 64 && k2 <= 4) {
+                if (!diag && !(flags & HTN_FLAG_COLMAJOR) && k <= 64 && (k & 7) == 0 && k2 <= 4) {
                     rc = htn_dalloc(ctx, (void**)&ctr, sizeof(unsigned));
                     if (!rc && cudaMemsetAsync(ctr, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = HTN_E_CUDA;
                     if (!rc)

@@ -840,3 +840,21 @@ def test_warp_per_problem_kernel_k64(h, oracle, k2):
     xsym, _ = h.hyperplane_truncated_mvnorm_batch(8, c["mean"][:8], c["cov"][:8], c["g"][:8], c["r"][:8], independent=True,
                                                   seed0=9)
     assert np.array_equal(x[6], xsym[6])
+
+
+@pytest.mark.parametrize("k", [8, 16, 24, 32, 40, 48, 56])
+def test_warp_per_problem_kernel_other_orders(h, oracle, k):
+    """k = 8 NT < 64 takes its own instantiation of the warp-per-problem kernel (one or two column sets per lane, fewer
+    panels): every k2 <= min(4, k), against the oracle, constraint at the 1e-12 bar, a not-PD problem in the middle."""
+    for k2 in (1, 2, 3, 4):
+        P = 700 + k
+        c = cases.ht_independent_case(nproblems=P, k=k, k2=k2, rng_seed=500 + 10 * k + k2)
+        cov = c["cov"].copy()
+        cov[5][k - 1, k - 1] = -3.0
+        x, info = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], cov, c["g"], c["r"], independent=True, seed0=3,
+                                                      raise_on_error=False)
+        xo, io, _ = oracle.hyperplane("pcg64", P, c["mean"], cov, c["g"], c["r"], independent=True, seed0=3)
+        assert np.array_equal(info, io) and info[5] == k and int((info != 0).sum()) == 1
+        ok = np.arange(P) != 5
+        assert rel_err(x[ok], xo[ok]) < REL_TOL, (k, k2)
+        assert constraint_violation(x[ok], c["g"][ok], c["r"][ok]) < RESID_TOL, (k, k2)
