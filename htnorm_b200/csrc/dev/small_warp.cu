@@ -70,7 +70,6 @@ __device__ __forceinline__ double fast_rcp(double x)
     }
     return y;
 }
-__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // Shared-memory map of one problem (doubles).  Tile (p, tj), p <= tj, of the factor is a dense block of 64 doubles at
 // 64 * tid(p, tj); its element (r, c) sits at pr * 8 + (c ^ sw(pr)) with pr = r ^ (tj & 1) and sw(pr) = 4 * ((pr >> 1) & 1).
@@ -262,10 +261,20 @@ ht_warp_kernel(size_t nproblems, int k2, const double* __restrict__ mean, const 
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 // the chain first: pivot, its reciprocal, the update of the NEXT pivot's row in the diagonal columns
-                const double ajj = shfl(v[csd][j], (8 * p + j) & 31);
+                // the pivot row of the diagonal tile (columns 8p + j .. 8p + 7, held by eight lanes) goes through shared
+                // memory: one store, broadcast 16-byte loads - 5 wavefronts instead of the 2 (8 - j) of a shuffle each
+                const int cc = (lane - 8 * p) & 31;
+                double* bcast = &sm[G::SCR + 8 * (j & 1)];
+                if (cc >= j && cc < 8) bcast[cc] = v[csd][j];
+                __syncwarp();
                 double bc[8];
 #pragma unroll
-                for (int r = j + 1; r < 8; r++) bc[r] = shfl(v[csd][j], (8 * p + r) & 31);  // a[j][8p + r], unscaled
+                for (int r = j & ~1; r < 8; r += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(&bcast[r]);
+                    bc[r] = t2.x;
+                    bc[r + 1] = t2.y;
+                }
+                const double ajj = bc[j];
                 const double rcp = fast_rcp(ajj);
                 double t[CS];
 #pragma unroll
