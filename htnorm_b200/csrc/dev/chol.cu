@@ -507,18 +507,32 @@ __device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double& a
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR, 1)
 trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __restrict__ l, size_t ldl,
-                 int nb, const double* __restrict__ rdiag_g)
+                 int nb, const double* __restrict__ rdiag_g, size_t sx, size_t sl, size_t sr)
 {
+    // problem blockIdx.y of a batched launch (strides in doubles; all zero for a single problem)
+    x += (size_t)blockIdx.y * sx;
+    l += (size_t)blockIdx.y * sl;
+    if (rdiag_g) rdiag_g += (size_t)blockIdx.y * sr;
     extern __shared__ double sm[];
-    double* S = sm;                  // [NB][LDB] : L (lower, zero-padded)
-    double* I8 = sm + NB * LDB;      // [16][8][LDI] : inverses of the 8 x 8 diagonal blocks
+    double* S = sm;                                    // [nb rounded up to 8][LDB] : L (lower, zero-padded)
+    double* I8 = sm + ((nb + 7) & ~7) * LDB;           // [16][8][LDI] : inverses of the 8 x 8 diagonal blocks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    load_block<NTHR>(S, l, ldl, nb, tid, true);  // potf2 left zeros above the diagonal
+    if (nb == NB) {
+        load_block<NTHR>(S, l, ldl, nb, tid, true);  // potf2 left zeros above the diagonal
+    } else {
+        // partial / narrow blocks (the 64-wide panels of the batched mid-size problems): only the rows and columns that are
+        // read - the lower triangle up to the next multiple of 8, zero-padded
+        const int nbp = (nb + 7) & ~7;
+        for (int idx = tid; idx < nbp * nbp; idx += NTHR) {
+            const int r = idx / nbp, c = idx - r * nbp;
+            S[r * LDB + c] = (r < nb && c <= r) ? l[(size_t)r * ldl + c] : 0.0;
+        }
+    }
     __syncthreads();
     // the warps invert the 8 x 8 diagonal blocks: lane c < 8 solves L_bb y = e_c; the reciprocal pivots come from
     // potf2 (rdiag), so there is no division on the chain
-    for (int blk = warp; blk < 16; blk += NTHR / 32) {
+    for (int blk = warp; blk < 16 && 8 * blk < nb; blk += NTHR / 32) {  // only the blocks that exist (S holds no more rows)
         const int j0 = 8 * blk;
         if (lane < 8) {
             double y[8];
@@ -642,12 +656,32 @@ extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows,
     if ((nrows + TR_ROWS - 1) / TR_ROWS >= 96) {
         if (cudaFuncSetAttribute(trsm_rows_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -201;
-        trsm_rows_kernel<512><<<(nrows + TR_ROWS - 1) / TR_ROWS, 512, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
+        trsm_rows_kernel<512><<<(nrows + TR_ROWS - 1) / TR_ROWS, 512, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag, 0, 0, 0);
     } else {
         if (cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -201;
-        trsm_rows_kernel<128><<<(nrows + 31) / 32, 128, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag);
+        trsm_rows_kernel<128><<<(nrows + 31) / 32, 128, smem, st>>>(x, ldx, nrows, l, ldl, nb, rdiag, 0, 0, 0);
     }
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+// the same panel solve for nbatch independent problems in one launch (gridDim.y = problem; strides in doubles)
+extern "C" int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, size_t sx, int nrows, const double* l, size_t ldl,
+                                      size_t sl, int nb, const double* rdiag, size_t sr, size_t nbatch)
+{
+    if (nrows <= 0 || nb <= 0 || nbatch == 0) return 0;
+    if (nb > NB) return -202;
+    const size_t smem = (size_t)(((nb + 7) & ~7) * LDB + 16 * 8 * LDI) * sizeof(double);  // several CTAs per SM for narrow blocks
+    if (cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double))) != cudaSuccess)
+        return -201;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
+        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        const dim3 grid((unsigned)((nrows + 31) / 32), nbt);
+        trsm_rows_kernel<128><<<grid, 128, smem, st>>>(x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
+        htnk_count_launch();
+        if (cudaGetLastError() != cudaSuccess) return -201;
+    }
+    return 0;
 }

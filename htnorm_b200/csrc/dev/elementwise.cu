@@ -18,8 +18,10 @@ inline int status()
 // UPPER triangle (-DHTNORM_COLMAJOR: the lower one).  full = symmetric copy, low = lower copy.
 __global__ void __launch_bounds__(256)
 sym_expand_kernel(const double* __restrict__ src, size_t lds, int n, int lower_src, double* __restrict__ full,
-                  size_t ldf, double* __restrict__ low, size_t ldl)
+                  size_t ldf, double* __restrict__ low, size_t ldl, size_t ssrc, size_t slow)
 {
+    src += (size_t)blockIdx.z * ssrc;  // problem blockIdx.z of a batched launch (strides in doubles, 0 for one problem)
+    if (low) low += (size_t)blockIdx.z * slow;
     __shared__ double d_t[32][33];  // direct tile   src[bi-rows][bj-cols]
     __shared__ double t_t[32][33];  // mirrored tile src[bj-rows][bi-cols]
     const int bi = blockIdx.y, bj = blockIdx.x;
@@ -357,8 +359,22 @@ extern "C" int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, i
 {
     if (n <= 0) return 0;
     dim3 grid((n + 31) / 32, (n + 31) / 32);
-    sym_expand_kernel<<<grid, 256, 0, st>>>(src, lds, n, lower_src, full, ldf, low, ldl);
+    sym_expand_kernel<<<grid, 256, 0, st>>>(src, lds, n, lower_src, full, ldf, low, ldl, 0, 0);
     return status();
+}
+
+// lower-triangle copies (zeros above) of nbatch symmetric matrices in one launch
+extern "C" int htnk_sym_expand_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src,
+                                       double* low, size_t ldl, size_t slow, size_t nbatch)
+{
+    if (n <= 0 || nbatch == 0) return 0;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
+        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        dim3 grid((n + 31) / 32, (n + 31) / 32, nbt);
+        sym_expand_kernel<<<grid, 256, 0, st>>>(src + b0 * ssrc, lds, n, lower_src, nullptr, 0, low + b0 * slow, ldl, ssrc, slow);
+        if (status()) return -201;
+    }
+    return 0;
 }
 
 extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,

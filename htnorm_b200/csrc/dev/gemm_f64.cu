@@ -42,6 +42,7 @@ struct GemmParams {
     int mode, ktri, kext0;
     int tiles_m, tiles_n;
     const int* skip;  // device flag: non-zero turns the launch into a no-op
+    size_t sA, sB, sC;  // batched launches (gridDim.y problems): strides between consecutive problems, in doubles
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes)
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
     const int warp = tid >> 5;
     const int wm = warp / WARPS_N;
     const int wn = warp % WARPS_N;
+    const double* const Ag = p.A + (size_t)blockIdx.y * p.sA;  // problem blockIdx.y of a batched launch
+    const double* const Bg = p.B + (size_t)blockIdx.y * p.sB;
+    double* const Cg = p.C + (size_t)blockIdx.y * p.sC;
 
     const int bid = blockIdx.x;
     const int tn = p.tiles_n - 1 - (bid % p.tiles_n);
@@ -136,8 +140,8 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
             int k0, kend;
             chunk_range(c, k0, kend);
             int s = c % STAGES;
-            load_tile<BM, NTHREADS, BK>(sA + s * A_STAGE, p.A, p.lda, m0, p.M, k0, kend, tid);
-            load_tile<BN, NTHREADS, BK>(sB + s * B_STAGE, p.B, p.ldb, n0, p.N, k0, kend, tid);
+            load_tile<BM, NTHREADS, BK>(sA + s * A_STAGE, Ag, p.lda, m0, p.M, k0, kend, tid);
+            load_tile<BN, NTHREADS, BK>(sB + s * B_STAGE, Bg, p.ldb, n0, p.N, k0, kend, tid);
         }
         cp_async_commit();
     };
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
     cp_async_wait<0>();
 
     // epilogue: thread holds C[m][n], C[m][n+1] with m = .. + g, n = .. + 2*t4
-    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < WM; i++) {
         const int m = m0 + wm * WM * 8 + i * 8 + g;
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
         for (int j = 0; j < WN; j++) {
             const int n = n0 + wn * WN * 8 + j * 8 + 2 * t4;
             if (n >= p.N) continue;
-            double* cp = p.C + (size_t)m * p.ldc + n;
+            double* cp = Cg + (size_t)m * p.ldc + n;
             const bool two = (n + 1 < p.N);
             double v0, v1;
             if (p.bias) {  // explicitly fused, as in gemm_tma.cu: the two kernels must round alike
@@ -251,14 +255,14 @@ __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, MINB) gemm_tn_kernel(c
 }
 
 template <int BN, int WARPS_M, int WARPS_N, int WM, int WN, int MINB, int BK = 16, int STAGES = 3>
-int launch(cudaStream_t st, const GemmParams& p)
+int launch(cudaStream_t st, const GemmParams& p, unsigned nbatch = 1)
 {
     constexpr size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
     auto kern = gemm_tn_kernel<BN, WARPS_M, WARPS_N, WM, WN, MINB, BK, STAGES>;
     // per-device attribute: set on every launch (cheap) so that any current device is covered
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
-    unsigned grid = (unsigned)p.tiles_m * (unsigned)p.tiles_n;
+    const dim3 grid((unsigned)p.tiles_m * (unsigned)p.tiles_n, nbatch);
     kern<<<grid, 32 * WARPS_M * WARPS_N, smem, st>>>(p);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
@@ -323,6 +327,7 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mode = mode; p.ktri = ktri; p.kext0 = kext0;
     p.skip = skip;
+    p.sA = p.sB = p.sC = 0;
     p.tiles_m = tiles_m;
     const int bn_cols = bn >= 128 ? 128 : (bn >= 64 ? 64 : bn);
     p.tiles_n = (N + bn_cols - 1) / bn_cols;
@@ -343,4 +348,38 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
         case 8: return launch<8, 8, 1, 2, 1, 1>(st, p);
         default: return -202;
     }
+}
+
+// The same GEMM over nbatch independent problems in ONE launch (gridDim.y = problem): problem b reads A + b sA, B + b sB and
+// updates C + b sC.  cp.async kernels only (no tensor maps per problem); N tile 64 / 32 / 8 by N.  Used by the batched
+// mid-size independent problems (hyperplane.c ht_independent_mid): the trailing updates of all problems' factorisations.
+extern "C" int htnk_gemm_tn_batched(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
+                                    size_t sA, const double* B, size_t ldb, size_t sB, double beta, double* C, size_t ldc,
+                                    size_t sC, int mode, size_t nbatch)
+{
+    if (M <= 0 || N <= 0 || nbatch == 0) return 0;
+    if (K < 0) return -202;
+    if ((lda & 1) || (ldb & 1) || (sA & 1) || (sB & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return -202;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.alpha = alpha; p.beta = beta;
+    p.bias = nullptr;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.mode = mode; p.ktri = 0; p.kext0 = 0;
+    p.skip = nullptr;
+    p.sA = sA; p.sB = sB; p.sC = sC;
+    p.tiles_m = (M + BM - 1) / BM;
+    const int bn = N <= 8 ? 8 : (N <= 32 ? 32 : 64);
+    p.tiles_n = (N + bn - 1) / bn;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {  // gridDim.y limit
+        const unsigned nb = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        p.A = A + b0 * sA; p.B = B + b0 * sB; p.C = C + b0 * sC;
+        int rc;
+        if (bn == 64) rc = launch<64, 2, 2, 8, 4, 2>(st, p, nb);
+        else if (bn == 32) rc = launch<32, 8, 1, 2, 4, 2>(st, p, nb);
+        else rc = launch<8, 8, 1, 2, 1, 1>(st, p, nb);
+        if (rc) return rc;
+    }
+    return 0;
 }

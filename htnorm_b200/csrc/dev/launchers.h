@@ -154,6 +154,26 @@ int htnk_ht_small_batched(cudaStream_t st, size_t nproblems, int k, int k2, cons
 int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int k2, const double* mean, const double* cov,
                        const double* g, const double* r, const double* zs, double* out, int* info, unsigned* counter);
 
+/* ---- batched building blocks of the mid-size independent problems (one launch over all problems; strides in doubles) ---- */
+int htnk_gemm_tn_batched(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda, size_t sA,
+                         const double* B, size_t ldb, size_t sB, double beta, double* C, size_t ldc, size_t sC, int mode,
+                         size_t nbatch);
+int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, size_t sx, int nrows, const double* l, size_t ldl, size_t sl,
+                           int nb, const double* rdiag, size_t sr, size_t nbatch);
+int htnk_sym_expand_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src, double* low,
+                            size_t ldl, size_t slow, size_t nbatch);
+/* diagonal 64-block of every problem's lower factorisation, one WARP per problem (mid_batched.cu): factorises in place the
+ * nb x nb (nb <= 64) block at row / column j0 of F + b * sF (lower storage, leading dimension ld); rdiag + b * sr + j0 receives
+ * 1 / L[j][j]; info[b] receives j0 + j + 1 at the first pivot <= 0 (if it still holds 0; problems whose info is set are skipped).
+ * counter: one zero-initialised device unsigned. */
+int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t sF, int j0, int nb, double* rdiag, size_t sr, int* info,
+                        size_t nbatch, unsigned* counter);
+/* projection of one sample per problem given the factor (mid_batched.cu): x = y + cov G^T (G cov G^T)^-1 (r - G y), y = mean + L z,
+ * formed around the factor (V = L^T G^T); k2 <= 4.  info[b]: set by the factorisation (row untouched) or by the k2 x k2 solve. */
+int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2, const double* F, size_t ld, size_t sF,
+                        const double* mean, const double* g, const double* r, const double* zs, int g_colmajor, double* out,
+                        int* info);
+
 /* ---- peak microbenchmarks (peak.cu) ---- */
 double htnk_dmma_peak_tflops(cudaStream_t st, double ms);
 double htnk_dfma_peak_tflops(cudaStream_t st, double ms);

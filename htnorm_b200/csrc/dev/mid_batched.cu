@@ -1,0 +1,453 @@
+// Batched MID-SIZE independent problems (128 < k <= 1024, one sample per problem, each with its own mean / cov / G / r):
+// the building blocks that have no counterpart among the single-problem kernels.  Round 1 ran one full shared-path call
+// per problem in a host loop (>= 0.5 ms each); here ALL problems go through one launch sequence (hyperplane.c
+// ht_independent_mid): per 64-column panel step
+//     potf64_kernel          diagonal 64-block of every problem, ONE WARP per problem (this file)
+//     trsm_rows_kernel       rows below, batched over problems (chol.cu)            L21 = A21 L11^-T
+//     gemm_tn_kernel         rank-64 trailing update, batched (gemm_f64.cu)          A22 -= L21 L21^T
+// and at the end ht_mid_project_kernel (this file), one CTA per problem: the projection of src/htnorm.c:85-187 formed
+// around the factor in two coalesced passes over L (V = L^T G^T, G cov G^T = V^T V, x = mean + L (z + V alpha)).
+// A 128-wide potf2 block costs 33 us of latency-bound work on one SM; the warp-level 64-block factorisation of
+// small_warp.cu runs eight problems per SM at once - that is what makes a batched factorisation worth having.
+// Reference semantics per problem: src/htnorm.c:85-187, src/htnorm_distributions.c:58-88; error codes SURVEY Q5 / Q6.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "launchers.h"
+
+namespace {
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double h = 0.5 * y;
+        const double e = fma(-x * y, h, 0.5);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+// shared-memory geometry of small_warp.cu for an 8 x 8 grid of tiles (see there): dense swizzled 8 x 8 tiles
+struct G {
+    static constexpr int NT = 8, K = 64, CS = 2;
+    static __host__ __device__ constexpr int tid(int p, int tj) { return p * NT - p * (p - 1) / 2 + (tj - p); }
+    static constexpr int NTILES = NT * (NT + 1) / 2;
+    static __host__ __device__ constexpr int didx(int q, int ti, int tj)
+    {
+        return (ti - q - 2) * NT - ((ti - 1) * ti - (q + 1) * (q + 2)) / 2 + (tj - ti);
+    }
+    static constexpr int WV = 64 * NTILES;  // [64] the pivots d
+    static constexpr int SCR = WV + 64;     // [16] pivot-row broadcast, double-buffered
+    static constexpr int TOTAL = SCR + 16;
+};
+
+// One warp factorises the nb x nb (nb <= 64) diagonal block at (j0, j0) of one problem's matrix (LOWER storage, row-major):
+// the block is loaded as the 36 upper 8 x 8 tiles of the symmetric block in the tensor-core accumulator layout (element
+// (r, c), r <= c, is stored at [c][r]; rows / columns beyond nb are padded with the identity), factorised exactly as in
+// small_warp.cu, and the Cholesky factor is written back row by row as each 8-row panel finishes.
+__global__ void __launch_bounds__(32, 8)
+potf64_kernel(double* __restrict__ F, size_t ld, size_t sF, int j0, int nb, double* __restrict__ rdiag, size_t sr,
+              int* __restrict__ info, size_t nbatch, unsigned* __restrict__ next)
+{
+    constexpr int NT = G::NT, K = G::K, CS = G::CS;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int swg = 4 * ((g >> 1) & 1), swt = 4 * ((t4 >> 1) & 1);
+    int cf[2], tf[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        cf[e] = (g ^ e) * 8 + ((2 * t4) ^ swg);
+        tf[e] = (t4 ^ e) * 8 + (g ^ swt);
+    }
+    int col[CS][8];
+#pragma unroll
+    for (int cs = 0; cs < CS; cs++) {
+        const int j = lane + 32 * cs, ej = (j >> 3) & 1, cj = j & 7;
+#pragma unroll
+        for (int c = 0; c < 8; c++) col[cs][c] = 64 * (j >> 3) + (c ^ ej) * 8 + (cj ^ (4 * ((c >> 1) & 1)));
+    }
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(next, 1u);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    for (;;) {
+        const size_t pb = nxt;
+        if (pb >= nbatch) break;
+        if (lane == 0) nxt = atomicAdd(next, 1u);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        if (info[pb] != 0) continue;  // an earlier panel of this problem failed: nothing to do (uniform)
+        double* Fp = F + pb * sF;
+        double* rd = rdiag + pb * sr;
+        double2 c[NT][NT];
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = ti; tj < NT; tj++) {
+                const int r = 8 * ti + g, c0 = 8 * tj + 2 * t4;
+                const double* src = Fp + (size_t)(j0 + c0) * ld + j0 + r;
+                c[ti][tj].x = (r < nb && c0 < nb) ? __ldg(src) : (r == c0 ? 1.0 : 0.0);
+                c[ti][tj].y = (r < nb && c0 + 1 < nb) ? __ldg(src + ld) : (r == c0 + 1 ? 1.0 : 0.0);
+            }
+        // ---- A_bb = U~^T D U~, panel by panel (the scheme of small_warp.cu) ----
+        int fail = 0;
+        // transposed fragments of the tiles of the panel factorised last: fa = U~, fad = -D U~ (the rank-8 update is
+        // C(ti, tj) -= U~(p, ti)^T D U~(p, tj))
+        double fa[NT][2], fad[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; t++) fa[t][0] = fa[t][1] = fad[t][0] = fad[t][1] = 0.0;
+#pragma unroll
+        for (int p = 0; p < NT; p++) {
+            // the panel's tiles leave the registers (accumulator layout) ...
+#pragma unroll
+            for (int tj = p; tj < NT; tj++)
+                *reinterpret_cast<double2*>(&sm[64 * G::tid(p, tj) + cf[tj & 1]]) = c[p][tj];
+            __syncwarp();
+            // ... and come back in the lane = column layout: v[cs][r] = A[8 p + r][j]
+            double v[CS][8];
+#pragma unroll
+            for (int cs = 0; cs < CS; cs++) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[cs][r] = 0.0;
+                if (32 * cs + 31 >= 8 * p) {  // compile-time: the column set reaches into the panel
+                    const int j = lane + 32 * cs;
+                    if (j >= 8 * p && j < K) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) v[cs][r] = sm[64 * (G::tid(p, p) - p) + col[cs][r]];
+                    }
+                }
+            }
+            const int csd = (8 * p) >> 5;  // column set that holds the diagonal tile (compile-time after unrolling)
+            double dpiv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                // the chain first: pivot, its reciprocal, the update of the NEXT pivot's row in the diagonal columns
+                // the pivot row of the diagonal tile (columns 8p + j .. 8p + 7, held by eight lanes) goes through shared
+                // memory: one store, broadcast 16-byte loads - 5 wavefronts instead of the 2 (8 - j) of a shuffle each
+                const int cc = (lane - 8 * p) & 31;
+                double* bcast = &sm[G::SCR + 8 * (j & 1)];
+                if (cc >= j && cc < 8) bcast[cc] = v[csd][j];
+                __syncwarp();
+                double bc[8];
+#pragma unroll
+                for (int r = j & ~1; r < 8; r += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(&bcast[r]);
+                    bc[r] = t2.x;
+                    bc[r + 1] = t2.y;
+                }
+                const double ajj = bc[j];
+                const double rcp = fast_rcp(ajj);
+                double t[CS];
+#pragma unroll
+                for (int cs = 0; cs < CS; cs++) t[cs] = v[cs][j] * rcp;
+                if (j + 1 < 8) v[csd][j + 1] = fma(-t[csd], bc[j + 1], v[csd][j + 1]);
+#pragma unroll
+                for (int cs = 0; cs < CS; cs++) {
+                    if (32 * cs + 31 >= 8 * p) {
+#pragma unroll
+                        for (int r = j + 1; r < 8; r++)
+                            if (!(cs == csd && r == j + 1)) v[cs][r] = fma(-t[cs], bc[r], v[cs][r]);
+                    }
+                }
+                if (ajj <= 0.0 && fail == 0) fail = j0 + 8 * p + j + 1;  // NaN passes
+                dpiv[j] = ajj;
+                // square-root free: row j of the UNIT upper factor is a[j][.] / d_j = t, the pivot d_j goes to WV
+#pragma unroll
+                for (int cs = 0; cs < CS; cs++)
+                    if (32 * cs + 31 >= 8 * p) v[cs][j] = t[cs];
+                if (lane == ((8 * p + j) & 31)) sm[G::WV + 8 * p + j] = ajj;
+                // deferred tiles of step p - 1 (tile rows >= p + 1), an eighth of them after every pivot: registers only
+                if (p >= 1) {
+                    const int q = p - 1;
+                    const int nd = (NT - 2 - q) * (NT - 1 - q) / 2;
+                    const int lo = j * nd / 8, hi = (j + 1) * nd / 8;
+                    // the chunk's first k-steps, then its second ones: no DMMA waits for the one before it
+#pragma unroll
+                    for (int ti = q + 2; ti < NT; ti++) {
+#pragma unroll
+                        for (int tj = ti; tj < NT; tj++) {
+                            const int idx = G::didx(q, ti, tj);
+                            if (idx >= lo && idx < hi) dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][0], fa[tj][0]);
+                        }
+                    }
+#pragma unroll
+                    for (int ti = q + 2; ti < NT; ti++) {
+#pragma unroll
+                        for (int tj = ti; tj < NT; tj++) {
+                            const int idx = G::didx(q, ti, tj);
+                            if (idx >= lo && idx < hi) dmma(c[ti][tj].x, c[ti][tj].y, fad[ti][1], fa[tj][1]);
+                        }
+                    }
+                }
+            }
+            // columns of the diagonal tile: nothing below the diagonal (the products below read whole tiles)
+#pragma unroll
+            for (int cs = 0; cs < CS; cs++) {
+                if (32 * cs + 31 >= 8 * p) {
+                    const int j = lane + 32 * cs;
+                    if (cs == csd) {  // compile-time: only this column set holds columns of the diagonal tile
+                        const int cc = j - 8 * p;
+#pragma unroll
+                        for (int r = 1; r < 8; r++)
+                            if (cc >= 0 && cc < r) v[cs][r] = 0.0;
+                    }
+                    if (j >= 8 * p && j < K) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) sm[64 * (G::tid(p, p) - p) + col[cs][r]] = v[cs][r];
+                    }
+                    // the Cholesky factor L = (sqrt(D) U~)^T leaves for global memory: row j0 + j, columns j0 + 8p .. + 7
+                    if (j >= 8 * p && j < nb) {
+                        double2* lp = reinterpret_cast<double2*>(Fp + (size_t)(j0 + j) * ld + j0 + 8 * p);
+#pragma unroll
+                        for (int q2 = 0; q2 < 4; q2++) {
+                            const double s0 = dpiv[2 * q2] * fast_rsqrt(dpiv[2 * q2]), s1 = dpiv[2 * q2 + 1] * fast_rsqrt(dpiv[2 * q2 + 1]);
+                            if (8 * p + 2 * q2 + 1 < nb) lp[q2] = make_double2(v[cs][2 * q2] * s0, v[cs][2 * q2 + 1] * s1);
+                            else if (8 * p + 2 * q2 < nb) reinterpret_cast<double*>(lp + q2)[0] = v[cs][2 * q2] * s0;
+                        }
+                    }
+                }
+            }
+            if (lane < 8 && 8 * p + lane < nb) {  // 1 / L[j][j] for the panel solve
+                double dv = dpiv[0];
+#pragma unroll
+                for (int r = 1; r < 8; r++)
+                    if (lane == r) dv = dpiv[r];
+                rd[j0 + 8 * p + lane] = fast_rsqrt(dv);
+            }
+            __syncwarp();
+            if (p + 1 < NT) {
+                // fragments of panel p, then the urgent tile row p + 1 (all that the next elimination reads)
+                const double ds0 = -sm[G::WV + 8 * p + t4], ds1 = -sm[G::WV + 8 * p + 4 + t4];  // -d of the fragment's rows
+#pragma unroll
+                for (int t = p + 1; t < NT; t++) {
+                    fa[t][0] = sm[64 * G::tid(p, t) + tf[t & 1]];
+                    fa[t][1] = sm[64 * G::tid(p, t) + 32 + tf[t & 1]];
+                    fad[t][0] = fa[t][0] * ds0;
+                    fad[t][1] = fa[t][1] * ds1;
+                }
+#pragma unroll
+                for (int tj = p + 1; tj < NT; tj++) dmma(c[p + 1][tj].x, c[p + 1][tj].y, fad[p + 1][0], fa[tj][0]);
+#pragma unroll
+                for (int tj = p + 1; tj < NT; tj++) dmma(c[p + 1][tj].x, c[p + 1][tj].y, fad[p + 1][1], fa[tj][1]);
+            }
+        }
+        if (fail && lane == 0) info[pb] = fail;  // cov not PD at that pivot (src/htnorm_distributions.c:78)
+        __syncwarp();
+    }
+}
+
+// ---- projection, one CTA per problem ----
+// y = mean + L z, V = L^T G^T (k x k2), S = V^T V = G cov G^T, G y = G mean + V^T z, alpha = S^-1 (r - G y),
+// x = mean + L (z + V alpha).  Two coalesced passes over the lower factor.  Pass 1 (V): every warp takes every eighth row of
+// L and accumulates that row's contribution to ALL columns of a 256-column chunk in registers (lane = columns lane + 32 m: eight
+// independent 256-byte loads in flight per row), the eight warps' partial sums are then added in a fixed order.  Pass 2: one row
+// per warp at a time.
+constexpr int PT = 256;
+__global__ void __launch_bounds__(PT)
+ht_mid_project_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F, size_t ld, size_t sF,
+                      const double* __restrict__ mean, const double* __restrict__ gm, const double* __restrict__ rv,
+                      const double* __restrict__ zs, int g_colmajor, double* __restrict__ out, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) double ps[];
+    double* z = ps;               // [k]
+    double* w = z + k;            // [k]
+    double* Gs = w + k;           // [4][k]
+    double* Vs = Gs + 4 * k;      // [k][4]
+    double* red = Vs + 4 * k;     // [8 warps][24]
+    __shared__ double s_al[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t pb = blockIdx.x; pb < nbatch; pb += gridDim.x) {
+        if (info[pb] != 0) continue;  // cov not PD: out untouched (uniform across the CTA)
+        const double* Lp = F + pb * sF;
+        const double* mp = mean + pb * (size_t)k;
+        for (int i = tid; i < k; i += PT) z[i] = zs[pb * (size_t)k + i];
+        for (int idx = tid; idx < 4 * k; idx += PT) {
+            const int c = idx / k, i = idx - c * k;
+            double v = 0.0;
+            if (c < k2) v = g_colmajor ? gm[pb * (size_t)k2 * k + (size_t)i * k2 + c] : gm[pb * (size_t)k2 * k + (size_t)c * k + i];
+            Gs[idx] = v;
+            Vs[idx] = 0.0;
+        }
+        __syncthreads();
+        // pass 1: V[j][c] = sum_{i >= j} L[i][j] G[c][i], a 256-column chunk at a time
+        for (int j0 = 0; j0 < k; j0 += 256) {
+            double acc[8][4];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[m][c] = 0.0;
+            for (int i = j0 + warp; i < k; i += PT / 32) {
+                const double* row = Lp + (size_t)i * ld + j0 + lane;
+                double l[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) l[m] = (j0 + lane + 32 * m <= i) ? __ldg(row + 32 * m) : 0.0;
+                const double g0 = Gs[i], g1 = Gs[k + i], g2 = Gs[2 * k + i], g3 = Gs[3 * k + i];
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    acc[m][0] = fma(l[m], g0, acc[m][0]);
+                    acc[m][1] = fma(l[m], g1, acc[m][1]);
+                    acc[m][2] = fma(l[m], g2, acc[m][2]);
+                    acc[m][3] = fma(l[m], g3, acc[m][3]);
+                }
+            }
+            for (int ww = 0; ww < PT / 32; ww++) {  // fixed order: bit-reproducible
+                if (warp == ww) {
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const int j = j0 + lane + 32 * m;
+                        if (j < k) {
+                            double4* vp = reinterpret_cast<double4*>(Vs + 4 * j);
+                            double4 v = *vp;
+                            v.x += acc[m][0]; v.y += acc[m][1]; v.z += acc[m][2]; v.w += acc[m][3];
+                            *vp = v;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // S (10 values), V^T z (4), G mean (4): per-thread partial sums over the rows j = tid + 256 m, fixed-order reduction
+        double part[18];
+#pragma unroll
+        for (int q = 0; q < 18; q++) part[q] = 0.0;
+        for (int j = tid; j < k; j += PT) {
+            const double4 v = *reinterpret_cast<const double4*>(Vs + 4 * j);
+            const double va[4] = {v.x, v.y, v.z, v.w};
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b <= a; b++) part[q++] += va[a] * va[b];
+            const double zj = z[j], mj = mp[j];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                part[10 + a] += va[a] * zj;
+                part[14 + a] += Gs[a * k + j] * mj;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 18; q++) {
+            double v = part[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp * 24 + q] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double t[18];
+            for (int q = 0; q < 18; q++) {
+                double v = 0.0;
+                for (int ww = 0; ww < PT / 32; ww++) v += red[ww * 24 + q];
+                t[q] = v;
+            }
+            double s[4][4], bv[4], ri[4];
+            int q = 0, f2 = 0;
+            for (int a = 0; a < 4; a++)
+                for (int b = 0; b <= a; b++, q++) s[a][b] = a < k2 ? t[q] : (a == b ? 1.0 : 0.0);
+            for (int a = 0; a < 4; a++) bv[a] = a < k2 ? rv[pb * (size_t)k2 + a] - t[14 + a] - t[10 + a] : 0.0;
+            if (k2 == 1) {
+                bv[0] = bv[0] / s[0][0];  // the reference divides by the scalar (src/htnorm.c:77)
+            } else {
+                for (int j = 0; j < 4; j++) {
+                    const double ajj = s[j][j];
+                    if (ajj <= 0.0 && f2 == 0) f2 = j + 1;
+                    const double rinv = fast_rsqrt(ajj);
+                    ri[j] = rinv;
+                    for (int i = j + 1; i < 4; i++) s[i][j] *= rinv;
+                    for (int i = j + 1; i < 4; i++)
+                        for (int cc = j + 1; cc <= i; cc++) s[i][cc] = fma(-s[i][j], s[cc][j], s[i][cc]);
+                }
+                for (int i = 0; i < 4; i++) {
+                    double v = bv[i];
+                    for (int u = 0; u < i; u++) v = fma(-s[i][u], bv[u], v);
+                    bv[i] = v * ri[i];
+                }
+                for (int i = 3; i >= 0; i--) {
+                    double v = bv[i];
+                    for (int u = i + 1; u < 4; u++) v = fma(-s[u][i], bv[u], v);
+                    bv[i] = v * ri[i];
+                }
+            }
+            for (int a = 0; a < 4; a++) s_al[a] = f2 ? 0.0 : bv[a];  // G cov G^T not PD: the unprojected y (src/htnorm.c:170)
+            info[pb] = f2;
+        }
+        __syncthreads();
+        const double a0 = s_al[0], a1 = s_al[1], a2 = s_al[2], a3 = s_al[3];
+        for (int j = tid; j < k; j += PT) {
+            const double4 v = *reinterpret_cast<const double4*>(Vs + 4 * j);
+            w[j] = z[j] + ((v.x * a0 + v.y * a1) + (v.z * a2 + v.w * a3));
+        }
+        __syncthreads();
+        // pass 2: x[i] = mean[i] + sum_{j <= i} L[i][j] w[j], two rows per warp at a time (a long and a short one)
+        for (int i = warp; i < k; i += PT / 32) {
+            const double* row = Lp + (size_t)i * ld;
+            double v = 0.0;
+            for (int j = lane; j <= i; j += 32) v = fma(__ldg(row + j), w[j], v);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) out[pb * (size_t)k + i] = mp[i] + v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t sF, int j0, int nb, double* rdiag, size_t sr,
+                                   int* info, size_t nbatch, unsigned* counter)
+{
+    if (nbatch == 0 || nb <= 0) return 0;
+    if (nb > 64 || (ld & 1) || (j0 & 1) || (sF & 1) || nbatch > 0xfffffff0u || (reinterpret_cast<uintptr_t>(F) & 15)) return -202;
+    const size_t smem = (size_t)G::TOTAL * sizeof(double);
+    if (cudaFuncSetAttribute(potf64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, potf64_kernel, 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > nbatch) grid = nbatch;
+    potf64_kernel<<<(unsigned)grid, 32, smem, st>>>(F, ld, sF, j0, nb, rdiag, sr, info, nbatch, counter);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2, const double* F, size_t ld, size_t sF,
+                                   const double* mean, const double* g, const double* r, const double* zs, int g_colmajor,
+                                   double* out, int* info)
+{
+    if (nbatch == 0) return 0;
+    if (k < 1 || k > 4 * PT || k2 < 1 || k2 > 4) return -202;
+    const size_t smem = ((size_t)10 * k + 8 * 24) * sizeof(double);
+    if (cudaFuncSetAttribute(ht_mid_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ht_mid_project_kernel, PT, smem);
+    if (per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > nbatch) grid = nbatch;
+    ht_mid_project_kernel<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}

@@ -405,6 +405,61 @@ done:
     return rc;
 }
 
+/* Independent problems of mid size (128 < k <= 1024, k2 <= 4, dense cov), ONE sample each: all problems go through one
+ * launch sequence - per 64-column panel step a warp-per-problem factorisation of the diagonal blocks, a batched panel solve and
+ * a batched rank-64 update - then one projection kernel (dev/mid_batched.cu).  Replaces the host loop of one shared-path
+ * call per problem (>= 0.5 ms each).  Reference per problem: src/htnorm.c:85-187, src/htnorm_distributions.c:58-88. */
+#define MID_K_MAX 1024
+#define MID_K2_MAX 4
+static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, unsigned flags, int k2, int k,
+                              const double* mean, const double* cov, const double* g, const double* r, double* out,
+                              int* info_dev)
+{
+    int rc = 0;
+    cudaStream_t st = ctx->stream;
+    const size_t ld = htn_round_up((size_t)k, 16), sF = (size_t)k * ld, sr = htn_round_up((size_t)k, 64);
+    const int nsteps = (k + 63) / 64;
+    double *F = NULL, *rd = NULL, *zs = NULL;
+    unsigned* ctr = NULL;
+    /* the workspace holds a full k x ld factor per problem: very large batches go through in slices of <= 2 GiB of factors */
+    size_t slice = ((size_t)2 << 30) / (sF * 8);
+    if (slice < 1) slice = 1;
+    if (slice > P) slice = P;
+    HTN_TRY(htn_dalloc(ctx, (void**)&F, slice * sF * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&rd, slice * sr * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&zs, slice * (size_t)k * 8));
+    HTN_TRY(htn_dalloc(ctx, (void**)&ctr, (size_t)nsteps * sizeof(unsigned)));
+    for (size_t p0 = 0; p0 < P && !rc; p0 += slice) {
+        const size_t np = P - p0 < slice ? P - p0 : slice;
+        htnk_streams_t sv;
+        streams_view(s, p0, &sv);
+        htnk_segment_t seg = {(size_t)k, zs, (size_t)k, NULL, NULL, NULL};
+        HTN_TRY(htnk_normal_fill(st, &sv, np, 1, &seg, NULL));
+        HTN_CUDA(cudaMemsetAsync(info_dev + p0, 0, np * sizeof(int), st));
+        HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nsteps * sizeof(unsigned), st));
+        HTN_TRY(htnk_sym_expand_batched(st, cov + p0 * (size_t)k * k, (size_t)k, (size_t)k * k, k,
+                                        (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, F, ld, sF, np));
+        for (int q = 0; q < nsteps; q++) {
+            const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64, rows = k - j0 - nb;
+            HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
+            if (rows <= 0) break;
+            double* x = F + (size_t)(j0 + nb) * ld + j0; /* A21 -> L21 = A21 L11^-T, then A22 -= L21 L21^T (lower tiles) */
+            HTN_TRY(htnk_trsm_rows_batched(st, x, ld, sF, rows, F + (size_t)j0 * ld + j0, ld, sF, nb, rd + j0, sr, np));
+            HTN_TRY(htnk_gemm_tn_batched(st, rows, rows, nb, -1.0, x, ld, sF, x, ld, sF, 1.0, F + (size_t)(j0 + nb) * ld + j0 + nb,
+                                         ld, sF, HTNK_GEMM_C_LOWER, np));
+        }
+        HTN_TRY(htnk_ht_mid_project(st, np, k, k2, F, ld, sF, mean + p0 * (size_t)k, g + p0 * (size_t)k2 * k,
+                                    r + p0 * (size_t)k2, zs, (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out + p0 * (size_t)k,
+                                    info_dev + p0));
+    }
+done:
+    htn_dfree(ctx, ctr);
+    htn_dfree(ctx, zs);
+    htn_dfree(ctx, rd);
+    htn_dfree(ctx, F);
+    return rc;
+}
+
 int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int independent, unsigned flags,
                   size_t k2, size_t k, const double* mean, const double* cov, const double* g, const double* r,
                   int diag, double* out, int* d_info_out, int* first_info)
@@ -453,6 +508,20 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
                                                (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out, info_dev);
             }
             htn_dfree(ctx, zs);
+            htn_dfree(ctx, tmp);
+            *first_info = 0; /* per-problem codes live in the device array */
+            return rc;
+        }
+        if (!diag && k <= MID_K_MAX && k2 <= MID_K2_MAX && nsamples >= 2 && !s->states && !s->zpre &&
+            !(getenv("HTN_MID_BATCHED") && atoi(getenv("HTN_MID_BATCHED")) == 0)) {
+            /* mid-size problems, batched: one launch sequence over all of them */
+            int* info_dev = d_info_out;
+            int* tmp = NULL;
+            if (!info_dev) {
+                HTN_TRY(htn_dalloc(ctx, (void**)&tmp, nsamples * sizeof(int)));
+                info_dev = tmp;
+            }
+            rc = ht_independent_mid(ctx, s, nsamples, flags, (int)k2, (int)k, mean, cov, g, r, out, info_dev);
             htn_dfree(ctx, tmp);
             *first_info = 0; /* per-problem codes live in the device array */
             return rc;

@@ -858,3 +858,44 @@ def test_warp_per_problem_kernel_other_orders(h, oracle, k):
         ok = np.arange(P) != 5
         assert rel_err(x[ok], xo[ok]) < REL_TOL, (k, k2)
         assert constraint_violation(x[ok], c["g"][ok], c["r"][ok]) < RESID_TOL, (k, k2)
+
+
+@pytest.mark.parametrize("k,k2,P", [(129, 1, 40), (192, 4, 70), (200, 3, 33), (256, 4, 300), (300, 2, 20), (1000, 4, 6)])
+def test_mid_size_independent_problems_batched(h, oracle, k, k2, P):
+    """Independent problems with 128 < k <= 1024, k2 <= 4 go through ONE batched launch sequence (64-column panels:
+    warp-per-problem diagonal blocks, batched panel solve and rank-64 update, one projection kernel; hyperplane.c
+    ht_independent_mid) instead of a host loop of shared-path calls: parity against the oracle (src/htnorm.c:85-187 per
+    problem), the constraint at the 1e-12 bar, per-problem error codes in the first / a middle / the last panel, a
+    singular G cov G^T, and the column-major flag."""
+    c = cases.ht_independent_case(nproblems=P, k=k, k2=k2, rng_seed=900 + k)
+    x, info = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=21)
+    xo, io, _ = oracle.hyperplane("pcg64", P, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=21)
+    assert not info.any() and np.array_equal(info, io)
+    assert rel_err(x, xo) < REL_TOL
+    assert constraint_violation(x, c["g"], c["r"]) < RESID_TOL
+    cov, g = c["cov"][:6].copy(), c["g"][:6].copy()
+    cov[1][5, 5] = -1.0                          # first panel
+    cov[2][k // 2 + 3, k // 2 + 3] = -2.0        # a middle panel
+    cov[3][k - 1, k - 1] = -1.0                  # the last pivot
+    if k2 >= 2:
+        cov[4] = 4.0 * np.eye(k)
+        g[4] = 0.0
+        g[4][:2, :16] = 1.0                      # G cov G^T = [[64, 64], [64, 64]] exactly: second pivot 0
+    out = np.full((6, k), 7.0)
+    x, info = h.hyperplane_truncated_mvnorm_batch(6, c["mean"][:6], cov, g, c["r"][:6], independent=True, seed0=21, out=out,
+                                                  raise_on_error=False)
+    xo, io, _ = oracle.hyperplane("pcg64", 6, c["mean"][:6], cov, g, c["r"][:6], independent=True, seed0=21)
+    want = [0, 6, k // 2 + 4, k, 2 if k2 >= 2 else 0, 0]
+    assert info.tolist() == io.tolist() == want
+    for b in (1, 2, 3):
+        assert (out[b] == 7.0).all()
+    ok = [0, 5] + ([4] if k2 >= 2 else [])
+    assert rel_err(x[ok], xo[ok]) < REL_TOL
+    # column-major: lower triangle valid, g transposed
+    junk = np.random.default_rng(2).standard_normal(c["cov"][:4].shape)
+    lo_ok = np.tril(c["cov"][:4]) + np.triu(junk, 1)
+    gcm = np.ascontiguousarray(np.swapaxes(c["g"][:4], 1, 2)).reshape(c["g"][:4].shape)
+    xc, _ = h.hyperplane_truncated_mvnorm_batch(4, c["mean"][:4], lo_ok, gcm, c["r"][:4], independent=True, seed0=21,
+                                                flags=h._lib.HTN_FLAG_COLMAJOR)
+    assert rel_err(xc, xo[:4] if False else oracle.hyperplane("pcg64", 4, c["mean"][:4], c["cov"][:4], c["g"][:4], c["r"][:4],
+                                                               independent=True, seed0=21)[0]) < REL_TOL
