@@ -676,10 +676,18 @@ extern "C" int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, si
     if (cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double))) != cudaSuccess)
         return -201;
+    const bool big = nrows >= 96;  // 128-row CTAs amortise the load of L and its 8 x 8 inverses
+    if (big && cudaFuncSetAttribute(trsm_rows_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double))) != cudaSuccess)
+        return -201;
     for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
         const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        const dim3 grid((unsigned)((nrows + 31) / 32), nbt);
-        trsm_rows_kernel<128><<<grid, 128, smem, st>>>(x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
+        if (big)
+            trsm_rows_kernel<512><<<dim3((unsigned)((nrows + TR_ROWS - 1) / TR_ROWS), nbt), 512, smem, st>>>(
+                x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
+        else
+            trsm_rows_kernel<128><<<dim3((unsigned)((nrows + 31) / 32), nbt), 128, smem, st>>>(
+                x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
         htnk_count_launch();
         if (cudaGetLastError() != cudaSuccess) return -201;
     }

@@ -160,6 +160,15 @@ int htnk_gemm_tn_batched(cudaStream_t st, int M, int N, int K, double alpha, con
                          size_t nbatch);
 int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, size_t sx, int nrows, const double* l, size_t ldl, size_t sl,
                            int nb, const double* rdiag, size_t sr, size_t nbatch);
+/* left-looking panel step of the batched mid-size factorisation (mid_batched.cu): diagonal block / rows below it */
+int htnk_chol_rows_batched(cudaStream_t st, const double* cov, size_t scov, int lower_src, double* F, size_t ld, size_t sF, int k,
+                           int j0, const double* rdiag, size_t sr, const int* info, int diag, size_t nbatch);
+/* C (rows x rows, lower 64 x 64 tiles) -= X X^T with X rows x nb (nb <= 64), batched (mid_batched.cu) */
+int htnk_syrk64_batched(cudaStream_t st, const double* X, size_t ldx, size_t sX, double* C, size_t ldc, size_t sC, int rows, int nb,
+                        size_t nbatch);
+/* lower-triangle copy (nothing written above the diagonal) of nbatch symmetric matrices (mid_batched.cu) */
+int htnk_lower_copy_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src, double* low,
+                            size_t ldl, size_t slow, size_t nbatch);
 int htnk_sym_expand_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src, double* low,
                             size_t ldl, size_t slow, size_t nbatch);
 /* diagonal 64-block of every problem's lower factorisation, one WARP per problem (mid_batched.cu): factorises in place the

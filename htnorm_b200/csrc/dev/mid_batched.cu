@@ -256,6 +256,272 @@ potf64_kernel(double* __restrict__ F, size_t ld, size_t sF, int j0, int nb, doub
     }
 }
 
+// ---- rank-nb trailing update, batched: C(i, j) -= X_i X_j^T for the 64 x 64 tiles i >= j of every problem ----
+// X = L21 (rows x nb, nb <= 64, the panel just solved), C = the trailing matrix (lower storage).  One CTA of four warps per
+// tile: both 64 x nb blocks of X are loaded whole (no K pipeline: K is one panel), every warp owns a 32 x 32 corner (16
+// accumulator tiles, DMMA m8n8k4, the K order of the other GEMM kernels is irrelevant here: nothing else computes these sums).
+constexpr int SY_LD = 68;  // 64 + 4: the fragment pattern (row g, column t4) is bank-conflict free
+__global__ void __launch_bounds__(128)
+syrk64_batched_kernel(const double* __restrict__ X, size_t ldx, size_t sX, double* __restrict__ C, size_t ldc, size_t sC,
+                      int rows, int nb, int ntile)
+{
+    extern __shared__ __align__(16) double sy[];
+    double* Xi = sy;                 // [64][SY_LD]
+    double* Xj = sy + 64 * SY_LD;    // [64][SY_LD]
+    // tile index -> (ti, tj), ti >= tj, row by row
+    int t = blockIdx.x, ti = 0;
+    while (t > ti) { t -= ti + 1; ti++; }
+    const int tj = t;
+    (void)ntile;
+    const double* Xp = X + (size_t)blockIdx.y * sX;
+    double* Cp = C + (size_t)blockIdx.y * sC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int nbp = (nb + 3) & ~3;
+    for (int idx = tid; idx < 64 * 64; idx += 128) {
+        const int r = idx >> 6, c = idx & 63;
+        const int ri = 64 * ti + r, rj = 64 * tj + r;
+        Xi[r * SY_LD + c] = (ri < rows && c < nb) ? Xp[(size_t)ri * ldx + c] : 0.0;
+        Xj[r * SY_LD + c] = (rj < rows && c < nb) ? Xp[(size_t)rj * ldx + c] : 0.0;
+    }
+    __syncthreads();
+    const int wm = warp >> 1, wn = warp & 1;  // 32 x 32 corner of the tile
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < nbp; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = Xi[(32 * wm + 8 * i + g) * SY_LD + k0 + t4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[j] = Xj[(32 * wn + 8 * j + g) * SY_LD + k0 + t4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = 64 * ti + 32 * wm + 8 * i + g;
+        if (m >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = 64 * tj + 32 * wn + 8 * j + 2 * t4;
+            if (n >= rows) continue;
+            double* cp = Cp + (size_t)m * ldc + n;
+            if (n + 1 < rows && ((ldc & 1) == 0)) {
+                double2 o = *reinterpret_cast<double2*>(cp);
+                o.x -= acc[i][j][0];
+                o.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(cp) = o;
+            } else {
+                cp[0] -= acc[i][j][0];
+                if (n + 1 < rows) cp[1] -= acc[i][j][1];
+            }
+        }
+    }
+}
+
+// lower-triangle copy of every problem's covariance: F[i][j] = cov(i, j) for j <= i, read through the UPPER triangle of the
+// row-major input (lower_src = 0) or through the lower one (column-major build).  Only the 32 x 32 tiles on and
+// below the diagonal are touched: nothing of the factor's workspace above the diagonal is ever read.
+__global__ void __launch_bounds__(256)
+lower_copy_batched_kernel(const double* __restrict__ src, size_t lds, size_t ssrc, int n, int lower_src,
+                          double* __restrict__ low, size_t ldl, size_t slow)
+{
+    __shared__ double tt[32][33];
+    int t = blockIdx.x, bi = 0;
+    while (t > bi) { t -= bi + 1; bi++; }
+    const int bj = t;  // bj <= bi
+    const double* sp = src + (size_t)blockIdx.y * ssrc;
+    double* lp = low + (size_t)blockIdx.y * slow;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (lower_src) {
+        for (int r = ty; r < 32; r += 8) {
+            const int i = bi * 32 + r, j = bj * 32 + tx;
+            if (i < n && j < n && j <= i) lp[(size_t)i * ldl + j] = sp[(size_t)i * lds + j];
+        }
+        return;
+    }
+    for (int r = ty; r < 32; r += 8) {  // mirrored tile: src[bj-rows][bi-cols]
+        const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+        tt[r][tx] = (i2 < n && j2 < n) ? sp[(size_t)i2 * lds + j2] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i < n && j < n && j <= i) lp[(size_t)i * ldl + j] = tt[tx][r];
+    }
+}
+
+// ---- LEFT-LOOKING panel kernel: one 64-row chunk of one problem's 64-column panel per CTA ----
+// chunk(i, c) = cov(i, c) - sum_{t < j0} L(i, t) L(c, t)   for the rows i of the chunk and the panel's columns c = j0 .. j0+63,
+// read straight from the caller's covariance (through its UPPER triangle for the row-major build): the factor
+// workspace is written once per entry and never updated in place, so a problem's HBM traffic is cov once + L once + the
+// left-looking re-reads of L (against a read-modify-write of the whole trailing matrix per panel for the right-looking form).
+//   DIAG:   the chunk is the diagonal block (rows j0 .. j0+63): its lower triangle is stored for potf64_kernel.
+//   !DIAG:  the chunk lies below: it is solved against the factored diagonal block, X = chunk L_jj^-T, and stored as L.
+// Eight warps, each 8 rows x 64 columns as eight accumulator tiles.  The panel's own rows of L (the B operand, shared by all
+// warps) are staged through shared memory 64 columns of K at a time (cp.async, double-buffered); the chunk's rows (the A
+// operand, private to a warp) come straight from global memory, 32 contiguous bytes per lane.  K is contracted in a permuted
+// order (the lane's four consecutive values feed four successive DMMAs, the same permutation on both operands), which is what
+// makes 16-byte loads possible without any shuffle; the same trick feeds accumulator tiles back as A operands in the solve.
+constexpr int CR_LDS = 66;              // stage row stride: 132 words = 4 mod 32, conflict-free for the 16-byte fragment reads
+constexpr int CR_LDD = 72;              // row stride of the diagonal block in the solve (pairs of columns per lane)
+constexpr int CR_STAGE = 64 * CR_LDS;
+constexpr int CR_LDI = 12;
+constexpr int CR_SMEM_DOUBLES = 2 * CR_STAGE + 64 * CR_LDI;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(256, 3)
+chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, double* F, size_t ld, size_t sF, int k, int j0,
+                 const double* __restrict__ rdiag, size_t sr, const int* __restrict__ info)
+{
+    extern __shared__ __align__(16) double sm[];
+    const size_t pb = blockIdx.y;
+    if (info[pb] != 0) return;  // an earlier panel of this problem failed (uniform)
+    const double* cp = cov + pb * scov;
+    double* Fp = F + pb * sF;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int nb = k - j0 < 64 ? k - j0 : 64;
+    const int r0 = j0 + 64 * ((int)blockIdx.x + (DIAG ? 0 : 1));
+    const int row = r0 + 8 * warp + g;
+    const bool live = row < k;
+    const int nstage = j0 >> 6;
+
+    auto load_stage = [&](int s, int buf) {  // rows j0 .. j0+63 of L, columns 64 s .. 64 s + 63
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = tid + 256 * it, r = idx >> 5, c2 = (idx & 31) * 2;
+            double* dst = sm + buf * CR_STAGE + r * CR_LDS + c2;
+            if (j0 + r < k) cp_async16(dst, Fp + (size_t)(j0 + r) * ld + 64 * s + c2);
+            else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+        }
+        cp_async_commit();
+    };
+    if (nstage > 0) load_stage(0, 0);
+
+    double acc[8][2];
+#pragma unroll
+    for (int n = 0; n < 8; n++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c = j0 + 8 * n + 2 * t4 + e;
+            const bool ok = live && c < k && (!DIAG || (n <= warp && c <= row));
+            acc[n][e] = ok ? (lower_src ? cp[(size_t)row * k + c] : cp[(size_t)c * k + row]) : 0.0;
+        }
+
+    const double* arow = Fp + (size_t)(live ? row : j0) * ld + 4 * t4;
+    for (int s = 0; s < nstage; s++) {
+        double2 a[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u][0] = *reinterpret_cast<const double2*>(arow + 64 * s + 16 * u);
+            a[u][1] = *reinterpret_cast<const double2*>(arow + 64 * s + 16 * u + 2);
+        }
+        if (s + 1 < nstage) {
+            load_stage(s + 1, (s + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* Bs = sm + (s & 1) * CR_STAGE + g * CR_LDS + 4 * t4;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double a0 = live ? -a[u][0].x : 0.0, a1 = live ? -a[u][0].y : 0.0;
+            const double a2 = live ? -a[u][1].x : 0.0, a3 = live ? -a[u][1].y : 0.0;
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+                if (DIAG && n > warp) continue;  // warp-uniform: tiles above the diagonal are never read
+                const double2 b01 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u);
+                const double2 b23 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u + 2);
+                dmma(acc[n][0], acc[n][1], a0, b01.x);
+                dmma(acc[n][0], acc[n][1], a1, b01.y);
+                dmma(acc[n][0], acc[n][1], a2, b23.x);
+                dmma(acc[n][0], acc[n][1], a3, b23.y);
+            }
+        }
+        __syncthreads();  // the buffer is refilled by the load issued in the next iteration
+    }
+
+    if (DIAG) {
+        if (live) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+                if (n > warp) continue;
+                const int c = j0 + 8 * n + 2 * t4;
+                if (c <= row && c < k) Fp[(size_t)row * ld + c] = acc[n][0];
+                if (c + 1 <= row && c + 1 < k) Fp[(size_t)row * ld + c + 1] = acc[n][1];
+            }
+        }
+        return;
+    }
+
+    // ---- X = chunk L_jj^-T ----
+    double* Dm = sm;                    // [64][CR_LDD]: L_jj, zero above the diagonal and beyond nb
+    double* I8 = sm + 2 * CR_STAGE;     // [8 blocks][8][CR_LDI]: inverses of its 8 x 8 diagonal blocks
+#pragma unroll 4
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        Dm[r * CR_LDD + c] = (r < nb && c <= r) ? Fp[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (lane < 8 && 8 * warp < nb) {  // warp b inverts block b: lane c solves L_bb y = e_c (reciprocal pivots from potf64)
+        const int b0 = 8 * warp;
+        const double* rd = rdiag + pb * sr + j0;
+        double y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            double v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                if (t < i) v = fma(-Dm[(b0 + i) * CR_LDD + b0 + t], y[t], v);
+            y[i] = v * ((b0 + i < nb) ? rd[b0 + i] : 1.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) I8[(b0 + i) * CR_LDI + lane] = y[i];
+    }
+    __syncthreads();
+    double* xr = Fp + (size_t)(live ? row : j0) * ld + j0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if (8 * b < nb) {  // uniform
+            const double2 iv = *reinterpret_cast<const double2*>(I8 + (8 * b + g) * CR_LDI + 2 * t4);
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, acc[b][0], iv.x);
+            dmma(x0, x1, acc[b][1], iv.y);
+            const int c = 8 * b + 2 * t4;
+            if (live && c + 1 < nb) *reinterpret_cast<double2*>(xr + c) = make_double2(x0, x1);
+            else if (live && c < nb) xr[c] = x0;
+            const double m0 = -x0, m1 = -x1;
+#pragma unroll
+            for (int tc = b + 1; tc < 8; tc++) {
+                if (8 * tc < nb) {  // uniform
+                    const double2 lv = *reinterpret_cast<const double2*>(Dm + (8 * tc + g) * CR_LDD + 8 * b + 2 * t4);
+                    dmma(acc[tc][0], acc[tc][1], m0, lv.x);
+                    dmma(acc[tc][0], acc[tc][1], m1, lv.y);
+                }
+            }
+        }
+    }
+}
+
 // ---- projection, one CTA per problem ----
 // y = mean + L z, V = L^T G^T (k x k2), S = V^T V = G cov G^T, G y = G mean + V^T z, alpha = S^-1 (r - G y),
 // x = mean + L (z + V alpha).  Two coalesced passes over the lower factor.  Pass 1 (V): every warp takes every eighth row of
@@ -450,4 +716,65 @@ extern "C" int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2
     ht_mid_project_kernel<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}
+
+extern "C" int htnk_syrk64_batched(cudaStream_t st, const double* X, size_t ldx, size_t sX, double* C, size_t ldc, size_t sC,
+                                   int rows, int nb, size_t nbatch)
+{
+    if (rows <= 0 || nb <= 0 || nbatch == 0) return 0;
+    if (nb > 64) return -202;
+    const size_t smem = (size_t)2 * 64 * SY_LD * sizeof(double);
+    if (cudaFuncSetAttribute(syrk64_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    const int nt = (rows + 63) / 64, ntile = nt * (nt + 1) / 2;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
+        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        syrk64_batched_kernel<<<dim3((unsigned)ntile, nbt), 128, smem, st>>>(X + b0 * sX, ldx, sX, C + b0 * sC, ldc, sC, rows, nb, ntile);
+        htnk_count_launch();
+        if (cudaGetLastError() != cudaSuccess) return -201;
+    }
+    return 0;
+}
+
+extern "C" int htnk_lower_copy_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src,
+                                       double* low, size_t ldl, size_t slow, size_t nbatch)
+{
+    if (n <= 0 || nbatch == 0) return 0;
+    const int nt = (n + 31) / 32, ntile = nt * (nt + 1) / 2;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
+        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        lower_copy_batched_kernel<<<dim3((unsigned)ntile, nbt), 256, 0, st>>>(src + b0 * ssrc, lds, ssrc, n, lower_src, low + b0 * slow, ldl, slow);
+        htnk_count_launch();
+        if (cudaGetLastError() != cudaSuccess) return -201;
+    }
+    return 0;
+}
+
+/* one panel step of the left-looking batched factorisation: diag != 0 forms the diagonal block (rows j0 .. j0+63) for
+ * htnk_potf64_batched, diag == 0 forms and solves the rows below it against the factored block. */
+extern "C" int htnk_chol_rows_batched(cudaStream_t st, const double* cov, size_t scov, int lower_src, double* F, size_t ld,
+                                      size_t sF, int k, int j0, const double* rdiag, size_t sr, const int* info, int diag,
+                                      size_t nbatch)
+{
+    if (nbatch == 0 || k <= 0 || j0 >= k) return 0;
+    if ((ld & 1) || (sF & 1) || (j0 & 63) || (reinterpret_cast<uintptr_t>(F) & 15)) return -202;
+    const int nb = k - j0 < 64 ? k - j0 : 64;
+    const int nchunk = diag ? 1 : (k - j0 - nb + 63) / 64;
+    if (nchunk <= 0) return 0;
+    const size_t smem = (size_t)CR_SMEM_DOUBLES * sizeof(double);
+    if (cudaFuncSetAttribute(chol_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(chol_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -201;
+    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
+        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
+        const dim3 grid((unsigned)nchunk, nbt);
+        if (diag)
+            chol_rows_kernel<true><<<grid, 256, smem, st>>>(cov + b0 * scov, scov, lower_src, F + b0 * sF, ld, sF, k, j0,
+                                                            rdiag + b0 * sr, sr, info + b0);
+        else
+            chol_rows_kernel<false><<<grid, 256, smem, st>>>(cov + b0 * scov, scov, lower_src, F + b0 * sF, ld, sF, k, j0,
+                                                             rdiag + b0 * sr, sr, info + b0);
+        htnk_count_launch();
+        if (cudaGetLastError() != cudaSuccess) return -201;
+    }
+    return 0;
 }

@@ -411,6 +411,16 @@ done:
  * call per problem (>= 0.5 ms each).  Reference per problem: src/htnorm.c:85-187, src/htnorm_distributions.c:58-88. */
 #define MID_K_MAX 1024
 #define MID_K2_MAX 4
+static int ht_mid_left_looking(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HTN_MID_LEFT");
+        v = (e && *e == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, unsigned flags, int k2, int k,
                               const double* mean, const double* cov, const double* g, const double* r, double* out,
                               int* info_dev)
@@ -437,16 +447,27 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
         HTN_TRY(htnk_normal_fill(st, &sv, np, 1, &seg, NULL));
         HTN_CUDA(cudaMemsetAsync(info_dev + p0, 0, np * sizeof(int), st));
         HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nsteps * sizeof(unsigned), st));
-        HTN_TRY(htnk_sym_expand_batched(st, cov + p0 * (size_t)k * k, (size_t)k, (size_t)k * k, k,
-                                        (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, F, ld, sF, np));
-        for (int q = 0; q < nsteps; q++) {
-            const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64, rows = k - j0 - nb;
-            HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
-            if (rows <= 0) break;
-            double* x = F + (size_t)(j0 + nb) * ld + j0; /* A21 -> L21 = A21 L11^-T, then A22 -= L21 L21^T (lower tiles) */
-            HTN_TRY(htnk_trsm_rows_batched(st, x, ld, sF, rows, F + (size_t)j0 * ld + j0, ld, sF, nb, rd + j0, sr, np));
-            HTN_TRY(htnk_gemm_tn_batched(st, rows, rows, nb, -1.0, x, ld, sF, x, ld, sF, 1.0, F + (size_t)(j0 + nb) * ld + j0 + nb,
-                                         ld, sF, HTNK_GEMM_C_LOWER, np));
+        if (ht_mid_left_looking()) {
+            /* left-looking: every panel is formed from the caller's covariance and the panels before it, written once */
+            const double* cv = cov + p0 * (size_t)k * k;
+            const int lo = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
+            for (int q = 0; q < nsteps; q++) {
+                const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64;
+                HTN_TRY(htnk_chol_rows_batched(st, cv, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info_dev + p0, 1, np));
+                HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
+                HTN_TRY(htnk_chol_rows_batched(st, cv, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info_dev + p0, 0, np));
+            }
+        } else {
+            HTN_TRY(htnk_lower_copy_batched(st, cov + p0 * (size_t)k * k, (size_t)k, (size_t)k * k, k,
+                                            (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, F, ld, sF, np));
+            for (int q = 0; q < nsteps; q++) {
+                const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64, rows = k - j0 - nb;
+                HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
+                if (rows <= 0) break;
+                double* x = F + (size_t)(j0 + nb) * ld + j0; /* A21 -> L21 = A21 L11^-T, then A22 -= L21 L21^T (lower tiles) */
+                HTN_TRY(htnk_trsm_rows_batched(st, x, ld, sF, rows, F + (size_t)j0 * ld + j0, ld, sF, nb, rd + j0, sr, np));
+                HTN_TRY(htnk_syrk64_batched(st, x, ld, sF, F + (size_t)(j0 + nb) * ld + j0 + nb, ld, sF, rows, nb, np));
+            }
         }
         HTN_TRY(htnk_ht_mid_project(st, np, k, k2, F, ld, sF, mean + p0 * (size_t)k, g + p0 * (size_t)k2 * k,
                                     r + p0 * (size_t)k2, zs, (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out + p0 * (size_t)k,
