@@ -368,11 +368,15 @@ lower_copy_batched_kernel(const double* __restrict__ src, size_t lds, size_t ssr
 // operand, private to a warp) come straight from global memory, 32 contiguous bytes per lane.  K is contracted in a permuted
 // order (the lane's four consecutive values feed four successive DMMAs, the same permutation on both operands), which is what
 // makes 16-byte loads possible without any shuffle; the same trick feeds accumulator tiles back as A operands in the solve.
-constexpr int CR_LDS = 66;              // stage row stride: 132 words = 4 mod 32, conflict-free for the 16-byte fragment reads
+constexpr int CR_KS = 32;               // K columns per stage
+constexpr int CR_LDS = 34;              // stage row stride: 68 words = 4 mod 32, conflict-free for the 16-byte fragment reads
 constexpr int CR_LDD = 72;              // row stride of the diagonal block in the solve (pairs of columns per lane)
-constexpr int CR_STAGE = 64 * CR_LDS;
+constexpr int CR_TILE = 64 * CR_LDS;    // one operand of one stage
+constexpr int CR_STAGE = 2 * CR_TILE;   // [B rows | A rows]
+constexpr int CR_NSTAGE = 2;
 constexpr int CR_LDI = 12;
-constexpr int CR_SMEM_DOUBLES = 2 * CR_STAGE + 64 * CR_LDI;
+constexpr int CR_SMEM_DOUBLES = CR_NSTAGE * CR_STAGE + 64 * CR_LDI;
+static_assert(CR_NSTAGE * CR_STAGE >= 64 * CR_LDD, "the diagonal block reuses the stage ring");
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src)
 {
@@ -396,20 +400,27 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
     if (info[pb] != 0) return;  // an earlier panel of this problem failed (uniform)
     const double* cp = cov + pb * scov;
     double* Fp = F + pb * sF;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // DIAG: row block rb needs rb + 1 tiles; warps w and w + 4 share a scheduler partition, so they take the row blocks
+    // (w, 7 - w): nine tiles per partition
+    const int warp = (DIAG && (tid >> 5) >= 4) ? 11 - (tid >> 5) : (tid >> 5);
     const int g = lane >> 2, t4 = lane & 3;
     const int nb = k - j0 < 64 ? k - j0 : 64;
     const int r0 = j0 + 64 * ((int)blockIdx.x + (DIAG ? 0 : 1));
     const int row = r0 + 8 * warp + g;
     const bool live = row < k;
-    const int nstage = j0 >> 6;
+    const int nstage = j0 / CR_KS;
 
-    auto load_stage = [&](int s, int buf) {  // rows j0 .. j0+63 of L, columns 64 s .. 64 s + 63
+    // stage s: columns 32 s .. 32 s + 31 of the panel's rows j0 .. j0+63 (B) and of the chunk's rows r0 .. r0+63 (A; the same
+    // rows when DIAG); rows beyond k are zero-filled
+    auto load_stage = [&](int s, int buf) {
+        double* base = sm + buf * CR_STAGE;
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int idx = tid + 256 * it, r = idx >> 5, c2 = (idx & 31) * 2;
-            double* dst = sm + buf * CR_STAGE + r * CR_LDS + c2;
-            if (j0 + r < k) cp_async16(dst, Fp + (size_t)(j0 + r) * ld + 64 * s + c2);
+        for (int it = 0; it < (DIAG ? 4 : 8); it++) {
+            const int idx = tid + 256 * it, op = idx >> 10, r = (idx >> 4) & 63, c2 = (idx & 15) * 2;
+            const int grow = (op ? r0 : j0) + r;
+            double* dst = base + op * CR_TILE + r * CR_LDS + c2;
+            if (grow < k) cp_async16(dst, Fp + (size_t)grow * ld + CR_KS * s + c2);
             else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
         }
         cp_async_commit();
@@ -426,14 +437,7 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
             acc[n][e] = ok ? (lower_src ? cp[(size_t)row * k + c] : cp[(size_t)c * k + row]) : 0.0;
         }
 
-    const double* arow = Fp + (size_t)(live ? row : j0) * ld + 4 * t4;
     for (int s = 0; s < nstage; s++) {
-        double2 a[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            a[u][0] = *reinterpret_cast<const double2*>(arow + 64 * s + 16 * u);
-            a[u][1] = *reinterpret_cast<const double2*>(arow + 64 * s + 16 * u + 2);
-        }
         if (s + 1 < nstage) {
             load_stage(s + 1, (s + 1) & 1);
             cp_async_wait<1>();
@@ -442,10 +446,12 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
         }
         __syncthreads();
         const double* Bs = sm + (s & 1) * CR_STAGE + g * CR_LDS + 4 * t4;
+        const double* As = Bs + (DIAG ? 0 : CR_TILE) + 8 * warp * CR_LDS;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const double a0 = live ? -a[u][0].x : 0.0, a1 = live ? -a[u][0].y : 0.0;
-            const double a2 = live ? -a[u][1].x : 0.0, a3 = live ? -a[u][1].y : 0.0;
+        for (int u = 0; u < CR_KS / 16; u++) {
+            const double2 a01 = *reinterpret_cast<const double2*>(As + 16 * u);
+            const double2 a23 = *reinterpret_cast<const double2*>(As + 16 * u + 2);
+            const double a0 = -a01.x, a1 = -a01.y, a2 = -a23.x, a3 = -a23.y;
 #pragma unroll
             for (int n = 0; n < 8; n++) {
                 if (DIAG && n > warp) continue;  // warp-uniform: tiles above the diagonal are never read
@@ -475,11 +481,19 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
 
     // ---- X = chunk L_jj^-T ----
     double* Dm = sm;                    // [64][CR_LDD]: L_jj, zero above the diagonal and beyond nb
-    double* I8 = sm + 2 * CR_STAGE;     // [8 blocks][8][CR_LDI]: inverses of its 8 x 8 diagonal blocks
-#pragma unroll 4
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-        const int r = idx >> 6, c = idx & 63;
-        Dm[r * CR_LDD + c] = (r < nb && c <= r) ? Fp[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+    double* I8 = sm + CR_NSTAGE * CR_STAGE;  // [8 blocks][8][CR_LDI]: inverses of its 8 x 8 diagonal blocks
+    {
+        double dv[16];  // all sixteen loads in flight before the first store
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+            const int idx = tid + 256 * it, r = idx >> 6, c = idx & 63;
+            dv[it] = (r < nb && c <= r) ? Fp[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+            const int idx = tid + 256 * it, r = idx >> 6, c = idx & 63;
+            Dm[r * CR_LDD + c] = dv[it];
+        }
     }
     __syncthreads();
     if (lane < 8 && 8 * warp < nb) {  // warp b inverts block b: lane c solves L_bb y = e_c (reciprocal pivots from potf64)
@@ -677,6 +691,194 @@ ht_mid_project_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F
     }
 }
 
+
+// ---- projection, second form: L streamed through shared memory by cp.async ----
+// The two passes over the factor of ht_mid_project_kernel were latency-bound (a warp waited for every row it read).  Here the
+// rows of L go through a three-deep ring of 16 KB row blocks filled by cp.async (two blocks always in flight per CTA, the
+// first blocks of pass 2 already during the k2 x k2 solve), and the arithmetic reads shared memory:
+//   pass 1 (rows ascending): thread t owns the columns t + 256 m of V = L^T G^T and adds row i's contribution L[i][j] G[:, i]
+//           - no reduction across threads at all, V never leaves the registers;
+//   pass 2 (rows descending, so the tail of pass 1 is still in L2): one row per warp (k <= 256) or per 2 / 4 warps.
+// KP = 256 MC is the row pitch of a block, RB = 2048 / KP its rows.
+template <int MC>
+__global__ void __launch_bounds__(PT)
+ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F, size_t ld, size_t sF,
+                       const double* __restrict__ mean, const double* __restrict__ gm, const double* __restrict__ rv,
+                       const double* __restrict__ zs, int g_colmajor, double* __restrict__ out, int* __restrict__ info)
+{
+    constexpr int KP = 256 * MC, RB = 2048 / KP, NSEG = 8 / RB, LOGH = (MC == 1 ? 7 : MC == 2 ? 8 : 9);
+    extern __shared__ __align__(16) double ps[];
+    const int kq = (k + 3) & ~3;
+    double* w = ps;             // [kq]
+    double* Gt = w + kq;        // [kq][4]: G transposed, rows beyond k2 zero
+    double* red = Gt + 4 * kq;  // [8 warps][24]
+    double* pp = red + 192;     // [8]: partial row sums of pass 2
+    double* bufs = pp + 8;      // [3][2048]
+    __shared__ double s_al[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (k + RB - 1) / RB;
+    for (size_t pb = blockIdx.x; pb < nbatch; pb += gridDim.x) {
+        if (info[pb] != 0) continue;  // cov not PD: out untouched (uniform across the CTA)
+        const double* Lp = F + pb * sF;
+        const double* mp = mean + pb * (size_t)k;
+        const double* zp = zs + pb * (size_t)k;
+        auto issue = [&](int q) {  // block q of the stream: pass 1 blocks ascending, then pass 2 blocks descending
+            if (q < 2 * nblk) {
+                const int i0 = (q < nblk ? q : 2 * nblk - 1 - q) * RB;
+                double* dst = bufs + (q % 3) * 2048;
+#pragma unroll
+                for (int it = 0; it < 4; it++) {
+                    const int idx = tid + 256 * it, r = idx >> LOGH, c2 = (idx & (KP / 2 - 1)) * 2, i = i0 + r;
+                    if (i < k && c2 <= i) cp_async16(dst + r * KP + c2, Lp + (size_t)i * ld + c2);
+                }
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        for (int c = 0; c < 4; c++)
+            for (int i = tid; i < k; i += PT) {
+                double v = 0.0;
+                if (c < k2) v = g_colmajor ? gm[pb * (size_t)k2 * k + (size_t)i * k2 + c] : gm[pb * (size_t)k2 * k + (size_t)c * k + i];
+                Gt[4 * i + c] = v;
+            }
+        double acc[MC][4];
+#pragma unroll
+        for (int m = 0; m < MC; m++) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0;
+        for (int q = 0; q < nblk; q++) {
+            cp_async_wait<1>();
+            __syncthreads();
+            issue(q + 2);
+            const double* B = bufs + (q % 3) * 2048;
+            const int i0 = q * RB;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const int i = i0 + r;
+                if (i < k) {  // uniform
+                    const double2 g01 = *reinterpret_cast<const double2*>(Gt + 4 * i);
+                    const double2 g23 = *reinterpret_cast<const double2*>(Gt + 4 * i + 2);
+#pragma unroll
+                    for (int m = 0; m < MC; m++) {
+                        const int j = tid + 256 * m;
+                        if (j <= i) {
+                            const double l = B[r * KP + j];
+                            acc[m][0] = fma(l, g01.x, acc[m][0]);
+                            acc[m][1] = fma(l, g01.y, acc[m][1]);
+                            acc[m][2] = fma(l, g23.x, acc[m][2]);
+                            acc[m][3] = fma(l, g23.y, acc[m][3]);
+                        }
+                    }
+                }
+            }
+        }
+        // S (10 values), V^T z (4), G mean (4) over the thread's own columns, fixed-order reduction
+        double part[18], zr[MC];
+#pragma unroll
+        for (int q = 0; q < 18; q++) part[q] = 0.0;
+#pragma unroll
+        for (int m = 0; m < MC; m++) {
+            const int j = tid + 256 * m;
+            zr[m] = 0.0;
+            if (j < k) {
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b <= a; b++) part[q++] += acc[m][a] * acc[m][b];
+                const double zj = zp[j], mj = mp[j];
+                zr[m] = zj;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    part[10 + a] += acc[m][a] * zj;
+                    part[14 + a] += Gt[4 * j + a] * mj;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 18; q++) {
+            double v = part[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp * 24 + q] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double t[18];
+            for (int q = 0; q < 18; q++) {
+                double v = 0.0;
+                for (int ww = 0; ww < PT / 32; ww++) v += red[ww * 24 + q];
+                t[q] = v;
+            }
+            double sq[4][4], bv[4], ri[4];
+            int q = 0, f2 = 0;
+            for (int a = 0; a < 4; a++)
+                for (int b = 0; b <= a; b++, q++) sq[a][b] = a < k2 ? t[q] : (a == b ? 1.0 : 0.0);
+            for (int a = 0; a < 4; a++) bv[a] = a < k2 ? rv[pb * (size_t)k2 + a] - t[14 + a] - t[10 + a] : 0.0;
+            if (k2 == 1) {
+                bv[0] = bv[0] / sq[0][0];  // the reference divides by the scalar (src/htnorm.c:77)
+            } else {
+                for (int j = 0; j < 4; j++) {
+                    const double ajj = sq[j][j];
+                    if (ajj <= 0.0 && f2 == 0) f2 = j + 1;
+                    const double rinv = fast_rsqrt(ajj);
+                    ri[j] = rinv;
+                    for (int i = j + 1; i < 4; i++) sq[i][j] *= rinv;
+                    for (int i = j + 1; i < 4; i++)
+                        for (int cc = j + 1; cc <= i; cc++) sq[i][cc] = fma(-sq[i][j], sq[cc][j], sq[i][cc]);
+                }
+                for (int i = 0; i < 4; i++) {
+                    double v = bv[i];
+                    for (int u = 0; u < i; u++) v = fma(-sq[i][u], bv[u], v);
+                    bv[i] = v * ri[i];
+                }
+                for (int i = 3; i >= 0; i--) {
+                    double v = bv[i];
+                    for (int u = i + 1; u < 4; u++) v = fma(-sq[u][i], bv[u], v);
+                    bv[i] = v * ri[i];
+                }
+            }
+            for (int a = 0; a < 4; a++) s_al[a] = f2 ? 0.0 : bv[a];  // G cov G^T not PD: the unprojected y (src/htnorm.c:170)
+            info[pb] = f2;
+        }
+        __syncthreads();
+        {
+            const double a0 = s_al[0], a1 = s_al[1], a2 = s_al[2], a3 = s_al[3];
+#pragma unroll
+            for (int m = 0; m < MC; m++) {
+                const int j = tid + 256 * m;
+                if (j < k) w[j] = zr[m] + ((acc[m][0] * a0 + acc[m][1] * a1) + (acc[m][2] * a2 + acc[m][3] * a3));
+            }
+        }
+        // pass 2: x[i] = mean[i] + sum_{j <= i} L[i][j] w[j]
+        for (int q = nblk; q < 2 * nblk; q++) {
+            cp_async_wait<1>();
+            __syncthreads();  // also orders the writes of w before the first block
+            issue(q + 2);
+            const double* B = bufs + (q % 3) * 2048;
+            const int i0 = (2 * nblk - 1 - q) * RB;
+            const int r = warp / NSEG, seg = warp % NSEG, i = i0 + r;
+            double v = 0.0;
+            if (i < k)
+                for (int j = seg * 32 + lane; j <= i; j += 32 * NSEG) v = fma(B[r * KP + j], w[j], v);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (NSEG == 1) {
+                if (lane == 0 && i < k) out[pb * (size_t)k + i] = mp[i] + v;
+            } else {
+                if (lane == 0) pp[warp] = v;
+                __syncthreads();
+                if (tid < RB && i0 + tid < k) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int sg = 0; sg < NSEG; sg++) sacc += pp[tid * NSEG + sg];
+                    out[pb * (size_t)k + i0 + tid] = mp[i0 + tid] + sacc;
+                }
+            }
+        }
+        __syncthreads();  // the ring, w and Gt are rewritten for the next problem
+    }
+}
+
 }  // namespace
 
 extern "C" int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t sF, int j0, int nb, double* rdiag, size_t sr,
@@ -704,16 +906,35 @@ extern "C" int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2
 {
     if (nbatch == 0) return 0;
     if (k < 1 || k > 4 * PT || k2 < 1 || k2 > 4) return -202;
-    const size_t smem = ((size_t)10 * k + 8 * 24) * sizeof(double);
-    if (cudaFuncSetAttribute(ht_mid_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    static int use_old = -1;
+    if (use_old < 0) {
+        const char* e = getenv("HTN_MID_PROJ");
+        use_old = (e && *e == '1') ? 1 : 0;
+    }
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ht_mid_project_kernel, PT, smem);
+    if (use_old) {
+        const size_t smem = ((size_t)10 * k + 8 * 24) * sizeof(double);
+        if (cudaFuncSetAttribute(ht_mid_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ht_mid_project_kernel, PT, smem);
+        if (per_sm < 1) per_sm = 1;
+        size_t grid = (size_t)sms * per_sm;
+        if (grid > nbatch) grid = nbatch;
+        ht_mid_project_kernel<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
+        htnk_count_launch();
+        return cudaGetLastError() == cudaSuccess ? 0 : -201;
+    }
+    if ((ld & 1) || (sF & 1) || (reinterpret_cast<uintptr_t>(F) & 15)) return -202;
+    const size_t kq = ((size_t)k + 3) & ~(size_t)3;
+    const size_t smem = (5 * kq + 192 + 8 + 3 * 2048) * sizeof(double);
+    auto kern = k <= 256 ? ht_mid_project2_kernel<1> : k <= 512 ? ht_mid_project2_kernel<2> : ht_mid_project2_kernel<4>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT, smem);
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)sms * per_sm;
     if (grid > nbatch) grid = nbatch;
-    ht_mid_project_kernel<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
+    kern<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }
