@@ -667,29 +667,3 @@ extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows,
 }
 
 // the same panel solve for nbatch independent problems in one launch (gridDim.y = problem; strides in doubles)
-extern "C" int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, size_t sx, int nrows, const double* l, size_t ldl,
-                                      size_t sl, int nb, const double* rdiag, size_t sr, size_t nbatch)
-{
-    if (nrows <= 0 || nb <= 0 || nbatch == 0) return 0;
-    if (nb > NB) return -202;
-    const size_t smem = (size_t)(((nb + 7) & ~7) * LDB + 16 * 8 * LDI) * sizeof(double);  // several CTAs per SM for narrow blocks
-    if (cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)((size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double))) != cudaSuccess)
-        return -201;
-    const bool big = nrows >= 96;  // 128-row CTAs amortise the load of L and its 8 x 8 inverses
-    if (big && cudaFuncSetAttribute(trsm_rows_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)((size_t)(NB * LDB + 16 * 8 * LDI) * sizeof(double))) != cudaSuccess)
-        return -201;
-    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
-        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        if (big)
-            trsm_rows_kernel<512><<<dim3((unsigned)((nrows + TR_ROWS - 1) / TR_ROWS), nbt), 512, smem, st>>>(
-                x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
-        else
-            trsm_rows_kernel<128><<<dim3((unsigned)((nrows + 31) / 32), nbt), 128, smem, st>>>(
-                x + b0 * sx, ldx, nrows, l + b0 * sl, ldl, nb, rdiag + b0 * sr, sx, sl, sr);
-        htnk_count_launch();
-        if (cudaGetLastError() != cudaSuccess) return -201;
-    }
-    return 0;
-}

@@ -364,18 +364,6 @@ extern "C" int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, i
 }
 
 // lower-triangle copies (zeros above) of nbatch symmetric matrices in one launch
-extern "C" int htnk_sym_expand_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src,
-                                       double* low, size_t ldl, size_t slow, size_t nbatch)
-{
-    if (n <= 0 || nbatch == 0) return 0;
-    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
-        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        dim3 grid((n + 31) / 32, (n + 31) / 32, nbt);
-        sym_expand_kernel<<<grid, 256, 0, st>>>(src + b0 * ssrc, lds, n, lower_src, nullptr, 0, low + b0 * slow, ldl, ssrc, slow);
-        if (status()) return -201;
-    }
-    return 0;
-}
 
 extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                               size_t ldd)

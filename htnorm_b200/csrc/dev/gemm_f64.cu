@@ -353,33 +353,3 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
 // The same GEMM over nbatch independent problems in ONE launch (gridDim.y = problem): problem b reads A + b sA, B + b sB and
 // updates C + b sC.  cp.async kernels only (no tensor maps per problem); N tile 64 / 32 / 8 by N.  Used by the batched
 // mid-size independent problems (hyperplane.c ht_independent_mid): the trailing updates of all problems' factorisations.
-extern "C" int htnk_gemm_tn_batched(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda,
-                                    size_t sA, const double* B, size_t ldb, size_t sB, double beta, double* C, size_t ldc,
-                                    size_t sC, int mode, size_t nbatch)
-{
-    if (M <= 0 || N <= 0 || nbatch == 0) return 0;
-    if (K < 0) return -202;
-    if ((lda & 1) || (ldb & 1) || (sA & 1) || (sB & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
-        return -202;
-    GemmParams p;
-    p.M = M; p.N = N; p.K = K;
-    p.alpha = alpha; p.beta = beta;
-    p.bias = nullptr;
-    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
-    p.mode = mode; p.ktri = 0; p.kext0 = 0;
-    p.skip = nullptr;
-    p.sA = sA; p.sB = sB; p.sC = sC;
-    p.tiles_m = (M + BM - 1) / BM;
-    const int bn = N <= 8 ? 8 : (N <= 32 ? 32 : 64);
-    p.tiles_n = (N + bn - 1) / bn;
-    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {  // gridDim.y limit
-        const unsigned nb = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        p.A = A + b0 * sA; p.B = B + b0 * sB; p.C = C + b0 * sC;
-        int rc;
-        if (bn == 64) rc = launch<64, 2, 2, 8, 4, 2>(st, p, nb);
-        else if (bn == 32) rc = launch<32, 8, 1, 2, 4, 2>(st, p, nb);
-        else rc = launch<8, 8, 1, 2, 1, 1>(st, p, nb);
-        if (rc) return rc;
-    }
-    return 0;
-}

@@ -155,22 +155,9 @@ int htnk_ht_small_warp(cudaStream_t st, size_t nproblems, int k, int k2, const d
                        const double* g, const double* r, const double* zs, double* out, int* info, unsigned* counter);
 
 /* ---- batched building blocks of the mid-size independent problems (one launch over all problems; strides in doubles) ---- */
-int htnk_gemm_tn_batched(cudaStream_t st, int M, int N, int K, double alpha, const double* A, size_t lda, size_t sA,
-                         const double* B, size_t ldb, size_t sB, double beta, double* C, size_t ldc, size_t sC, int mode,
-                         size_t nbatch);
-int htnk_trsm_rows_batched(cudaStream_t st, double* x, size_t ldx, size_t sx, int nrows, const double* l, size_t ldl, size_t sl,
-                           int nb, const double* rdiag, size_t sr, size_t nbatch);
 /* left-looking panel step of the batched mid-size factorisation (mid_batched.cu): diagonal block / rows below it */
 int htnk_chol_rows_batched(cudaStream_t st, const double* cov, size_t scov, int lower_src, double* F, size_t ld, size_t sF, int k,
                            int j0, const double* rdiag, size_t sr, const int* info, int diag, size_t nbatch);
-/* C (rows x rows, lower 64 x 64 tiles) -= X X^T with X rows x nb (nb <= 64), batched (mid_batched.cu) */
-int htnk_syrk64_batched(cudaStream_t st, const double* X, size_t ldx, size_t sX, double* C, size_t ldc, size_t sC, int rows, int nb,
-                        size_t nbatch);
-/* lower-triangle copy (nothing written above the diagonal) of nbatch symmetric matrices (mid_batched.cu) */
-int htnk_lower_copy_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src, double* low,
-                            size_t ldl, size_t slow, size_t nbatch);
-int htnk_sym_expand_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src, double* low,
-                            size_t ldl, size_t slow, size_t nbatch);
 /* diagonal 64-block of every problem's lower factorisation, one WARP per problem (mid_batched.cu): factorises in place the
  * nb x nb (nb <= 64) block at row / column j0 of F + b * sF (lower storage, leading dimension ld); rdiag + b * sr + j0 receives
  * 1 / L[j][j]; info[b] receives j0 + j + 1 at the first pivot <= 0 (if it still holds 0; problems whose info is set are skipped).

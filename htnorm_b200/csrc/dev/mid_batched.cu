@@ -1,14 +1,15 @@
-// Batched MID-SIZE independent problems (128 < k <= 1024, one sample per problem, each with its own mean / cov / G / r):
-// the building blocks that have no counterpart among the single-problem kernels.  Round 1 ran one full shared-path call
-// per problem in a host loop (>= 0.5 ms each); here ALL problems go through one launch sequence (hyperplane.c
-// ht_independent_mid): per 64-column panel step
-//     potf64_kernel          diagonal 64-block of every problem, ONE WARP per problem (this file)
-//     trsm_rows_kernel       rows below, batched over problems (chol.cu)            L21 = A21 L11^-T
-//     gemm_tn_kernel         rank-64 trailing update, batched (gemm_f64.cu)          A22 -= L21 L21^T
-// and at the end ht_mid_project_kernel (this file), one CTA per problem: the projection of src/htnorm.c:85-187 formed
-// around the factor in two coalesced passes over L (V = L^T G^T, G cov G^T = V^T V, x = mean + L (z + V alpha)).
-// A 128-wide potf2 block costs 33 us of latency-bound work on one SM; the warp-level 64-block factorisation of
-// small_warp.cu runs eight problems per SM at once - that is what makes a batched factorisation worth having.
+// Batched MID-SIZE independent problems (128 < k <= 1024, one sample per problem, each with its own mean / cov / G / r).
+// Round 1 ran one full shared-path call per problem in a host loop (>= 0.5 ms each); here ALL problems go through one launch
+// sequence (hyperplane.c ht_independent_mid), a LEFT-LOOKING blocked Cholesky with 64-column panels:
+//     chol_rows_kernel<true>    diagonal block of the panel: cov block - L(rows, :j0) L(rows, :j0)^T            (this file)
+//     potf64_kernel             its factorisation, ONE WARP per problem (the scheme of small_warp.cu)          (this file)
+//     chol_rows_kernel<false>   rows below: (cov chunk - L(chunk, :j0) L(panel, :j0)^T) L_jj^-T, stored as L   (this file)
+// and at the end ht_mid_project_kernel, one CTA per problem: the projection of src/htnorm.c:85-187 formed around the factor
+// in two passes over L (V = L^T G^T, G cov G^T = V^T V, x = mean + L (z + V alpha)).
+// Left-looking because the workspace is then written once per entry: the first version was right-looking (a batched
+// rank-64 update of the whole trailing matrix per panel through the general GEMM kernel: 7.2 ms for 4096 x k = 256, 4.8 ms
+// with a dedicated 64 x 64-tile update kernel) and spent its time re-reading and re-writing the trailing matrices; this
+// form reads each covariance once, writes each factor once, and runs the same batch in 1.9 ms.
 // Reference semantics per problem: src/htnorm.c:85-187, src/htnorm_distributions.c:58-88; error codes SURVEY Q5 / Q6.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -256,106 +257,6 @@ potf64_kernel(double* __restrict__ F, size_t ld, size_t sF, int j0, int nb, doub
     }
 }
 
-// ---- rank-nb trailing update, batched: C(i, j) -= X_i X_j^T for the 64 x 64 tiles i >= j of every problem ----
-// X = L21 (rows x nb, nb <= 64, the panel just solved), C = the trailing matrix (lower storage).  One CTA of four warps per
-// tile: both 64 x nb blocks of X are loaded whole (no K pipeline: K is one panel), every warp owns a 32 x 32 corner (16
-// accumulator tiles, DMMA m8n8k4, the K order of the other GEMM kernels is irrelevant here: nothing else computes these sums).
-constexpr int SY_LD = 68;  // 64 + 4: the fragment pattern (row g, column t4) is bank-conflict free
-__global__ void __launch_bounds__(128)
-syrk64_batched_kernel(const double* __restrict__ X, size_t ldx, size_t sX, double* __restrict__ C, size_t ldc, size_t sC,
-                      int rows, int nb, int ntile)
-{
-    extern __shared__ __align__(16) double sy[];
-    double* Xi = sy;                 // [64][SY_LD]
-    double* Xj = sy + 64 * SY_LD;    // [64][SY_LD]
-    // tile index -> (ti, tj), ti >= tj, row by row
-    int t = blockIdx.x, ti = 0;
-    while (t > ti) { t -= ti + 1; ti++; }
-    const int tj = t;
-    (void)ntile;
-    const double* Xp = X + (size_t)blockIdx.y * sX;
-    double* Cp = C + (size_t)blockIdx.y * sC;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
-    const int nbp = (nb + 3) & ~3;
-    for (int idx = tid; idx < 64 * 64; idx += 128) {
-        const int r = idx >> 6, c = idx & 63;
-        const int ri = 64 * ti + r, rj = 64 * tj + r;
-        Xi[r * SY_LD + c] = (ri < rows && c < nb) ? Xp[(size_t)ri * ldx + c] : 0.0;
-        Xj[r * SY_LD + c] = (rj < rows && c < nb) ? Xp[(size_t)rj * ldx + c] : 0.0;
-    }
-    __syncthreads();
-    const int wm = warp >> 1, wn = warp & 1;  // 32 x 32 corner of the tile
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int k0 = 0; k0 < nbp; k0 += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) af[i] = Xi[(32 * wm + 8 * i + g) * SY_LD + k0 + t4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) bf[j] = Xj[(32 * wn + 8 * j + g) * SY_LD + k0 + t4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int m = 64 * ti + 32 * wm + 8 * i + g;
-        if (m >= rows) continue;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int n = 64 * tj + 32 * wn + 8 * j + 2 * t4;
-            if (n >= rows) continue;
-            double* cp = Cp + (size_t)m * ldc + n;
-            if (n + 1 < rows && ((ldc & 1) == 0)) {
-                double2 o = *reinterpret_cast<double2*>(cp);
-                o.x -= acc[i][j][0];
-                o.y -= acc[i][j][1];
-                *reinterpret_cast<double2*>(cp) = o;
-            } else {
-                cp[0] -= acc[i][j][0];
-                if (n + 1 < rows) cp[1] -= acc[i][j][1];
-            }
-        }
-    }
-}
-
-// lower-triangle copy of every problem's covariance: F[i][j] = cov(i, j) for j <= i, read through the UPPER triangle of the
-// row-major input (lower_src = 0) or through the lower one (column-major build).  Only the 32 x 32 tiles on and
-// below the diagonal are touched: nothing of the factor's workspace above the diagonal is ever read.
-__global__ void __launch_bounds__(256)
-lower_copy_batched_kernel(const double* __restrict__ src, size_t lds, size_t ssrc, int n, int lower_src,
-                          double* __restrict__ low, size_t ldl, size_t slow)
-{
-    __shared__ double tt[32][33];
-    int t = blockIdx.x, bi = 0;
-    while (t > bi) { t -= bi + 1; bi++; }
-    const int bj = t;  // bj <= bi
-    const double* sp = src + (size_t)blockIdx.y * ssrc;
-    double* lp = low + (size_t)blockIdx.y * slow;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (lower_src) {
-        for (int r = ty; r < 32; r += 8) {
-            const int i = bi * 32 + r, j = bj * 32 + tx;
-            if (i < n && j < n && j <= i) lp[(size_t)i * ldl + j] = sp[(size_t)i * lds + j];
-        }
-        return;
-    }
-    for (int r = ty; r < 32; r += 8) {  // mirrored tile: src[bj-rows][bi-cols]
-        const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
-        tt[r][tx] = (i2 < n && j2 < n) ? sp[(size_t)i2 * lds + j2] : 0.0;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int i = bi * 32 + r, j = bj * 32 + tx;
-        if (i < n && j < n && j <= i) lp[(size_t)i * ldl + j] = tt[tx][r];
-    }
-}
-
 // ---- LEFT-LOOKING panel kernel: one 64-row chunk of one problem's 64-column panel per CTA ----
 // chunk(i, c) = cov(i, c) - sum_{t < j0} L(i, t) L(c, t)   for the rows i of the chunk and the panel's columns c = j0 .. j0+63,
 // read straight from the caller's covariance (through its UPPER triangle for the row-major build): the factor
@@ -370,13 +271,11 @@ lower_copy_batched_kernel(const double* __restrict__ src, size_t lds, size_t ssr
 // makes 16-byte loads possible without any shuffle; the same trick feeds accumulator tiles back as A operands in the solve.
 constexpr int CR_KS = 32;               // K columns per stage
 constexpr int CR_LDS = 34;              // stage row stride: 68 words = 4 mod 32, conflict-free for the 16-byte fragment reads
-constexpr int CR_LDD = 72;              // row stride of the diagonal block in the solve (pairs of columns per lane)
 constexpr int CR_TILE = 64 * CR_LDS;    // one operand of one stage
 constexpr int CR_STAGE = 2 * CR_TILE;   // [B rows | A rows]
 constexpr int CR_NSTAGE = 2;
-constexpr int CR_LDI = 12;
-constexpr int CR_SMEM_DOUBLES = CR_NSTAGE * CR_STAGE + 64 * CR_LDI;
-static_assert(CR_NSTAGE * CR_STAGE >= 64 * CR_LDD, "the diagonal block reuses the stage ring");
+constexpr int CR_SMEM_DOUBLES = CR_NSTAGE * CR_STAGE;
+static_assert(CR_STAGE >= 36 * 64, "the packed diagonal block reuses one buffer of the ring");
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src)
 {
@@ -390,23 +289,41 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-template <bool DIAG>
-__global__ void __launch_bounds__(256, 3)
-chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, double* F, size_t ld, size_t sF, int k, int j0,
-                 const double* __restrict__ rdiag, size_t sr, const int* __restrict__ info)
+// one K stage of a warp's NT accumulator tiles (a branch per tile count: a predicated-off DMMA still occupies the pipe)
+template <int NT>
+__device__ __forceinline__ void cr_stage_mma(double (&acc)[8][2], const double* As, const double* Bs)
 {
-    extern __shared__ __align__(16) double sm[];
-    const size_t pb = blockIdx.y;
-    if (info[pb] != 0) return;  // an earlier panel of this problem failed (uniform)
-    const double* cp = cov + pb * scov;
-    double* Fp = F + pb * sF;
+#pragma unroll
+    for (int u = 0; u < CR_KS / 16; u++) {
+        const double2 a01 = *reinterpret_cast<const double2*>(As + 16 * u);
+        const double2 a23 = *reinterpret_cast<const double2*>(As + 16 * u + 2);
+        const double a0 = -a01.x, a1 = -a01.y, a2 = -a23.x, a3 = -a23.y;
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+            const double2 b01 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u);
+            const double2 b23 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u + 2);
+            dmma(acc[n][0], acc[n][1], a0, b01.x);
+            dmma(acc[n][0], acc[n][1], a1, b01.y);
+            dmma(acc[n][0], acc[n][1], a2, b23.x);
+            dmma(acc[n][0], acc[n][1], a3, b23.y);
+        }
+    }
+}
+
+// offset of the packed 8 x 8 block (tc, b), tc >= b, of the factored diagonal block
+__device__ __forceinline__ int cr_blk(int tc, int b) { return (tc * (tc + 1) / 2 + b) * 64; }
+
+template <bool DIAG>
+__device__ __forceinline__ void cr_chunk(double* sm, const double* __restrict__ cp, int lower_src, double* Fp, size_t ld, int k,
+                                         int j0, int chunk, const double* __restrict__ rd)
+{
     const int tid = threadIdx.x, lane = tid & 31;
     // DIAG: row block rb needs rb + 1 tiles; warps w and w + 4 share a scheduler partition, so they take the row blocks
     // (w, 7 - w): nine tiles per partition
     const int warp = (DIAG && (tid >> 5) >= 4) ? 11 - (tid >> 5) : (tid >> 5);
     const int g = lane >> 2, t4 = lane & 3;
     const int nb = k - j0 < 64 ? k - j0 : 64;
-    const int r0 = j0 + 64 * ((int)blockIdx.x + (DIAG ? 0 : 1));
+    const int r0 = j0 + 64 * (DIAG ? 0 : chunk + 1);
     const int row = r0 + 8 * warp + g;
     const bool live = row < k;
     const int nstage = j0 / CR_KS;
@@ -425,7 +342,23 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
         }
         cp_async_commit();
     };
+    // the factored diagonal block L_jj as 36 packed 8 x 8 blocks (cr_blk), into the ring buffer the K loop no longer needs:
+    // issued before the last stage is computed, so its latency hides behind that stage (or behind the covariance loads)
+    double* const Dm = sm + (nstage & 1) * CR_STAGE;
+    auto load_diag = [&]() {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = tid + 256 * it, r = idx >> 5, c2 = (idx & 31) * 2;
+            if ((c2 >> 3) <= (r >> 3)) {
+                double* dst = Dm + cr_blk(r >> 3, c2 >> 3) + (r & 7) * 8 + (c2 & 7);
+                if (r < nb && c2 <= r) cp_async16(dst, Fp + (size_t)(j0 + r) * ld + j0 + c2);
+                else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+            }
+        }
+        cp_async_commit();
+    };
     if (nstage > 0) load_stage(0, 0);
+    if (!DIAG && nstage <= 1) load_diag();
 
     double acc[8][2];
 #pragma unroll
@@ -441,27 +374,30 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
         if (s + 1 < nstage) {
             load_stage(s + 1, (s + 1) & 1);
             cp_async_wait<1>();
+        } else if (!DIAG && nstage > 1) {
+            load_diag();  // the other buffer was released by the barrier that ended the previous iteration
+            cp_async_wait<1>();
+        } else if (!DIAG) {
+            cp_async_wait<1>();  // nstage == 1: the diagonal block was requested after stage 0 and may still be in flight
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
         const double* Bs = sm + (s & 1) * CR_STAGE + g * CR_LDS + 4 * t4;
         const double* As = Bs + (DIAG ? 0 : CR_TILE) + 8 * warp * CR_LDS;
-#pragma unroll
-        for (int u = 0; u < CR_KS / 16; u++) {
-            const double2 a01 = *reinterpret_cast<const double2*>(As + 16 * u);
-            const double2 a23 = *reinterpret_cast<const double2*>(As + 16 * u + 2);
-            const double a0 = -a01.x, a1 = -a01.y, a2 = -a23.x, a3 = -a23.y;
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-                if (DIAG && n > warp) continue;  // warp-uniform: tiles above the diagonal are never read
-                const double2 b01 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u);
-                const double2 b23 = *reinterpret_cast<const double2*>(Bs + 8 * n * CR_LDS + 16 * u + 2);
-                dmma(acc[n][0], acc[n][1], a0, b01.x);
-                dmma(acc[n][0], acc[n][1], a1, b01.y);
-                dmma(acc[n][0], acc[n][1], a2, b23.x);
-                dmma(acc[n][0], acc[n][1], a3, b23.y);
+        if (DIAG) {
+            switch (warp) {  // warp-uniform: only the tiles on and below the diagonal
+            case 0: cr_stage_mma<1>(acc, As, Bs); break;
+            case 1: cr_stage_mma<2>(acc, As, Bs); break;
+            case 2: cr_stage_mma<3>(acc, As, Bs); break;
+            case 3: cr_stage_mma<4>(acc, As, Bs); break;
+            case 4: cr_stage_mma<5>(acc, As, Bs); break;
+            case 5: cr_stage_mma<6>(acc, As, Bs); break;
+            case 6: cr_stage_mma<7>(acc, As, Bs); break;
+            default: cr_stage_mma<8>(acc, As, Bs); break;
             }
+        } else {
+            cr_stage_mma<8>(acc, As, Bs);
         }
         __syncthreads();  // the buffer is refilled by the load issued in the next iteration
     }
@@ -480,43 +416,33 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
     }
 
     // ---- X = chunk L_jj^-T ----
-    double* Dm = sm;                    // [64][CR_LDD]: L_jj, zero above the diagonal and beyond nb
-    double* I8 = sm + CR_NSTAGE * CR_STAGE;  // [8 blocks][8][CR_LDI]: inverses of its 8 x 8 diagonal blocks
-    {
-        double dv[16];  // all sixteen loads in flight before the first store
-#pragma unroll
-        for (int it = 0; it < 16; it++) {
-            const int idx = tid + 256 * it, r = idx >> 6, c = idx & 63;
-            dv[it] = (r < nb && c <= r) ? Fp[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
-        }
-#pragma unroll
-        for (int it = 0; it < 16; it++) {
-            const int idx = tid + 256 * it, r = idx >> 6, c = idx & 63;
-            Dm[r * CR_LDD + c] = dv[it];
-        }
-    }
+    cp_async_wait<0>();
     __syncthreads();
-    if (lane < 8 && 8 * warp < nb) {  // warp b inverts block b: lane c solves L_bb y = e_c (reciprocal pivots from potf64)
-        const int b0 = 8 * warp;
-        const double* rd = rdiag + pb * sr + j0;
-        double y[8];
+    if (8 * warp < nb) {  // warp b inverts the diagonal 8 x 8 block b IN PLACE: lane c < 8 owns column c of the inverse
+        double* Db = Dm + cr_blk(warp, warp);
+        rd += 8 * warp;
+        double v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            double v = (i == lane) ? 1.0 : 0.0;
+        for (int i = 0; i < 8; i++) v[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-            for (int t = 0; t < 8; t++)
-                if (t < i) v = fma(-Dm[(b0 + i) * CR_LDD + b0 + t], y[t], v);
-            y[i] = v * ((b0 + i < nb) ? rd[b0 + i] : 1.0);
+        for (int t = 0; t < 8; t++) {  // right-looking: one multiply and one fused multiply-add on the chain per step
+            v[t] *= (8 * warp + t < nb) ? rd[t] : 1.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i > t) v[i] = fma(-Db[i * 8 + t], v[t], v[i]);  // broadcast reads
         }
+        __syncwarp();  // every lane has read the block before it is overwritten
+        if (lane < 8) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) I8[(b0 + i) * CR_LDI + lane] = y[i];
+            for (int i = 0; i < 8; i++) Db[i * 8 + lane] = v[i];
+        }
     }
     __syncthreads();
     double* xr = Fp + (size_t)(live ? row : j0) * ld + j0;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
         if (8 * b < nb) {  // uniform
-            const double2 iv = *reinterpret_cast<const double2*>(I8 + (8 * b + g) * CR_LDI + 2 * t4);
+            const double2 iv = *reinterpret_cast<const double2*>(Dm + cr_blk(b, b) + g * 8 + 2 * t4);
             double x0 = 0.0, x1 = 0.0;
             dmma(x0, x1, acc[b][0], iv.x);
             dmma(x0, x1, acc[b][1], iv.y);
@@ -527,7 +453,7 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
 #pragma unroll
             for (int tc = b + 1; tc < 8; tc++) {
                 if (8 * tc < nb) {  // uniform
-                    const double2 lv = *reinterpret_cast<const double2*>(Dm + (8 * tc + g) * CR_LDD + 8 * b + 2 * t4);
+                    const double2 lv = *reinterpret_cast<const double2*>(Dm + cr_blk(tc, b) + g * 8 + 2 * t4);
                     dmma(acc[tc][0], acc[tc][1], m0, lv.x);
                     dmma(acc[tc][0], acc[tc][1], m1, lv.y);
                 }
@@ -536,173 +462,44 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
     }
 }
 
-// ---- projection, one CTA per problem ----
-// y = mean + L z, V = L^T G^T (k x k2), S = V^T V = G cov G^T, G y = G mean + V^T z, alpha = S^-1 (r - G y),
-// x = mean + L (z + V alpha).  Two coalesced passes over the lower factor.  Pass 1 (V): every warp takes every eighth row of
-// L and accumulates that row's contribution to ALL columns of a 256-column chunk in registers (lane = columns lane + 32 m: eight
-// independent 256-byte loads in flight per row), the eight warps' partial sums are then added in a fixed order.  Pass 2: one row
-// per warp at a time.
-constexpr int PT = 256;
-__global__ void __launch_bounds__(PT)
-ht_mid_project_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F, size_t ld, size_t sF,
-                      const double* __restrict__ mean, const double* __restrict__ gm, const double* __restrict__ rv,
-                      const double* __restrict__ zs, int g_colmajor, double* __restrict__ out, int* __restrict__ info)
+// (Forming the NEXT panel's diagonal block at the end of the first chunk's CTA - its rows are complete by then - saves a launch
+// per panel but was measured slower: 1103 us against 1062 us for the three panels of k = 256, and it lengthens the critical
+// path of small batches.  The diagonal block keeps its own launch.)
+template <bool DIAG>
+__global__ void __launch_bounds__(256, 3)
+chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, double* F, size_t ld, size_t sF, int k, int j0,
+                 const double* __restrict__ rdiag, size_t sr, const int* __restrict__ info)
 {
-    extern __shared__ __align__(16) double ps[];
-    double* z = ps;               // [k]
-    double* w = z + k;            // [k]
-    double* Gs = w + k;           // [4][k]
-    double* Vs = Gs + 4 * k;      // [k][4]
-    double* red = Vs + 4 * k;     // [8 warps][24]
-    __shared__ double s_al[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (size_t pb = blockIdx.x; pb < nbatch; pb += gridDim.x) {
-        if (info[pb] != 0) continue;  // cov not PD: out untouched (uniform across the CTA)
-        const double* Lp = F + pb * sF;
-        const double* mp = mean + pb * (size_t)k;
-        for (int i = tid; i < k; i += PT) z[i] = zs[pb * (size_t)k + i];
-        for (int idx = tid; idx < 4 * k; idx += PT) {
-            const int c = idx / k, i = idx - c * k;
-            double v = 0.0;
-            if (c < k2) v = g_colmajor ? gm[pb * (size_t)k2 * k + (size_t)i * k2 + c] : gm[pb * (size_t)k2 * k + (size_t)c * k + i];
-            Gs[idx] = v;
-            Vs[idx] = 0.0;
-        }
-        __syncthreads();
-        // pass 1: V[j][c] = sum_{i >= j} L[i][j] G[c][i], a 256-column chunk at a time
-        for (int j0 = 0; j0 < k; j0 += 256) {
-            double acc[8][4];
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) acc[m][c] = 0.0;
-            for (int i = j0 + warp; i < k; i += PT / 32) {
-                const double* row = Lp + (size_t)i * ld + j0 + lane;
-                double l[8];
-#pragma unroll
-                for (int m = 0; m < 8; m++) l[m] = (j0 + lane + 32 * m <= i) ? __ldg(row + 32 * m) : 0.0;
-                const double g0 = Gs[i], g1 = Gs[k + i], g2 = Gs[2 * k + i], g3 = Gs[3 * k + i];
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    acc[m][0] = fma(l[m], g0, acc[m][0]);
-                    acc[m][1] = fma(l[m], g1, acc[m][1]);
-                    acc[m][2] = fma(l[m], g2, acc[m][2]);
-                    acc[m][3] = fma(l[m], g3, acc[m][3]);
-                }
-            }
-            for (int ww = 0; ww < PT / 32; ww++) {  // fixed order: bit-reproducible
-                if (warp == ww) {
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const int j = j0 + lane + 32 * m;
-                        if (j < k) {
-                            double4* vp = reinterpret_cast<double4*>(Vs + 4 * j);
-                            double4 v = *vp;
-                            v.x += acc[m][0]; v.y += acc[m][1]; v.z += acc[m][2]; v.w += acc[m][3];
-                            *vp = v;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        // S (10 values), V^T z (4), G mean (4): per-thread partial sums over the rows j = tid + 256 m, fixed-order reduction
-        double part[18];
-#pragma unroll
-        for (int q = 0; q < 18; q++) part[q] = 0.0;
-        for (int j = tid; j < k; j += PT) {
-            const double4 v = *reinterpret_cast<const double4*>(Vs + 4 * j);
-            const double va[4] = {v.x, v.y, v.z, v.w};
-            int q = 0;
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b <= a; b++) part[q++] += va[a] * va[b];
-            const double zj = z[j], mj = mp[j];
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                part[10 + a] += va[a] * zj;
-                part[14 + a] += Gs[a * k + j] * mj;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 18; q++) {
-            double v = part[q];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp * 24 + q] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double t[18];
-            for (int q = 0; q < 18; q++) {
-                double v = 0.0;
-                for (int ww = 0; ww < PT / 32; ww++) v += red[ww * 24 + q];
-                t[q] = v;
-            }
-            double s[4][4], bv[4], ri[4];
-            int q = 0, f2 = 0;
-            for (int a = 0; a < 4; a++)
-                for (int b = 0; b <= a; b++, q++) s[a][b] = a < k2 ? t[q] : (a == b ? 1.0 : 0.0);
-            for (int a = 0; a < 4; a++) bv[a] = a < k2 ? rv[pb * (size_t)k2 + a] - t[14 + a] - t[10 + a] : 0.0;
-            if (k2 == 1) {
-                bv[0] = bv[0] / s[0][0];  // the reference divides by the scalar (src/htnorm.c:77)
-            } else {
-                for (int j = 0; j < 4; j++) {
-                    const double ajj = s[j][j];
-                    if (ajj <= 0.0 && f2 == 0) f2 = j + 1;
-                    const double rinv = fast_rsqrt(ajj);
-                    ri[j] = rinv;
-                    for (int i = j + 1; i < 4; i++) s[i][j] *= rinv;
-                    for (int i = j + 1; i < 4; i++)
-                        for (int cc = j + 1; cc <= i; cc++) s[i][cc] = fma(-s[i][j], s[cc][j], s[i][cc]);
-                }
-                for (int i = 0; i < 4; i++) {
-                    double v = bv[i];
-                    for (int u = 0; u < i; u++) v = fma(-s[i][u], bv[u], v);
-                    bv[i] = v * ri[i];
-                }
-                for (int i = 3; i >= 0; i--) {
-                    double v = bv[i];
-                    for (int u = i + 1; u < 4; u++) v = fma(-s[u][i], bv[u], v);
-                    bv[i] = v * ri[i];
-                }
-            }
-            for (int a = 0; a < 4; a++) s_al[a] = f2 ? 0.0 : bv[a];  // G cov G^T not PD: the unprojected y (src/htnorm.c:170)
-            info[pb] = f2;
-        }
-        __syncthreads();
-        const double a0 = s_al[0], a1 = s_al[1], a2 = s_al[2], a3 = s_al[3];
-        for (int j = tid; j < k; j += PT) {
-            const double4 v = *reinterpret_cast<const double4*>(Vs + 4 * j);
-            w[j] = z[j] + ((v.x * a0 + v.y * a1) + (v.z * a2 + v.w * a3));
-        }
-        __syncthreads();
-        // pass 2: x[i] = mean[i] + sum_{j <= i} L[i][j] w[j], two rows per warp at a time (a long and a short one)
-        for (int i = warp; i < k; i += PT / 32) {
-            const double* row = Lp + (size_t)i * ld;
-            double v = 0.0;
-            for (int j = lane; j <= i; j += 32) v = fma(__ldg(row + j), w[j], v);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) out[pb * (size_t)k + i] = mp[i] + v;
-        }
-        __syncthreads();
+    extern __shared__ __align__(16) double sm[];
+    const size_t pb = blockIdx.y;
+    if (info[pb] != 0) return;  // an earlier panel of this problem failed (uniform)
+    const double* cp = cov + pb * scov;
+    double* Fp = F + pb * sF;
+    if (DIAG) {
+        cr_chunk<true>(sm, cp, lower_src, Fp, ld, k, j0, 0, nullptr);
+    } else {
+        cr_chunk<false>(sm, cp, lower_src, Fp, ld, k, j0, (int)blockIdx.x, rdiag + pb * sr + j0);
     }
 }
 
-
-// ---- projection, second form: L streamed through shared memory by cp.async ----
-// The two passes over the factor of ht_mid_project_kernel were latency-bound (a warp waited for every row it read).  Here the
-// rows of L go through a three-deep ring of 16 KB row blocks filled by cp.async (two blocks always in flight per CTA, the
-// first blocks of pass 2 already during the k2 x k2 solve), and the arithmetic reads shared memory:
-//   pass 1 (rows ascending): thread t owns the columns t + 256 m of V = L^T G^T and adds row i's contribution L[i][j] G[:, i]
-//           - no reduction across threads at all, V never leaves the registers;
+// ---- projection, one CTA per problem: L streamed through shared memory by cp.async ----
+// y = mean + L z, V = L^T G^T (k x k2), S = V^T V = G cov G^T, G y = G mean + V^T z, alpha = S^-1 (r - G y),
+// x = mean + L (z + V alpha): two passes over the lower factor.  The rows of L go through a ring of PJ_NBUF 16 KB row blocks
+// filled by cp.async (PJ_NBUF - 1 blocks in flight per CTA, the first blocks of pass 2 already during the k2 x k2 solve), and
+// the arithmetic reads shared memory:
+//   pass 1 (rows ascending): thread t owns the columns t + 256 m of V and adds row i's contribution L[i][j] G[:, i] - no
+//           reduction across threads at all, V never leaves the registers;
 //   pass 2 (rows descending, so the tail of pass 1 is still in L2): one row per warp (k <= 256) or per 2 / 4 warps.
+// Variants measured and dropped (4096 x k = 256, this kernel 0.565 ms of the 1.9 ms call): a first form with warps reading
+// rows straight from global memory (0.75 ms: every warp waited for every row); single bulk copies per row counted by
+// full / empty mbarrier pairs with row-length-packed blocks (0.69 ms: a quarter of the instructions, but short rows make
+// small TMA requests and the ring advances at the pace of the slowest warp); a ring of four blocks (two CTAs per SM: 0.63 ms).
 // KP = 256 MC is the row pitch of a block, RB = 2048 / KP its rows.
+constexpr int PT = 256;    // threads of a projection CTA
+constexpr int PJ_NBUF = 3;  // ring depth of the projection's row blocks (PJ_NBUF - 1 blocks in flight)
 template <int MC>
 __global__ void __launch_bounds__(PT)
-ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F, size_t ld, size_t sF,
+ht_mid_project_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F, size_t ld, size_t sF,
                        const double* __restrict__ mean, const double* __restrict__ gm, const double* __restrict__ rv,
                        const double* __restrict__ zs, int g_colmajor, double* __restrict__ out, int* __restrict__ info)
 {
@@ -713,7 +510,7 @@ ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ 
     double* Gt = w + kq;        // [kq][4]: G transposed, rows beyond k2 zero
     double* red = Gt + 4 * kq;  // [8 warps][24]
     double* pp = red + 192;     // [8]: partial row sums of pass 2
-    double* bufs = pp + 8;      // [3][2048]
+    double* bufs = pp + 8;      // [PJ_NBUF][2048]
     __shared__ double s_al[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = (k + RB - 1) / RB;
@@ -725,17 +522,30 @@ ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ 
         auto issue = [&](int q) {  // block q of the stream: pass 1 blocks ascending, then pass 2 blocks descending
             if (q < 2 * nblk) {
                 const int i0 = (q < nblk ? q : 2 * nblk - 1 - q) * RB;
-                double* dst = bufs + (q % 3) * 2048;
+                // thread t copies the 16-byte piece (t mod KP/2) of the rows (t div KP/2) + (512 / KP) it; a warp whose first
+                // piece lies beyond the block's last row has nothing to copy (the triangle: half of all warp-blocks)
+                const int c2 = (tid & (KP / 2 - 1)) * 2, r0 = tid >> LOGH;
+                if (MC == 4) {  // 512 pieces per row: two per thread and row
+                    double* dst = bufs + (q % PJ_NBUF) * 2048;
 #pragma unroll
-                for (int it = 0; it < 4; it++) {
-                    const int idx = tid + 256 * it, r = idx >> LOGH, c2 = (idx & (KP / 2 - 1)) * 2, i = i0 + r;
-                    if (i < k && c2 <= i) cp_async16(dst + r * KP + c2, Lp + (size_t)i * ld + c2);
+                    for (int it = 0; it < 4; it++) {
+                        const int r = it >> 1, c4 = (tid + 256 * (it & 1)) * 2, i = i0 + r;
+                        if (i < k && c4 <= i) cp_async16(dst + r * KP + c4, Lp + (size_t)i * ld + c4);
+                    }
+                } else if (((tid & ~31) & (KP / 2 - 1)) * 2 <= i0 + RB - 1) {
+                    double* dst = bufs + (q % PJ_NBUF) * 2048 + r0 * KP + c2;
+                    const double* src = Lp + (size_t)(i0 + r0) * ld + c2;
+#pragma unroll
+                    for (int it = 0; it < 4; it++) {
+                        const int i = i0 + r0 + (512 / KP) * it;
+                        if (i < k && c2 <= i) cp_async16(dst + (512 / KP) * it * KP, src + (size_t)(512 / KP) * it * ld);
+                    }
                 }
             }
             cp_async_commit();
         };
-        issue(0);
-        issue(1);
+#pragma unroll
+        for (int q = 0; q < PJ_NBUF - 1; q++) issue(q);
         for (int c = 0; c < 4; c++)
             for (int i = tid; i < k; i += PT) {
                 double v = 0.0;
@@ -746,11 +556,12 @@ ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ 
 #pragma unroll
         for (int m = 0; m < MC; m++) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0;
         for (int q = 0; q < nblk; q++) {
-            cp_async_wait<1>();
+            cp_async_wait<PJ_NBUF - 2>();
             __syncthreads();
-            issue(q + 2);
-            const double* B = bufs + (q % 3) * 2048;
+            issue(q + PJ_NBUF - 1);
+            const double* B = bufs + (q % PJ_NBUF) * 2048;
             const int i0 = q * RB;
+            if (32 * warp <= i0 + RB - 1)  // the block's rows hold none of this warp's columns otherwise (m = 0 is its first)
 #pragma unroll
             for (int r = 0; r < RB; r++) {
                 const int i = i0 + r;
@@ -851,10 +662,10 @@ ht_mid_project2_kernel(size_t nbatch, int k, int k2, const double* __restrict__ 
         }
         // pass 2: x[i] = mean[i] + sum_{j <= i} L[i][j] w[j]
         for (int q = nblk; q < 2 * nblk; q++) {
-            cp_async_wait<1>();
+            cp_async_wait<PJ_NBUF - 2>();
             __syncthreads();  // also orders the writes of w before the first block
-            issue(q + 2);
-            const double* B = bufs + (q % 3) * 2048;
+            issue(q + PJ_NBUF - 1);
+            const double* B = bufs + (q % PJ_NBUF) * 2048;
             const int i0 = (2 * nblk - 1 - q) * RB;
             const int r = warp / NSEG, seg = warp % NSEG, i = i0 + r;
             double v = 0.0;
@@ -906,29 +717,13 @@ extern "C" int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2
 {
     if (nbatch == 0) return 0;
     if (k < 1 || k > 4 * PT || k2 < 1 || k2 > 4) return -202;
-    static int use_old = -1;
-    if (use_old < 0) {
-        const char* e = getenv("HTN_MID_PROJ");
-        use_old = (e && *e == '1') ? 1 : 0;
-    }
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (use_old) {
-        const size_t smem = ((size_t)10 * k + 8 * 24) * sizeof(double);
-        if (cudaFuncSetAttribute(ht_mid_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ht_mid_project_kernel, PT, smem);
-        if (per_sm < 1) per_sm = 1;
-        size_t grid = (size_t)sms * per_sm;
-        if (grid > nbatch) grid = nbatch;
-        ht_mid_project_kernel<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
-        htnk_count_launch();
-        return cudaGetLastError() == cudaSuccess ? 0 : -201;
-    }
     if ((ld & 1) || (sF & 1) || (reinterpret_cast<uintptr_t>(F) & 15)) return -202;
     const size_t kq = ((size_t)k + 3) & ~(size_t)3;
-    const size_t smem = (5 * kq + 192 + 8 + 3 * 2048) * sizeof(double);
-    auto kern = k <= 256 ? ht_mid_project2_kernel<1> : k <= 512 ? ht_mid_project2_kernel<2> : ht_mid_project2_kernel<4>;
+    const size_t smem = (5 * kq + 192 + 8 + PJ_NBUF * 2048) * sizeof(double);
+    auto kern = k <= 256 ? ht_mid_project_kernel<1> : k <= 512 ? ht_mid_project_kernel<2> : ht_mid_project_kernel<4>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT, smem);
     if (per_sm < 1) per_sm = 1;
@@ -937,37 +732,6 @@ extern "C" int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2
     kern<<<(unsigned)grid, PT, smem, st>>>(nbatch, k, k2, F, ld, sF, mean, g, r, zs, g_colmajor, out, info);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
-}
-
-extern "C" int htnk_syrk64_batched(cudaStream_t st, const double* X, size_t ldx, size_t sX, double* C, size_t ldc, size_t sC,
-                                   int rows, int nb, size_t nbatch)
-{
-    if (rows <= 0 || nb <= 0 || nbatch == 0) return 0;
-    if (nb > 64) return -202;
-    const size_t smem = (size_t)2 * 64 * SY_LD * sizeof(double);
-    if (cudaFuncSetAttribute(syrk64_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
-    const int nt = (rows + 63) / 64, ntile = nt * (nt + 1) / 2;
-    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
-        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        syrk64_batched_kernel<<<dim3((unsigned)ntile, nbt), 128, smem, st>>>(X + b0 * sX, ldx, sX, C + b0 * sC, ldc, sC, rows, nb, ntile);
-        htnk_count_launch();
-        if (cudaGetLastError() != cudaSuccess) return -201;
-    }
-    return 0;
-}
-
-extern "C" int htnk_lower_copy_batched(cudaStream_t st, const double* src, size_t lds, size_t ssrc, int n, int lower_src,
-                                       double* low, size_t ldl, size_t slow, size_t nbatch)
-{
-    if (n <= 0 || nbatch == 0) return 0;
-    const int nt = (n + 31) / 32, ntile = nt * (nt + 1) / 2;
-    for (size_t b0 = 0; b0 < nbatch; b0 += 65535) {
-        const unsigned nbt = (unsigned)(nbatch - b0 < 65535 ? nbatch - b0 : 65535);
-        lower_copy_batched_kernel<<<dim3((unsigned)ntile, nbt), 256, 0, st>>>(src + b0 * ssrc, lds, ssrc, n, lower_src, low + b0 * slow, ldl, slow);
-        htnk_count_launch();
-        if (cudaGetLastError() != cudaSuccess) return -201;
-    }
-    return 0;
 }
 
 /* one panel step of the left-looking batched factorisation: diag != 0 forms the diagonal block (rows j0 .. j0+63) for

@@ -411,14 +411,23 @@ done:
  * call per problem (>= 0.5 ms each).  Reference per problem: src/htnorm.c:85-187, src/htnorm_distributions.c:58-88. */
 #define MID_K_MAX 1024
 #define MID_K2_MAX 4
-static int ht_mid_left_looking(void)
+/* the launch sequence of one range of problems on one stream (workspace pointers already offset to the range) */
+static int ht_mid_range(cudaStream_t st, size_t np, unsigned flags, int k2, int k, const double* mean, const double* cov,
+                        const double* g, const double* r, const double* zs, double* F, size_t ld, size_t sF, double* rd,
+                        size_t sr, unsigned* ctr, double* out, int* info)
 {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("HTN_MID_LEFT");
-        v = (e && *e == '0') ? 0 : 1;
+    int rc = 0;
+    const int nsteps = (k + 63) / 64, lo = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
+    /* left-looking: every panel is formed from the caller's covariance and the panels before it, written once */
+    for (int q = 0; q < nsteps; q++) {
+        const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64;
+        HTN_TRY(htnk_chol_rows_batched(st, cov, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info, 1, np));
+        HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info, np, ctr + q));
+        HTN_TRY(htnk_chol_rows_batched(st, cov, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info, 0, np));
     }
-    return v;
+    HTN_TRY(htnk_ht_mid_project(st, np, k, k2, F, ld, sF, mean, g, r, zs, lo, out, info));
+done:
+    return rc;
 }
 
 static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, unsigned flags, int k2, int k,
@@ -431,14 +440,35 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
     const int nsteps = (k + 63) / 64;
     double *F = NULL, *rd = NULL, *zs = NULL;
     unsigned* ctr = NULL;
+    int side_used = 0;
+    /* Two halves of a large batch go down two streams: the diagonal-block kernel is one latency-bound warp per problem
+     * (eight warps per SM), so the other half's panel kernels fill the machine beside it. */
+    static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_fork, ev_join; } ms = {-1, NULL, NULL, NULL};
+    size_t split_min = 1024;
+    {
+        const char* e = getenv("HTN_MID_SPLIT"); /* experiments: smallest batch that is split (0 = never) */
+        if (e) split_min = (size_t)atol(e);
+    }
     /* the workspace holds a full k x ld factor per problem: very large batches go through in slices of <= 2 GiB of factors */
     size_t slice = ((size_t)2 << 30) / (sF * 8);
     if (slice < 1) slice = 1;
     if (slice > P) slice = P;
+    if (split_min && P >= split_min && ms.device != ctx->device) {
+        if (ms.device >= 0) {
+            cudaEventDestroy(ms.ev_fork);
+            cudaEventDestroy(ms.ev_join);
+            cudaStreamDestroy(ms.side);
+            ms.device = -1;
+        }
+        HTN_CUDA(cudaStreamCreateWithFlags(&ms.side, cudaStreamNonBlocking));
+        HTN_CUDA(cudaEventCreateWithFlags(&ms.ev_fork, cudaEventDisableTiming));
+        HTN_CUDA(cudaEventCreateWithFlags(&ms.ev_join, cudaEventDisableTiming));
+        ms.device = ctx->device;
+    }
     HTN_TRY(htn_dalloc(ctx, (void**)&F, slice * sF * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&rd, slice * sr * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&zs, slice * (size_t)k * 8));
-    HTN_TRY(htn_dalloc(ctx, (void**)&ctr, (size_t)nsteps * sizeof(unsigned)));
+    HTN_TRY(htn_dalloc(ctx, (void**)&ctr, (size_t)2 * nsteps * sizeof(unsigned)));
     for (size_t p0 = 0; p0 < P && !rc; p0 += slice) {
         const size_t np = P - p0 < slice ? P - p0 : slice;
         htnk_streams_t sv;
@@ -446,34 +476,29 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
         htnk_segment_t seg = {(size_t)k, zs, (size_t)k, NULL, NULL, NULL};
         HTN_TRY(htnk_normal_fill(st, &sv, np, 1, &seg, NULL));
         HTN_CUDA(cudaMemsetAsync(info_dev + p0, 0, np * sizeof(int), st));
-        HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nsteps * sizeof(unsigned), st));
-        if (ht_mid_left_looking()) {
-            /* left-looking: every panel is formed from the caller's covariance and the panels before it, written once */
-            const double* cv = cov + p0 * (size_t)k * k;
-            const int lo = (flags & HTN_FLAG_COLMAJOR) ? 1 : 0;
-            for (int q = 0; q < nsteps; q++) {
-                const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64;
-                HTN_TRY(htnk_chol_rows_batched(st, cv, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info_dev + p0, 1, np));
-                HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
-                HTN_TRY(htnk_chol_rows_batched(st, cv, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info_dev + p0, 0, np));
-            }
-        } else {
-            HTN_TRY(htnk_lower_copy_batched(st, cov + p0 * (size_t)k * k, (size_t)k, (size_t)k * k, k,
-                                            (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, F, ld, sF, np));
-            for (int q = 0; q < nsteps; q++) {
-                const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64, rows = k - j0 - nb;
-                HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info_dev + p0, np, ctr + q));
-                if (rows <= 0) break;
-                double* x = F + (size_t)(j0 + nb) * ld + j0; /* A21 -> L21 = A21 L11^-T, then A22 -= L21 L21^T (lower tiles) */
-                HTN_TRY(htnk_trsm_rows_batched(st, x, ld, sF, rows, F + (size_t)j0 * ld + j0, ld, sF, nb, rd + j0, sr, np));
-                HTN_TRY(htnk_syrk64_batched(st, x, ld, sF, F + (size_t)(j0 + nb) * ld + j0 + nb, ld, sF, rows, nb, np));
-            }
+        HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)2 * nsteps * sizeof(unsigned), st));
+        const size_t na = (split_min && np >= split_min) ? np / 2 : np, nbh = np - na;
+        if (nbh) {
+            HTN_CUDA(cudaEventRecord(ms.ev_fork, st));
+            HTN_CUDA(cudaStreamWaitEvent(ms.side, ms.ev_fork, 0));
+            side_used = 1;
         }
-        HTN_TRY(htnk_ht_mid_project(st, np, k, k2, F, ld, sF, mean + p0 * (size_t)k, g + p0 * (size_t)k2 * k,
-                                    r + p0 * (size_t)k2, zs, (flags & HTN_FLAG_COLMAJOR) ? 1 : 0, out + p0 * (size_t)k,
-                                    info_dev + p0));
+        for (int h = 0; h < (nbh ? 2 : 1) && !rc; h++) {
+            const size_t q0 = h ? na : 0, nq = h ? nbh : na, a0 = p0 + q0;
+            rc = ht_mid_range(h ? ms.side : st, nq, flags, k2, k, mean + a0 * (size_t)k, cov + a0 * (size_t)k * k,
+                              g + a0 * (size_t)k2 * k, r + a0 * (size_t)k2, zs + q0 * (size_t)k, F + q0 * sF, ld, sF,
+                              rd + q0 * sr, sr, ctr + h * nsteps, out + a0 * (size_t)k, info_dev + a0);
+        }
+        if (nbh) { /* the slice's workspace is reused by the next slice, and freed in stream order on st */
+            if (cudaEventRecord(ms.ev_join, ms.side) != cudaSuccess || cudaStreamWaitEvent(st, ms.ev_join, 0) != cudaSuccess) {
+                cudaStreamSynchronize(ms.side);
+                if (!rc) rc = HTN_E_CUDA;
+            }
+            side_used = 0;
+        }
     }
 done:
+    if (side_used) cudaStreamSynchronize(ms.side); /* an error between fork and join */
     htn_dfree(ctx, ctr);
     htn_dfree(ctx, zs);
     htn_dfree(ctx, rd);

@@ -862,8 +862,8 @@ def test_warp_per_problem_kernel_other_orders(h, oracle, k):
 
 @pytest.mark.parametrize("k,k2,P", [(129, 1, 40), (192, 4, 70), (200, 3, 33), (256, 4, 300), (300, 2, 20), (1000, 4, 6)])
 def test_mid_size_independent_problems_batched(h, oracle, k, k2, P):
-    """Independent problems with 128 < k <= 1024, k2 <= 4 go through ONE batched launch sequence (64-column panels:
-    warp-per-problem diagonal blocks, batched panel solve and rank-64 update, one projection kernel; hyperplane.c
+    """Independent problems with 128 < k <= 1024, k2 <= 4 go through ONE batched launch sequence (a left-looking Cholesky
+    with 64-column panels: panel kernel, warp-per-problem diagonal blocks, one projection kernel; hyperplane.c
     ht_independent_mid) instead of a host loop of shared-path calls: parity against the oracle (src/htnorm.c:85-187 per
     problem), the constraint at the 1e-12 bar, per-problem error codes in the first / a middle / the last panel, a
     singular G cov G^T, and the column-major flag."""
@@ -899,3 +899,26 @@ def test_mid_size_independent_problems_batched(h, oracle, k, k2, P):
                                                 flags=h._lib.HTN_FLAG_COLMAJOR)
     assert rel_err(xc, xo[:4] if False else oracle.hyperplane("pcg64", 4, c["mean"][:4], c["cov"][:4], c["g"][:4], c["r"][:4],
                                                                independent=True, seed0=21)[0]) < REL_TOL
+
+
+def test_mid_size_batch_split_over_two_streams(h, oracle, monkeypatch):
+    """Batches of >= 1024 mid-size problems go down two streams in halves (hyperplane.c ht_independent_mid): the result is
+    bit-identical to the single-stream run, matches the oracle, and an error code in either half lands on its problem."""
+    k, k2, P = 136, 3, 1100
+    c = cases.ht_independent_case(nproblems=P, k=k, k2=k2, rng_seed=77)
+    cov = c["cov"].copy()
+    cov[7][70, 70] = -1.0            # first half, second panel
+    cov[P - 2][135, 135] = -1.0      # second half, last pivot
+    x, info = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], cov, c["g"], c["r"], independent=True, seed0=5,
+                                                  raise_on_error=False)
+    monkeypatch.setenv("HTN_MID_SPLIT", "0")
+    x1, info1 = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], cov, c["g"], c["r"], independent=True, seed0=5,
+                                                    raise_on_error=False)
+    monkeypatch.delenv("HTN_MID_SPLIT")
+    ok = info == 0
+    assert np.array_equal(info, info1) and info[7] == 71 and info[P - 2] == 136 and int((~ok).sum()) == 2
+    assert np.array_equal(x[ok], x1[ok])
+    xo, io, _ = oracle.hyperplane("pcg64", P, c["mean"], cov, c["g"], c["r"], independent=True, seed0=5)
+    assert np.array_equal(info, io)
+    assert rel_err(x[ok], xo[ok]) < REL_TOL
+    assert constraint_violation(x[ok], c["g"][ok], c["r"][ok]) < RESID_TOL
