@@ -395,8 +395,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the figures that include the output gather")
     ap.add_argument("--no-configs", action="store_true",
-                    help="skip the `configs` object (cfg2 ... cfg5, generator alone; N = 1) and cfg5 over N GPUs (N > 1)")
-    ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5_shard,normal_fill", help="which entries of `configs` to run")
+                    help="skip the `configs` object (cfg2 ... cfg5, mid-size batch, generator alone; N = 1) and cfg5 over N GPUs (N > 1)")
+    ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5_shard,mid256,normal_fill", help="which entries of `configs` to run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,6 +1,6 @@
 """The other BASELINE.json configurations, measured by bench.py next to the headline (the `configs` object of its
-JSON line): cfg2 (2^20 independent small problems), cfg3 / cfg4 (structured precision), cfg5's one-GPU shard, and the
-standalone ziggurat generator with BOTH of its rooflines.  Device-resident synthetic inputs (SURVEY 8d shapes),
+JSON line): cfg2 (2^20 independent small problems), cfg3 / cfg4 (structured precision), cfg5's one-GPU shard, 4096
+independent mid-size problems (k = 256) in one call, and the standalone ziggurat generator with BOTH of its rooflines.  Device-resident synthetic inputs (SURVEY 8d shapes),
 CUDA events on the launching stream, a few steps each.  `frac` = SURVEY 8(d)'s algorithmic flops / bytes of the
 configuration divided by the measured time, over the measured peak (FP64 tensor: in-run DMMA microbenchmark; HBM:
 MEASURED_PEAKS.json).  Not the headline: `value` of the bench line stays the k = 1000 workload."""
@@ -74,6 +74,30 @@ def cfg2(h, torch, dev, hbm_gbs, nproblems=1 << 20):
                          "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
                          "fp64_tflops": flops / (ms * 1e-3) / 1e12},
             "failed_problems": bad, "max_abs_constraint_residual_first_4096": resid}
+
+
+def mid256(h, torch, dev, peak_tf, nproblems=4096, k=256, k2=4):
+    """independent MID-SIZE problems (own mean / cov / G / r each, one sample per problem) in one call:
+    the batched left-looking factorisation + projection of csrc/dev/mid_batched.cu.  Flops per problem as SURVEY 8(d) counts
+    them for one hyperplane call with its own covariance: k^3/3 + k^2 + 2 k^2 k2 + 2 k k2^2 + k2^3/3 + 2 k2^2 + 4 k k2."""
+    import cases
+    rng = np.random.default_rng(k)
+    base = torch.from_numpy(np.stack([cases.spd(rng, k) for _ in range(8)])).to(dev)
+    g_ = torch.Generator(device=dev).manual_seed(9)
+    cov = base.repeat(nproblems // 8, 1, 1)
+    cov.mul_(1.0 + torch.rand(nproblems, 1, 1, dtype=torch.float64, device=dev, generator=g_))
+    g = torch.randn(nproblems, k2, k, dtype=torch.float64, device=dev, generator=g_)
+    r = torch.randn(nproblems, k2, dtype=torch.float64, device=dev, generator=g_)
+    mu = torch.randn(nproblems, k, dtype=torch.float64, device=dev, generator=g_)
+    out = torch.empty(nproblems, k, dtype=torch.float64, device=dev)
+    info = torch.empty(nproblems, dtype=torch.int32, device=dev)
+    ms = _time(torch, lambda: h.hyperplane_truncated_mvnorm_batch(nproblems, mu, cov, g, r, independent=True, seed0=12345,
+                                                                   out=out, info=info))
+    flops = nproblems * (k ** 3 / 3 + k * k + 2 * k * k * k2 + 2 * k * k2 * k2 + k2 ** 3 / 3 + 2 * k2 * k2 + 4 * k * k2)
+    resid = float((torch.einsum("bck,bk->bc", g[:256], out[:256]) - r[:256]).abs().max().item())
+    return _tensor_entry("hyperplane-truncated MVN k=%d, k2=%d, %d independent problems (one batched call)"
+                         % (k, k2, nproblems), ms, nproblems, flops, peak_tf,
+                         {"failed_problems": int((info != 0).sum().item()), "max_abs_constraint_residual_first_256": resid})
 
 
 def cfg3(h, torch, dev, peak_tf):
@@ -170,7 +194,7 @@ def normal_fill(h, torch, dev, hbm_gbs, issue_peak_gops, nstreams=65536, n=1000)
     return entry
 
 
-def run_all(h, torch, dev, peak_tf, hbm_gbs, which=("cfg2", "cfg3", "cfg4", "cfg5_shard", "normal_fill")):
+def run_all(h, torch, dev, peak_tf, hbm_gbs, which=("cfg2", "cfg3", "cfg4", "cfg5_shard", "mid256", "normal_fill")):
     """Every entry is computed independently: a failure is reported in place and does not take the bench line down."""
     out = {}
     issue = None
@@ -181,6 +205,7 @@ def run_all(h, torch, dev, peak_tf, hbm_gbs, which=("cfg2", "cfg3", "cfg4", "cfg
             issue = None
     table = {"cfg2": lambda: cfg2(h, torch, dev, hbm_gbs), "cfg3": lambda: cfg3(h, torch, dev, peak_tf),
              "cfg4": lambda: cfg4(h, torch, dev, peak_tf), "cfg5_shard": lambda: cfg5_shard(h, torch, dev, peak_tf),
+             "mid256": lambda: mid256(h, torch, dev, peak_tf),
              "normal_fill": lambda: normal_fill(h, torch, dev, hbm_gbs, issue)}
     for name in which:
         try:

@@ -161,9 +161,10 @@ int htnk_chol_rows_batched(cudaStream_t st, const double* cov, size_t scov, int 
 /* diagonal 64-block of every problem's lower factorisation, one WARP per problem (mid_batched.cu): factorises in place the
  * nb x nb (nb <= 64) block at row / column j0 of F + b * sF (lower storage, leading dimension ld); rdiag + b * sr + j0 receives
  * 1 / L[j][j]; info[b] receives j0 + j + 1 at the first pivot <= 0 (if it still holds 0; problems whose info is set are skipped).
- * counter: one zero-initialised device unsigned. */
+ * counter: one zero-initialised device unsigned.  src != NULL (j0 = 0 only): the block is read from the caller's matrices
+ * (src + b * ssrc, leading dimension src_ld, lower or upper triangle valid) instead of from F. */
 int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t sF, int j0, int nb, double* rdiag, size_t sr, int* info,
-                        size_t nbatch, unsigned* counter);
+                        size_t nbatch, unsigned* counter, const double* src, size_t ssrc, size_t src_ld, int src_lower);
 /* projection of one sample per problem given the factor (mid_batched.cu): x = y + cov G^T (G cov G^T)^-1 (r - G y), y = mean + L z,
  * formed around the factor (V = L^T G^T); k2 <= 4.  info[b]: set by the factorisation (row untouched) or by the k2 x k2 solve. */
 int htnk_ht_mid_project(cudaStream_t st, size_t nbatch, int k, int k2, const double* F, size_t ld, size_t sF,

@@ -69,7 +69,8 @@ struct G {
 // small_warp.cu, and the Cholesky factor is written back row by row as each 8-row panel finishes.
 __global__ void __launch_bounds__(32, 8)
 potf64_kernel(double* __restrict__ F, size_t ld, size_t sF, int j0, int nb, double* __restrict__ rdiag, size_t sr,
-              int* __restrict__ info, size_t nbatch, unsigned* __restrict__ next)
+              int* __restrict__ info, size_t nbatch, unsigned* __restrict__ next, const double* __restrict__ src,
+              size_t ssrc, size_t src_sc, size_t src_sr)
 {
     constexpr int NT = G::NT, K = G::K, CS = G::CS;
     extern __shared__ __align__(16) double sm[];
@@ -105,10 +106,14 @@ potf64_kernel(double* __restrict__ F, size_t ld, size_t sF, int j0, int nb, doub
         for (int ti = 0; ti < NT; ti++)
 #pragma unroll
             for (int tj = ti; tj < NT; tj++) {
+                // element (r, c), r <= c, of the block: from the lower storage of F ([c][r]), or - first panel - straight from
+                // the caller's matrix (src: its valid triangle through the strides src_sc, src_sr)
                 const int r = 8 * ti + g, c0 = 8 * tj + 2 * t4;
-                const double* src = Fp + (size_t)(j0 + c0) * ld + j0 + r;
-                c[ti][tj].x = (r < nb && c0 < nb) ? __ldg(src) : (r == c0 ? 1.0 : 0.0);
-                c[ti][tj].y = (r < nb && c0 + 1 < nb) ? __ldg(src + ld) : (r == c0 + 1 ? 1.0 : 0.0);
+                const double* e0 = src ? src + pb * ssrc + (size_t)c0 * src_sc + (size_t)r * src_sr
+                                       : Fp + (size_t)(j0 + c0) * ld + j0 + r;
+                const size_t step = src ? src_sc : ld;
+                c[ti][tj].x = (r < nb && c0 < nb) ? __ldg(e0) : (r == c0 ? 1.0 : 0.0);
+                c[ti][tj].y = (r < nb && c0 + 1 < nb) ? __ldg(e0 + step) : (r == c0 + 1 ? 1.0 : 0.0);
             }
         // ---- A_bb = U~^T D U~, panel by panel (the scheme of small_warp.cu) ----
         int fail = 0;
@@ -693,8 +698,10 @@ ht_mid_project_kernel(size_t nbatch, int k, int k2, const double* __restrict__ F
 }  // namespace
 
 extern "C" int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t sF, int j0, int nb, double* rdiag, size_t sr,
-                                   int* info, size_t nbatch, unsigned* counter)
+                                   int* info, size_t nbatch, unsigned* counter, const double* src, size_t ssrc, size_t src_ld,
+                                   int src_lower)
 {
+    if (src && j0 != 0) return -202;  /* only the first block can come from the caller's matrix: the others need the update */
     if (nbatch == 0 || nb <= 0) return 0;
     if (nb > 64 || (ld & 1) || (j0 & 1) || (sF & 1) || nbatch > 0xfffffff0u || (reinterpret_cast<uintptr_t>(F) & 15)) return -202;
     const size_t smem = (size_t)G::TOTAL * sizeof(double);
@@ -706,7 +713,9 @@ extern "C" int htnk_potf64_batched(cudaStream_t st, double* F, size_t ld, size_t
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)sms * per_sm;
     if (grid > nbatch) grid = nbatch;
-    potf64_kernel<<<(unsigned)grid, 32, smem, st>>>(F, ld, sF, j0, nb, rdiag, sr, info, nbatch, counter);
+    /* element (r, c), r <= c: [c][r] of a lower-valid (column-major build) matrix, [r][c] of an upper-valid (row-major) one */
+    potf64_kernel<<<(unsigned)grid, 32, smem, st>>>(F, ld, sF, j0, nb, rdiag, sr, info, nbatch, counter, src, ssrc,
+                                                    src_lower ? src_ld : 1, src_lower ? 1 : src_ld);
     htnk_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -201;
 }

@@ -421,8 +421,10 @@ static int ht_mid_range(cudaStream_t st, size_t np, unsigned flags, int k2, int 
     /* left-looking: every panel is formed from the caller's covariance and the panels before it, written once */
     for (int q = 0; q < nsteps; q++) {
         const int j0 = 64 * q, nb = k - j0 < 64 ? k - j0 : 64;
-        HTN_TRY(htnk_chol_rows_batched(st, cov, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info, 1, np));
-        HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info, np, ctr + q));
+        /* the first diagonal block is the caller's own: the factorisation reads it in place */
+        if (q > 0) HTN_TRY(htnk_chol_rows_batched(st, cov, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info, 1, np));
+        HTN_TRY(htnk_potf64_batched(st, F, ld, sF, j0, nb, rd, sr, info, np, ctr + q, q == 0 ? cov : NULL, (size_t)k * k,
+                                    (size_t)k, lo));
         HTN_TRY(htnk_chol_rows_batched(st, cov, (size_t)k * k, lo, F, ld, sF, k, j0, rd, sr, info, 0, np));
     }
     HTN_TRY(htnk_ht_mid_project(st, np, k, k2, F, ld, sF, mean, g, r, zs, lo, out, info));
