@@ -452,7 +452,12 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
         if (e) split_min = (size_t)atol(e);
     }
     /* the workspace holds a full k x ld factor per problem: very large batches go through in slices of <= 2 GiB of factors */
-    size_t slice = ((size_t)2 << 30) / (sF * 8);
+    size_t slice_bytes = (size_t)2 << 30;
+    {
+        const char* e = getenv("HTN_MID_SLICE_BYTES"); /* the tests shrink it to force the multi-slice path */
+        if (e && atoll(e) > 0) slice_bytes = (size_t)atoll(e);
+    }
+    size_t slice = slice_bytes / (sF * 8);
     if (slice < 1) slice = 1;
     if (slice > P) slice = P;
     if (split_min && P >= split_min && ms.device != ctx->device) {

@@ -922,3 +922,21 @@ def test_mid_size_batch_split_over_two_streams(h, oracle, monkeypatch):
     assert np.array_equal(info, io)
     assert rel_err(x[ok], xo[ok]) < REL_TOL
     assert constraint_violation(x[ok], c["g"][ok], c["r"][ok]) < RESID_TOL
+
+
+def test_mid_size_batch_in_slices(h, oracle, monkeypatch):
+    """The mid-size workspace holds one factor per problem and very large batches go through in slices (<= 2 GiB of
+    factors); a small slice size and split threshold force several slices, each split over the two streams."""
+    k, k2, P = 150, 2, 45
+    c = cases.ht_independent_case(nproblems=P, k=k, k2=k2, rng_seed=31)
+    monkeypatch.setenv("HTN_MID_SLICE_BYTES", str(10 * 150 * 160 * 8))   # ten problems per slice
+    monkeypatch.setenv("HTN_MID_SPLIT", "4")
+    x, info = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=9)
+    monkeypatch.delenv("HTN_MID_SLICE_BYTES")
+    monkeypatch.delenv("HTN_MID_SPLIT")
+    x1, _ = h.hyperplane_truncated_mvnorm_batch(P, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=9)
+    xo, io, _ = oracle.hyperplane("pcg64", P, c["mean"], c["cov"], c["g"], c["r"], independent=True, seed0=9)
+    assert not info.any() and not io.any()
+    assert np.array_equal(x, x1)
+    assert rel_err(x, xo) < REL_TOL
+    assert constraint_violation(x, c["g"], c["r"]) < RESID_TOL
