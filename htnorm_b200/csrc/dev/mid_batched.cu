@@ -498,7 +498,9 @@ chol_rows_kernel(const double* __restrict__ cov, size_t scov, int lower_src, dou
 // Variants measured and dropped (4096 x k = 256, this kernel 0.565 ms of the 1.9 ms call): a first form with warps reading
 // rows straight from global memory (0.75 ms: every warp waited for every row); single bulk copies per row counted by
 // full / empty mbarrier pairs with row-length-packed blocks (0.69 ms: a quarter of the instructions, but short rows make
-// small TMA requests and the ring advances at the pace of the slowest warp); a ring of four blocks (two CTAs per SM: 0.63 ms).
+// small TMA requests and the ring advances at the pace of the slowest warp); a ring of four blocks (two CTAs per SM: 0.63 ms);
+// seven rows per block so that four CTAs fit an SM (64 registers, 55 KB: no gain over three, 1.87 vs 1.85 ms per call, while
+// one / two CTAs per SM cost 2.08 / 2.01 ms: the kernel is latency-bound up to three).
 // KP = 256 MC is the row pitch of a block, RB = 2048 / KP its rows.
 constexpr int PT = 256;    // threads of a projection CTA
 constexpr int PJ_NBUF = 3;  // ring depth of the projection's row blocks (PJ_NBUF - 1 blocks in flight)

@@ -432,6 +432,7 @@ done:
     return rc;
 }
 
+#define MID_PARTS_MAX 8
 static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, unsigned flags, int k2, int k,
                               const double* mean, const double* cov, const double* g, const double* r, double* out,
                               int* info_dev)
@@ -447,9 +448,12 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
      * (eight warps per SM), so the other half's panel kernels fill the machine beside it. */
     static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_fork, ev_join; } ms = {-1, NULL, NULL, NULL};
     size_t split_min = 1024;
+    int mid_parts = 2;
     {
         const char* e = getenv("HTN_MID_SPLIT"); /* experiments: smallest batch that is split (0 = never) */
         if (e) split_min = (size_t)atol(e);
+        e = getenv("HTN_MID_PARTS");
+        if (e && atoi(e) >= 1 && atoi(e) <= MID_PARTS_MAX) mid_parts = atoi(e);
     }
     /* the workspace holds a full k x ld factor per problem: very large batches go through in slices of <= 2 GiB of factors */
     size_t slice_bytes = (size_t)2 << 30;
@@ -475,7 +479,7 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
     HTN_TRY(htn_dalloc(ctx, (void**)&F, slice * sF * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&rd, slice * sr * 8));
     HTN_TRY(htn_dalloc(ctx, (void**)&zs, slice * (size_t)k * 8));
-    HTN_TRY(htn_dalloc(ctx, (void**)&ctr, (size_t)2 * nsteps * sizeof(unsigned)));
+    HTN_TRY(htn_dalloc(ctx, (void**)&ctr, (size_t)MID_PARTS_MAX * nsteps * sizeof(unsigned)));
     for (size_t p0 = 0; p0 < P && !rc; p0 += slice) {
         const size_t np = P - p0 < slice ? P - p0 : slice;
         htnk_streams_t sv;
@@ -483,20 +487,20 @@ static int ht_independent_mid(htn_ctx_t* ctx, const htn_streams_t* s, size_t P, 
         htnk_segment_t seg = {(size_t)k, zs, (size_t)k, NULL, NULL, NULL};
         HTN_TRY(htnk_normal_fill(st, &sv, np, 1, &seg, NULL));
         HTN_CUDA(cudaMemsetAsync(info_dev + p0, 0, np * sizeof(int), st));
-        HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)2 * nsteps * sizeof(unsigned), st));
-        const size_t na = (split_min && np >= split_min) ? np / 2 : np, nbh = np - na;
-        if (nbh) {
+        HTN_CUDA(cudaMemsetAsync(ctr, 0, (size_t)MID_PARTS_MAX * nsteps * sizeof(unsigned), st));
+        const int nparts = (split_min && np >= split_min) ? mid_parts : 1;
+        if (nparts > 1) {
             HTN_CUDA(cudaEventRecord(ms.ev_fork, st));
             HTN_CUDA(cudaStreamWaitEvent(ms.side, ms.ev_fork, 0));
             side_used = 1;
         }
-        for (int h = 0; h < (nbh ? 2 : 1) && !rc; h++) {
-            const size_t q0 = h ? na : 0, nq = h ? nbh : na, a0 = p0 + q0;
-            rc = ht_mid_range(h ? ms.side : st, nq, flags, k2, k, mean + a0 * (size_t)k, cov + a0 * (size_t)k * k,
+        for (int h = 0; h < nparts && !rc; h++) { /* even parts on the caller's stream, odd parts on the side stream */
+            const size_t q0 = np * (size_t)h / nparts, nq = np * (size_t)(h + 1) / nparts - q0, a0 = p0 + q0;
+            rc = ht_mid_range((h & 1) ? ms.side : st, nq, flags, k2, k, mean + a0 * (size_t)k, cov + a0 * (size_t)k * k,
                               g + a0 * (size_t)k2 * k, r + a0 * (size_t)k2, zs + q0 * (size_t)k, F + q0 * sF, ld, sF,
                               rd + q0 * sr, sr, ctr + h * nsteps, out + a0 * (size_t)k, info_dev + a0);
         }
-        if (nbh) { /* the slice's workspace is reused by the next slice, and freed in stream order on st */
+        if (nparts > 1) { /* the slice's workspace is reused by the next slice, and freed in stream order on st */
             if (cudaEventRecord(ms.ev_join, ms.side) != cudaSuccess || cudaStreamWaitEvent(st, ms.ev_join, 0) != cudaSuccess) {
                 cudaStreamSynchronize(ms.side);
                 if (!rc) rc = HTN_E_CUDA;
