@@ -61,6 +61,35 @@ done:
 /* side stream of the super-panel look-ahead (one per host thread and device, kept) */
 static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_chain, ev_b; } sl = {-1, NULL, NULL, NULL};
 
+/* Block column [c0, c1) of the factorisation (all rows from c0 down), RECURSIVELY: left half, one update of the right
+ * half's columns by the left half (a GEMM with K = half the width - long and fat), right half.  The flat left-looking
+ * loop over 128-panels updated every panel by all earlier panels of the super-panel: only skinny (N = 128) GEMMs, which
+ * ran at 14 TFLOP/s (n = 8192: 2.4 ms of the 9.6); the recursion does the same flops with N = width / 2. */
+static int potrf_block_column(htn_ctx_t* ctx, htn_factor_t* fa, int c0, int c1, int* d_info)
+{
+    int rc = 0;
+    const int n = fa->n;
+    const size_t ld = fa->ld;
+    if (c1 - c0 <= HTN_NB) {
+        const int nb = c1 - c0, rows = n - c1;
+        double* ajj = fa->f + (size_t)c0 * ld + c0;
+        int rows_done = 0;
+        HTN_TRY(htnk_potf2_panel(ctx->stream, ajj, ld, nb, c0, fa->rdiag + c0, d_info, rows, fa->pscr,
+                                 (unsigned*)(fa->pscr + 16 * 64), &rows_done));
+        if (rows > 0 && !rows_done)
+            HTN_TRY(htnk_trsm_rows(ctx->stream, fa->f + (size_t)c1 * ld + c0, ld, rows, ajj, ld, nb, fa->rdiag + c0));
+        return 0;
+    }
+    const int cm = c0 + (int)htn_round_up((size_t)((c1 - c0) / 2), HTN_NB);
+    HTN_TRY(potrf_block_column(ctx, fa, c0, cm, d_info));
+    /* A[cm:, cm:c1] -= L[cm:, c0:cm] L[cm:c1, c0:cm]^T (the tiles above the diagonal of the square part are skipped) */
+    HTN_TRY(htnk_gemm_tn(ctx->stream, n - cm, c1 - cm, cm - c0, -1.0, fa->f + (size_t)cm * ld + c0, ld,
+                         fa->f + (size_t)cm * ld + c0, ld, 1.0, fa->f + (size_t)cm * ld + cm, ld, NULL, HTNK_GEMM_C_LOWER, 0, 0, 0));
+    HTN_TRY(potrf_block_column(ctx, fa, cm, c1, d_info));
+done:
+    return rc;
+}
+
 int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
 {
     int rc = 0;
@@ -78,7 +107,11 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
         const char* e = getenv("HTN_POTRF_LA");
         la_max = e ? atoi(e) : 4096;
     }
-    const int W = n >= 8192 ? 1024 : (n >= 2048 ? 512 : HTN_NB);
+    int W = n >= 8192 ? 1024 : (n >= 2048 ? 512 : HTN_NB);
+    {
+        const char* e = getenv("HTN_POTRF_W"); /* experiments: super-panel width */
+        if (e && atoi(e) >= HTN_NB) W = (int)htn_round_up((size_t)atoi(e), HTN_NB);
+    }
     static int la_min = -1;
     if (la_min < 0) {
         const char* e = getenv("HTN_POTRF_LA_MIN");
@@ -175,9 +208,17 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
             use_sla = 0; /* no side stream: the plain order below */
         }
     }
+    static int rec_on = -1; /* HTN_POTRF_REC=0: the flat left-looking loop inside a super-panel */
+    if (rec_on < 0) {
+        const char* e = getenv("HTN_POTRF_REC");
+        rec_on = (e && *e == '0') ? 0 : 1;
+    }
     int pending_b = 0;
     for (int J0 = 0; J0 < n; J0 += W) {
         const int J1 = J0 + W < n ? J0 + W : n;
+        if (rec_on && J1 - J0 > HTN_NB) {
+            HTN_TRY(potrf_block_column(ctx, fa, J0, J1, d_info));
+        } else
         for (int j0 = J0; j0 < J1; j0 += HTN_NB) {
             const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
             const int rows = n - j0 - nb;
