@@ -14,6 +14,29 @@
  */
 #include "htn_internal.h"
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+/* HTN_SP_TRACE=1 (development only): synchronise the device at the phase boundaries of htn_sp_device and print how long
+ * each phase took on its own (no overlap between phases is left in such a run) */
+static int sp_trace_on(void)
+{
+    static int v = -1;
+    if (v < 0) v = getenv("HTN_SP_TRACE") != NULL;
+    return v;
+}
+static void sp_trace(const char* label)
+{
+    static _Thread_local double t_prev = 0.0;
+    if (!sp_trace_on()) return;
+    cudaDeviceSynchronize();
+    struct timespec ts;
+    timespec_get(&ts, TIME_UTC);
+    const double t = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (label) fprintf(stderr, "[sp] %-28s %8.3f ms\n", label, t - t_prev);
+    t_prev = t;
+}
+
 #include <stdlib.h>
 #include <string.h>
 
@@ -47,9 +70,13 @@ static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src,
     HTN_CUDA(cudaMemsetAsync(*buf, 0, (size_t)n * ld * 8, ctx->stream));
     HTN_TRY(htnk_sym_expand(ctx->stream, src, (size_t)n, n, lower_src, NULL, 0, *buf, ld));
     HTN_TRY(htn_factor_init(ctx, fa, *buf, ld, n, 1));
+    sp_trace("  (before potrf)");
     HTN_TRY(htn_potrf(ctx, fa, d_info));
+    sp_trace("  potrf");
     HTN_TRY(htn_factor_make_u(ctx, fa));
+    sp_trace("  U = L^T");
     HTN_TRY(htn_factor_make_inverse_blocks(ctx, fa, wblock)); /* wblock = 0: the whole inverse */
+    sp_trace("  inverse factor");
 done:
     return rc;
 }
@@ -172,6 +199,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         }
     }
 
+    sp_trace(NULL);
     /* ---- A, Omega: factor (dense) (mvn_rand_prec, src/htnorm_distributions.c:110-123) ---- */
     if (a_id == NORMAL && o_id == NORMAL) { /* two dense factorisations: Omega's (the smaller one) runs beside A's */
         htn_ctx_t c2 = *ctx;
@@ -183,9 +211,20 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         HTN_CUDA(cudaEventRecord(ev_o, side2));
         omega_forked = 1;
     }
+    int early0 = 0; /* chunk 0: Y1, X and b = Phi y1 + y2 were formed on side2, beside the chain that builds and factors M */
     if (a_id == NORMAL) {
         HTN_TRY(factor_dense(ctx, a, p, lower_src, &FA, &fa, d_info + 0, inverse_block_width(p, (size_t)2 * n_ + nsamples)));
-        if (rng_in_flight) { /* L^T y1 = z for chunk 0 (see the loop below), started as soon as L_A^-1 exists */
+        /* T1 = Phi L_A^-T (n x p): M needs only T1 (Phi A^-1 Phi^T = T1 T1^T); X^T = T1 L_A^-1 is not needed before the
+         * last GEMM of a chunk, so it leaves the critical path */
+        HTN_TRY(htn_dalloc(ctx, (void**)&T1, (size_t)n * pp * 8));
+        HTN_TRY(htn_dalloc(ctx, (void**)&XT, (size_t)n * pp * 8));
+        HTN_TRY(htn_dalloc(ctx, (void**)&X, (size_t)p * np * 8));
+        HTN_CUDA(cudaMemsetAsync(XT, 0, (size_t)n * pp * 8, st));
+        HTN_CUDA(cudaMemsetAsync(X, 0, (size_t)p * np * 8, st));
+        HTN_TRY(htn_solve_lt(ctx, &fa, Phip, pp, T1, pp, n));
+        if (rng_in_flight) {
+            /* side2: L^T y1 = z for chunk 0 (see the loop below), X^T = T1 L_A^-1, X, and chunk 0's b = Phi y1 + y2 -
+             * four device-filling GEMMs that need nothing of M, beside the latency-bound chain M -> chol(M) -> M^-1 */
             const size_t nb0 = nsamples < chunk ? nsamples : chunk;
             htn_ctx_t c2 = *ctx;
             c2.stream = side2;
@@ -193,28 +232,40 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
             HTN_CUDA(cudaStreamWaitEvent(side2, ev_a, 0));
             HTN_CUDA(cudaStreamWaitEvent(side2, ev_rng, 0));
             side2_used = 1;
+            y1_in_flight = 1; /* joined at the exits from here on */
             HTN_TRY(htn_solve_l(&c2, &fa, Z1, pp, Y1, pp, (int)nb0));
+            HTN_TRY(htn_solve_l(&c2, &fa, T1, pp, XT, pp, n));
+            HTN_TRY(htnk_transpose(side2, XT, pp, n, p, X, np));
+            {
+                double* bm0 = Z2;
+                if (o_id == NORMAL) { /* chol(Omega) ran on side2 as well: its factor is there in stream order */
+                    HTN_TRY(htn_solve_l(&c2, &fo, Z2, np, Y2, np, (int)nb0));
+                    bm0 = Y2;
+                }
+                HTN_TRY(htnk_gemm_tn(side2, (int)nb0, n, p, 1.0, Y1, pp, Phip, pp, 1.0, bm0, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+                if (struct_mean) HTN_TRY(htnk_rsub_rows(side2, bm0, np, (int)nb0, n, mean));
+            }
             HTN_CUDA(cudaEventRecord(ev_y1, side2));
-            y1_in_flight = 1;
+            early0 = 1;
+        } else {
+            HTN_TRY(htn_solve_l(ctx, &fa, T1, pp, XT, pp, n));
+            HTN_TRY(htnk_transpose(st, XT, pp, n, p, X, np));
         }
     }
+    sp_trace("factor A (+inverse), Y1, Omega");
     if (omega_forked) /* Omega^-1 itself is formed from the whole inverse factor below */
         HTN_CUDA(cudaStreamWaitEvent(st, ev_o, 0));
     else if (o_id == NORMAL)
         HTN_TRY(factor_dense(ctx, omega, n, lower_src, &FO, &fo, d_info + 1, 0));
-    /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs) */
+    /* ---- X^T = Phi A^-1 (n x p)   (src/htnorm.c:261-302; dpotri + dsymm replaced by two triangular GEMMs: above) */
     if (a_id == IDENTITY) {
         XT = Phip;
-    } else {
+    } else if (a_id == DIAGONAL) {
         HTN_TRY(htn_dalloc(ctx, (void**)&XT, (size_t)n * pp * 8));
         HTN_CUDA(cudaMemsetAsync(XT, 0, (size_t)n * pp * 8, st));
-        if (a_id == DIAGONAL) {
-            HTN_TRY(htnk_coldiv(st, Phip, pp, n, p, da, XT, pp));
-        } else {
-            HTN_TRY(htn_dalloc(ctx, (void**)&T1, (size_t)n * pp * 8));
-            HTN_TRY(htn_solve_spd(ctx, &fa, Phip, pp, T1, XT, pp, n));
-        }
+        HTN_TRY(htnk_coldiv(st, Phip, pp, n, p, da, XT, pp));
     }
+    sp_trace("X^T = Phi A^-1");
     /* ---- M = Omega^-1 + X^T Phi^T  (compute_precision_inverse, src/htnorm.c:190-214; dgemm/dsyrk :267-300) */
     HTN_TRY(htn_dalloc(ctx, (void**)&M, (size_t)n * np * 8));
     HTN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * np * 8, st));
@@ -225,15 +276,22 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         HTN_TRY(htnk_diag_set(st, M, np, n, invo, 0.0));
     else
         HTN_TRY(htnk_diag_set(st, M, np, n, NULL, 1 / identity_factor_garbage()));
-    HTN_TRY(htnk_gemm_tn(st, n, n, p, 1.0, XT, pp, Phip, pp, 1.0, M, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    if (a_id == NORMAL) /* Phi A^-1 Phi^T = T1 T1^T */
+        HTN_TRY(htnk_gemm_tn(st, n, n, p, 1.0, T1, pp, T1, pp, 1.0, M, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    else
+        HTN_TRY(htnk_gemm_tn(st, n, n, p, 1.0, XT, pp, Phip, pp, 1.0, M, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    sp_trace("M");
     HTN_TRY(htn_factor_init(ctx, &fm, M, np, n, 1));
     HTN_TRY(htn_potrf(ctx, &fm, d_info + 2)); /* dposv, src/htnorm.c:330 */
     HTN_TRY(htn_factor_make_u(ctx, &fm));
     HTN_TRY(htn_factor_make_inverse(ctx, &fm));
-    /* X = (X^T)^T, p x n: the B operand of the final GEMM */
-    HTN_TRY(htn_dalloc(ctx, (void**)&X, (size_t)p * np * 8));
-    HTN_CUDA(cudaMemsetAsync(X, 0, (size_t)p * np * 8, st));
-    HTN_TRY(htnk_transpose(st, XT, pp, n, p, X, np));
+    sp_trace("factor M + inverse");
+    /* X = (X^T)^T, p x n: the B operand of the final GEMM (A dense: formed above, beside this chain) */
+    if (a_id != NORMAL) {
+        HTN_TRY(htn_dalloc(ctx, (void**)&X, (size_t)p * np * 8));
+        HTN_CUDA(cudaMemsetAsync(X, 0, (size_t)p * np * 8, st));
+        HTN_TRY(htnk_transpose(st, XT, pp, n, p, X, np));
+    }
 
     int h_info[3] = {0, 0, 0};
     HTN_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
@@ -243,6 +301,7 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
         goto finish;
     }
 
+    sp_trace("transpose X, sync");
     double coef = struct_mean ? -1.0 : 1.0;
     if (flags & HTN_FLAG_PAPER_SIGN) coef = -coef;
     for (size_t b0 = 0; b0 < nsamples; b0 += chunk) {
@@ -272,27 +331,33 @@ int htn_sp_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, unsig
             }
             y1 = Y1;
         }
+    sp_trace("chunk: normals / Y1");
+        const int early = (b0 == 0 && early0); /* Y2, b and (structured mean) t - b of this chunk are already there */
         double* bm = Z2;
         if (o_id == NORMAL) {
-            HTN_TRY(htn_solve_l(ctx, &fo, Z2, np, Y2, np, nb));
+            if (!early) HTN_TRY(htn_solve_l(ctx, &fo, Z2, np, Y2, np, nb));
             bm = Y2;
         }
         double* scratch = (bm == Z2) ? Y2 : Z2;
         /* b = Phi y1 + y2 (dgemm, src/htnorm.c:310) */
-        HTN_TRY(htnk_gemm_tn(st, nb, n, p, 1.0, y1, pp, Phip, pp, 1.0, bm, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        if (!early) HTN_TRY(htnk_gemm_tn(st, nb, n, p, 1.0, y1, pp, Phip, pp, 1.0, bm, np, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+    sp_trace("chunk: Y2, b = Phi y1 + y2");
         double* o = out + b0 * p_;
         if (struct_mean) { /* src/htnorm.c:314-321 */
-            HTN_TRY(htnk_rsub_rows(st, bm, np, nb, n, mean));
+            if (!early) HTN_TRY(htnk_rsub_rows(st, bm, np, nb, n, mean));
             HTN_TRY(htnk_copy2d(st, y1, pp, nb, p, o, p_, NULL));
         } else { /* src/htnorm.c:322-326 */
             HTN_TRY(htnk_copy2d(st, y1, pp, nb, p, o, p_, mean));
         }
         if (h_info[2]) continue; /* M not PD: out keeps y1 (+ mean), as after a failed dposv (:330-346) */
+    sp_trace("chunk: copy y1 to out");
         /* alpha = b M^-1: two triangular GEMMs, result back in bm */
         HTN_TRY(htn_solve_lt(ctx, &fm, bm, np, scratch, np, nb));
         HTN_TRY(htn_solve_l(ctx, &fm, scratch, np, bm, np, nb));
+    sp_trace("chunk: alpha solves");
         /* out += coef * alpha X^T  (dgemv / dgemm, src/htnorm.c:332-346) */
         HTN_TRY(htnk_gemm_tn(st, nb, p, n, coef, bm, np, X, np, 1.0, o, p_, NULL, HTNK_GEMM_FULL, 0, 0, 0));
+        sp_trace("chunk: out += alpha X^T");
     }
     *first_info = h_info[1] ? h_info[1] : h_info[2];
 finish:
