@@ -590,6 +590,76 @@ trsm_rows_kernel(double* __restrict__ x, size_t ldx, int nrows, const double* __
     }
 }
 
+
+// ---- look-ahead update of the NEXT block column: C(rows x nb2) -= X(rows x 128) X(0:nb2, :)^T ----
+// The one GEMM that stands between two fused panel kernels in the look-ahead factorisation (linalg.c): rows x 128 x 128,
+// far too small for the pipelined GEMM kernels (15 us, most of it prologue and epilogue latency).  Here a CTA takes 32 rows
+// x 64 columns with the WHOLE K = 128 of both operands staged at once by cp.async (100 KB, two CTAs per SM), four warps of
+// 8 rows x 64 columns, K contracted in the permuted order that makes every fragment a 16-byte load (see mid_batched.cu):
+// about 7 us for n = 2000 ... 4096.
+constexpr int PU_LD = 130;  // 260 words = 4 mod 32: conflict-free 16-byte fragment reads
+__global__ void __launch_bounds__(128)
+panel_update_kernel(double* __restrict__ c, size_t ldc, const double* __restrict__ x, size_t ldx, int rows, int nb2)
+{
+    extern __shared__ __align__(16) double pu[];
+    double* As = pu;               // [32][PU_LD]: this CTA's rows of X
+    double* Bs = pu + 32 * PU_LD;  // [64][PU_LD]: rows c0 .. c0+63 of X (the columns of C)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int r0 = 32 * (int)blockIdx.x, c0 = 64 * (int)blockIdx.y;
+#pragma unroll
+    for (int it = 0; it < 48; it++) {  // 96 rows x 64 pieces of 16 bytes
+        const int idx = tid + 128 * it, r = idx >> 6, c2 = (idx & 63) * 2;
+        const int grow = r < 32 ? r0 + r : c0 + (r - 32);
+        const bool ok = r < 32 ? grow < rows : grow < nb2;
+        double* dst = (r < 32 ? As + r * PU_LD : Bs + (r - 32) * PU_LD) + c2;
+        if (ok) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(x + (size_t)grow * ldx + c2));
+        } else {
+            *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    const int row = r0 + 8 * warp + g;
+    const bool live = row < rows;
+    double* crow = c + (size_t)(live ? row : 0) * ldc + c0 + 2 * t4;
+    double acc[8][2];
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        const int cc = c0 + 8 * n + 2 * t4;
+        acc[n][0] = (live && cc < nb2) ? crow[8 * n] : 0.0;
+        acc[n][1] = (live && cc + 1 < nb2) ? crow[8 * n + 1] : 0.0;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    const double* ar = As + (8 * warp + g) * PU_LD + 4 * t4;
+    const double* br = Bs + g * PU_LD + 4 * t4;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const double2 a01 = *reinterpret_cast<const double2*>(ar + 16 * u);
+        const double2 a23 = *reinterpret_cast<const double2*>(ar + 16 * u + 2);
+        const double a0 = -a01.x, a1 = -a01.y, a2 = -a23.x, a3 = -a23.y;
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            const double2 b01 = *reinterpret_cast<const double2*>(br + 8 * n * PU_LD + 16 * u);
+            const double2 b23 = *reinterpret_cast<const double2*>(br + 8 * n * PU_LD + 16 * u + 2);
+            dmma_sub(acc[n][0], acc[n][1], a0, b01.x);
+            dmma_sub(acc[n][0], acc[n][1], a1, b01.y);
+            dmma_sub(acc[n][0], acc[n][1], a2, b23.x);
+            dmma_sub(acc[n][0], acc[n][1], a3, b23.y);
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            const int cc = c0 + 8 * n + 2 * t4;
+            if (cc < nb2) crow[8 * n] = acc[n][0];
+            if (cc + 1 < nb2) crow[8 * n + 1] = acc[n][1];
+        }
+    }
+}
+
 }  // namespace
 
 static int potf2_launch(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info,
@@ -667,3 +737,17 @@ extern "C" int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows,
 }
 
 // the same panel solve for nbatch independent problems in one launch (gridDim.y = problem; strides in doubles)
+
+/* C (rows x nb2, leading dimension ldc) -= X (rows x 128, leading dimension ldx) * X[0:nb2, :]^T: the next block column's
+ * update between two fused panels of the look-ahead factorisation.  Returns 1 when the operands are not 16-byte aligned
+ * (the caller then takes the general GEMM). */
+extern "C" int htnk_panel_update(cudaStream_t st, double* c, size_t ldc, const double* x, size_t ldx, int rows, int nb2)
+{
+    if (rows <= 0 || nb2 <= 0) return 0;
+    if (nb2 > NB || (ldx & 1) || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
+    const size_t smem = (size_t)96 * PU_LD * sizeof(double);
+    if (cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -201;
+    panel_update_kernel<<<dim3((unsigned)((rows + 31) / 32), (unsigned)((nb2 + 63) / 64)), 128, smem, st>>>(c, ldc, x, ldx, rows, nb2);
+    htnk_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -201;
+}

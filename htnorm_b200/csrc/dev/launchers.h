@@ -80,6 +80,9 @@ int htnk_potf2(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* 
  * tscr: 16 * 64 doubles, flags: 17 unsigned - scratch private to the factorisation, no initialisation needed */
 int htnk_potf2_panel(cudaStream_t st, double* a, size_t ld, int nb, int col0, double* rdiag, int* info, int nrows_below,
                      double* tscr, unsigned* flags, int* rows_done);
+/* next block column of the look-ahead factorisation: C (rows x nb2) -= X (rows x 128) X[0:nb2, :]^T (chol.cu); returns 1
+ * when the operands are not 16-byte aligned (take the general GEMM) */
+int htnk_panel_update(cudaStream_t st, double* c, size_t ldc, const double* x, size_t ldx, int rows, int nb2);
 /* x (nrows x nb, leading dimension ldx) := x * L^-T with the nb x nb lower block l; rdiag = 1 / diag(l) */
 int htnk_trsm_rows(cudaStream_t st, double* x, size_t ldx, int nrows, const double* l, size_t ldl, int nb,
                    const double* rdiag);

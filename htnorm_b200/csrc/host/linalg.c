@@ -115,15 +115,17 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
     static int la_min = -1;
     if (la_min < 0) {
         const char* e = getenv("HTN_POTRF_LA_MIN");
-        la_min = e ? atoi(e) : 1536;
+        la_min = e ? atoi(e) : 2 * HTN_NB + 1;
     }
     if (n >= la_min && n > 2 * HTN_NB && n <= la_max) {
-        /* Mid-size n (measured: 0.90 instead of 1.00 ms at n = 2000, 2.25 instead of 2.76 ms at n = 4096; at n = 1000
-         * the trailing updates are too short to pay for the cross-stream hand-offs, 0.46 instead of 0.40 ms, and from
-         * n = 8192 the wide super-panels below win): plain right-looking with LOOK-AHEAD.  The rank-128 update of panel j is split into (a) the next
-         * block column - all that potf2(j+1) and the row solve (j+1) need - on the main stream, and (b) the rest of
-         * the trailing matrix on a side stream, beside potf2(j+1) + solve(j+1), which are single-CTA / latency
-         * bound.  (a)_{j+1} writes what (b)_j writes, so it waits for it; nothing else is shared. */
+        /* Up to n = 4096 (from n = 8192 the wide super-panels below win): plain right-looking with LOOK-AHEAD.  The
+         * rank-128 update of panel j is split into (a) the next block column - all that potf2(j+1) and the row solve
+         * (j+1) need - on the main stream, and (b) the rest of the trailing matrix on a side stream, beside potf2(j+1) +
+         * solve(j+1), which are single-CTA / latency bound.  (a)_{j+1} writes what (b)_j writes, so it waits for it;
+         * nothing else is shared.  (a) has its own kernel (htnk_panel_update: 7 us instead of the 15 us of the general
+         * GEMM on a rows x 128 x 128 problem); with it the look-ahead pays from the smallest multi-panel orders on
+         * (n = 500 / 1000 / 2000 / 4096: 0.159 / 0.314 / 0.69 / 2.04 ms against 0.170 / 0.353 / 0.76 / 2.11 ms for the
+         * plain order or the general GEMM). */
         /* the side stream and the two events are created once per host thread and device, and kept */
         static _Thread_local struct { int device; cudaStream_t side; cudaEvent_t ev_t, ev_b; } la = {-1, NULL, NULL, NULL};
         if (la.device != ctx->device) {
@@ -142,6 +144,11 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
         }
         cudaStream_t side = la.side;
         cudaEvent_t ev_t = la.ev_t, ev_b = la.ev_b;
+        static int pu_on = -1; /* HTN_POTRF_PU=0: the general GEMM for the next block column */
+        if (pu_on < 0) {
+            const char* e = getenv("HTN_POTRF_PU");
+            pu_on = (e && *e == '0') ? 0 : 1;
+        }
         int pending_b = 0;
         for (int j0 = 0; j0 < n && !rc; j0 += HTN_NB) {
             const int nb = n - j0 < HTN_NB ? n - j0 : HTN_NB;
@@ -160,8 +167,10 @@ int htn_potrf(htn_ctx_t* ctx, htn_factor_t* fa, int* d_info)
             if (pending_b && cudaStreamWaitEvent(ctx->stream, ev_b, 0) != cudaSuccess) { rc = HTN_E_CUDA; break; }
             pending_b = 0;
             /* (a) next block column: A[J1:, J1:J2] -= L[J1:, j] * L[J1:J2, j]^T */
-            rc = htnk_gemm_tn(ctx->stream, rows, nb2, nb, -1.0, pan, ld, pan, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld,
-                              NULL, HTNK_GEMM_FULL, 0, 0, 0);
+            rc = nb == HTN_NB && pu_on ? htnk_panel_update(ctx->stream, fa->f + (size_t)J1 * ld + J1, ld, pan, ld, rows, nb2) : 1;
+            if (rc == 1)
+                rc = htnk_gemm_tn(ctx->stream, rows, nb2, nb, -1.0, pan, ld, pan, ld, 1.0, fa->f + (size_t)J1 * ld + J1, ld,
+                                  NULL, HTNK_GEMM_FULL, 0, 0, 0);
             if (rc) break;
             if (R2 > 0) { /* (b) the rest, lower tiles: A[J2:, J2:] -= L[J2:, j] * L[J2:, j]^T */
                 const double* pan2 = fa->f + (size_t)J2 * ld + j0;

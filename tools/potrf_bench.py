@@ -6,7 +6,8 @@ DEV = h._lib.load_dev()   # htn_dbg_* hooks: dev build only
 DEV.htn_dbg_potrf_time.restype = C.c_double
 peak = h.fp64_tensor_peak_tflops(0, 100.0)
 print(f"DMMA peak {peak:.1f} TFLOP/s")
-for n in (1000, 2000, 4096, 8192, 16384):
+sizes = [int(a) for a in sys.argv[1:]] or [1000, 2000, 4096, 8192, 16384]
+for n in sizes:
     info = C.c_int(0)
     ms = DEV.htn_dbg_potrf_time(n, 3, C.byref(info))
     tf = n ** 3 / 3 / (ms * 1e-3) / 1e12
