@@ -10,6 +10,7 @@
 //
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "launchers.h"
 
@@ -486,6 +487,107 @@ trtri_batched_kernel(const double* __restrict__ f, size_t ld, int n, double* __r
     }
 }
 
+// ---- inverse of diagonal blocks, second form: recursive doubling on the tensor cores ----
+// The forward elimination above is a chain of 128 block-wide steps (75-100 us per launch, on the critical path of every
+// structured-precision call: twice in cfg3).  Here inv(L) is built bottom-up and IN PLACE in one shared-memory copy of the
+// block: the sixteen 8 x 8 diagonal inverses first (one warp each, lane = column), then for h = 8, 16, 32, 64 every
+// 2h-block gets its off-diagonal part
+//     X21 = -inv(L22) (L21 inv(L11))
+// as two DMMA products (zero halves of the triangular factors skipped).  A warp owns an 8-row block of a product: T = L21
+// inv(L11) overwrites L21 (row block i of T depends on row block i of L21 only); X21 is formed in registers and overwrites
+// T after a barrier.
+template <int H>
+__device__ __forceinline__ void trtri_level(double* S, int warp, int lane)
+{
+    constexpr int NTL = H / 8;  // 8-column tiles per row block (and row blocks per pair)
+    const int g = lane >> 2, t4 = lane & 3;
+    const int pair = warp / NTL, rb = warp % NTL;  // eight tasks per level: warps 0 .. 7
+    const int o = 2 * H * pair;
+    double acc[NTL][2];
+    if (warp < 8) {  // T = L21 inv(L11), in place
+        const double* arow = S + (o + H + 8 * rb + g) * LDB + o + t4;
+#pragma unroll
+        for (int nt = 0; nt < NTL; nt++) {
+            acc[nt][0] = acc[nt][1] = 0.0;
+            const double* bcol = S + (size_t)(o + t4) * LDB + o + 8 * nt + g;
+#pragma unroll
+            for (int k0 = 8 * nt; k0 < H; k0 += 4)  // inv(L11)[k][n] = 0 for k < n
+                dmma_sub(acc[nt][0], acc[nt][1], arow[k0], bcol[k0 * LDB]);
+        }
+        __syncwarp();
+        double* trow = S + (o + H + 8 * rb + g) * LDB + o + 2 * t4;
+#pragma unroll
+        for (int nt = 0; nt < NTL; nt++) *reinterpret_cast<double2*>(trow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+    }
+    __syncthreads();
+    if (warp < 8) {  // X21 = -inv(L22) T
+        const double* arow = S + (o + H + 8 * rb + g) * LDB + o + H + t4;
+#pragma unroll
+        for (int nt = 0; nt < NTL; nt++) {
+            acc[nt][0] = acc[nt][1] = 0.0;
+            const double* bcol = S + (size_t)(o + H + t4) * LDB + o + 8 * nt + g;
+#pragma unroll 2
+            for (int k0 = 0; k0 < 8 * (rb + 1); k0 += 4)  // inv(L22)[r][k] = 0 for k > r
+                dmma_sub(acc[nt][0], acc[nt][1], arow[k0], bcol[k0 * LDB]);
+        }
+    }
+    __syncthreads();  // every row block of T has been read
+    if (warp < 8) {
+        double* xrow = S + (o + H + 8 * rb + g) * LDB + o + 2 * t4;
+#pragma unroll
+        for (int nt = 0; nt < NTL; nt++) *reinterpret_cast<double2*>(xrow + 8 * nt) = make_double2(-acc[nt][0], -acc[nt][1]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1)
+trtri_dmma_kernel(const double* __restrict__ f, size_t ld, int n, double* __restrict__ dinv_all, double* __restrict__ dinvt_all)
+{
+    extern __shared__ double sm[];
+    double* S = sm;  // [NB][LDB]: L (lower, zero above), turned into inv(L) block by block
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * NB;
+    const int nb = min(NB, n - j0);
+    const double* a = f + (size_t)j0 * ld + j0;
+    double* dinv = dinv_all + (size_t)blockIdx.x * NB * NB;
+    double* dinvt = dinvt_all + (size_t)blockIdx.x * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        S[r * LDB + c] = (r < nb && c <= r) ? a[(size_t)r * ld + c] : (r == c ? 1.0 : 0.0);  // identity beyond a partial block
+    }
+    __syncthreads();
+    {  // the 8 x 8 diagonal inverses, in place: warp b, lane c < 8 owns column c (right-looking: one multiply + one FMA per step)
+        double* Sb = S + (8 * warp) * LDB + 8 * warp;
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            v[t] *= 1.0 / Sb[t * LDB + t];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i > t) v[i] = fma(-Sb[i * LDB + t], v[t], v[i]);
+        }
+        __syncwarp();  // every lane has read the block
+        if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) Sb[i * LDB + lane] = v[i];
+        }
+    }
+    __syncthreads();
+    trtri_level<8>(S, warp, lane);
+    trtri_level<16>(S, warp, lane);
+    trtri_level<32>(S, warp, lane);
+    trtri_level<64>(S, warp, lane);
+    for (int idx = tid; idx < nb * NB; idx += NT) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        if (c < nb) {
+            dinv[(size_t)r * NB + c] = S[r * LDB + c];
+            dinvt[(size_t)r * NB + c] = S[c * LDB + r];
+        }
+    }
+}
+
 // ---- panel solve of the blocked Cholesky: X := X * L^-T for the rows of a panel, on the tensor cores ----
 // A warp owns 8 rows and keeps their 128 entries as sixteen 8 x 8 DMMA accumulator tiles.  For each 8-column
 // block b: X_b = Acc_b * inv(L_bb)^T (two DMMAs with the 8 x 8 inverse computed once per CTA), X_b is final
@@ -707,6 +809,18 @@ extern "C" int htnk_potf2_panel(cudaStream_t st, double* a, size_t ld, int nb, i
 extern "C" int htnk_trtri_batched(cudaStream_t st, const double* f, size_t ld, int n, double* dinv, double* dinvt)
 {
     if (n <= 0) return 0;
+    static int old_form = -1;  // HTN_TRTRI=0: the forward-elimination kernel
+    if (old_form < 0) {
+        const char* e = getenv("HTN_TRTRI");
+        old_form = (e && *e == '0') ? 1 : 0;
+    }
+    if (!old_form) {
+        const size_t smem2 = (size_t)NB * LDB * sizeof(double);
+        if (cudaFuncSetAttribute(trtri_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) return -201;
+        trtri_dmma_kernel<<<(n + NB - 1) / NB, NT, smem2, st>>>(f, ld, n, dinv, dinvt);
+        htnk_count_launch();
+        return cudaGetLastError() == cudaSuccess ? 0 : -201;
+    }
     const size_t smem = (size_t)(NB * LDB + 3 * NB) * sizeof(double);
     if (cudaFuncSetAttribute(trtri_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
