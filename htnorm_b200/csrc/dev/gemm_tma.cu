@@ -394,7 +394,17 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     if (wm_env != 4 && wm_env != 8) {
         const long long t128 = (long long)((M + 127) / 128) * ((N + BN - 1) / BN);
         const long long work = (mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_C_LOWER || mode == HTNK_GEMM_B_UPPER) ? t128 / 2 : t128;
-        if (work < 3 * 148) wm_cfg = 4;
+        if (work < 3 * 148) {
+            wm_cfg = 4;
+        } else {
+            // enough large tiles to fill the device once - but a last, mostly empty wave is expensive (a lone CTA of four
+            // warps runs at half the SM's rate): compare how full the waves are with 3 x 148 slots of 128 x 64 tiles and with
+            // 4 x 148 slots of 64 x 64 tiles (cfg3's Y1 = Z1 L^-1: 512 CTA pairs on 444 slots against 1024 on 592)
+            const long long c8 = work, c4 = 2 * work;
+            const double e8 = (double)c8 / (double)(((c8 + 443) / 444) * 444);
+            const double e4 = (double)c4 / (double)(((c4 + 591) / 592) * 592);
+            if (e8 < 0.80 && e4 > e8 + 0.05) wm_cfg = 4;
+        }
     }
     const int BM = 16 * wm_cfg, A_BYTES = BM * BK * 8;
     if (!make_map(&tmA, A, lda, M, K, BM) || !make_map(&tmB, B, ldb, N, K, BN)) return 1;
