@@ -316,8 +316,9 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
                 const char* e = getenv("HTN_GEMM_KWIDE");
                 kwide = e ? atoi(e) : 512;
             }
-            // (from 64 tiles on: the 128-column strips of the look-ahead factorisation, 30 tiles, stay narrow - measured)
-            bn = (ctas64 < min64 && (K < kwide || ctas64 < 64)) ? 32 : wide_config();
+            // (up to 64 tiles the narrow kernel stays - measured on the products of the recursive inversion, K <= 2048 - unless K is
+            // very long: cfg4's b = Phi y1 + y2, 256 x 1024 x 8192, takes the 32 x 64 tiles of the TMA kernel)
+            bn = (ctas64 < min64 && (K < kwide || (ctas64 < 64 && K < 4096))) ? 32 : wide_config();
         }
     }
     GemmParams p;
@@ -349,7 +350,3 @@ extern "C" int htnk_gemm_tn(cudaStream_t st, int M, int N, int K, double alpha, 
         default: return -202;
     }
 }
-
-// The same GEMM over nbatch independent problems in ONE launch (gridDim.y = problem): problem b reads A + b sA, B + b sB and
-// updates C + b sC.  cp.async kernels only (no tensor maps per problem); N tile 64 / 32 / 8 by N.  Used by the batched
-// mid-size independent problems (hyperplane.c ht_independent_mid): the trailing updates of all problems' factorisations.

@@ -390,11 +390,16 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
         const char* e = getenv("HTN_TMA_WM");
         wm_env = e ? atoi(e) : 0;
     }
-    int wm_cfg = wm_env == 4 || wm_env == 8 ? wm_env : 8;
-    if (wm_env != 4 && wm_env != 8) {
+    int wm_cfg = wm_env == 2 || wm_env == 4 || wm_env == 8 ? wm_env : 8;
+    if (wm_env != 2 && wm_env != 4 && wm_env != 8) {
         const long long t128 = (long long)((M + 127) / 128) * ((N + BN - 1) / BN);
         const long long work = (mode == HTNK_GEMM_B_LOWER || mode == HTNK_GEMM_C_LOWER || mode == HTNK_GEMM_B_UPPER) ? t128 / 2 : t128;
-        if (work < 3 * 148) {
+        if (2 * work < 148 && K >= 2048) {
+            // not even the 64 x 64 tiles give every SM a CTA (few rows: small batches against a large factor): 32 x 64 tiles,
+            // six CTAs per SM.  Only with a long K: the small products of the recursive inversion are faster on 64 x 64 tiles
+            // (cfg3 2.87 -> 2.92 ms without this condition)
+            wm_cfg = 2;
+        } else if (work < 3 * 148) {
             wm_cfg = 4;
         } else {
             // enough large tiles to fill the device once - but a last, mostly empty wave is expensive (a lone CTA of four
@@ -424,10 +429,10 @@ extern "C" int htnk_gemm_tn_tma(cudaStream_t st, int M, int N, int K, double alp
     const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * STAGES * sizeof(uint64_t) + 1024;
     void (*kern)(const CUtensorMap, const CUtensorMap, const TmaGemmParams) = nullptr;
     switch (mode) {  // the mode is a template parameter: each instance carries only its own tile logic
-        case HTNK_GEMM_B_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_LOWER>; break;
-        case HTNK_GEMM_C_LOWER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_C_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_C_LOWER>; break;
-        case HTNK_GEMM_B_UPPER: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_UPPER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_UPPER>; break;
-        default: kern = wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_FULL> : gemm_tma_kernel<8, 3, HTNK_GEMM_FULL>; break;
+        case HTNK_GEMM_B_LOWER: kern = wm_cfg == 2 ? gemm_tma_kernel<2, 6, HTNK_GEMM_B_LOWER> : wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_LOWER>; break;
+        case HTNK_GEMM_C_LOWER: kern = wm_cfg == 2 ? gemm_tma_kernel<2, 6, HTNK_GEMM_C_LOWER> : wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_C_LOWER> : gemm_tma_kernel<8, 3, HTNK_GEMM_C_LOWER>; break;
+        case HTNK_GEMM_B_UPPER: kern = wm_cfg == 2 ? gemm_tma_kernel<2, 6, HTNK_GEMM_B_UPPER> : wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_B_UPPER> : gemm_tma_kernel<8, 3, HTNK_GEMM_B_UPPER>; break;
+        default: kern = wm_cfg == 2 ? gemm_tma_kernel<2, 6, HTNK_GEMM_FULL> : wm_cfg == 4 ? gemm_tma_kernel<4, 4, HTNK_GEMM_FULL> : gemm_tma_kernel<8, 3, HTNK_GEMM_FULL>; break;
     }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -201;
