@@ -26,11 +26,16 @@ sym_expand_kernel(const double* __restrict__ src, size_t lds, int n, int lower_s
     __shared__ double t_t[32][33];  // mirrored tile src[bj-rows][bi-cols]
     const int bi = blockIdx.y, bj = blockIdx.x;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    // an off-diagonal tile lies wholly on one side of the diagonal: it needs the direct tile OR the mirrored one, and a
+    // tile above the diagonal of a lower-only copy needs neither (it is all zeros): half the reads, or none
+    const bool use_direct = bi == bj || (lower_src ? bj < bi : bj > bi);
+    const bool use_mirror = bi == bj || !use_direct;
+    const bool zeros_only = full == nullptr && bj > bi;
     for (int r = ty; r < 32; r += 8) {
         int i = bi * 32 + r, j = bj * 32 + tx;
-        d_t[r][tx] = (i < n && j < n) ? src[(size_t)i * lds + j] : 0.0;
+        d_t[r][tx] = (use_direct && !zeros_only && i < n && j < n) ? src[(size_t)i * lds + j] : 0.0;
         int i2 = bj * 32 + r, j2 = bi * 32 + tx;
-        t_t[r][tx] = (i2 < n && j2 < n) ? src[(size_t)i2 * lds + j2] : 0.0;
+        t_t[r][tx] = (use_mirror && !zeros_only && i2 < n && j2 < n) ? src[(size_t)i2 * lds + j2] : 0.0;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -362,8 +367,6 @@ extern "C" int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, i
     sym_expand_kernel<<<grid, 256, 0, st>>>(src, lds, n, lower_src, full, ldf, low, ldl, 0, 0);
     return status();
 }
-
-// lower-triangle copies (zeros above) of nbatch symmetric matrices in one launch
 
 extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                               size_t ldd)

@@ -472,8 +472,13 @@ int htn_factor_make_inverse_blocks(htn_ctx_t* ctx, htn_factor_t* fa, int w)
     if (w <= 0 || w % HTN_NB || !fa->dinv || !fa->dinvt || !fa->u || w >= fa->n) return htn_factor_make_inverse(ctx, fa);
     if (!fa->linv) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linv, bytes));
     if (!fa->linvt) HTN_TRY(htn_dalloc(ctx, (void**)&fa->linvt, bytes));
-    HTN_CUDA(cudaMemsetAsync(fa->linv, 0, bytes, ctx->stream));
-    HTN_CUDA(cudaMemsetAsync(fa->linvt, 0, bytes, ctx->stream));
+    /* only the diagonal w x w blocks are ever read (solve_*_blocks): zero those, not the whole matrices (p = 8192: 268 MB
+     * instead of 1 GB) */
+    for (int lo = 0; lo < fa->n; lo += w) {
+        const size_t wj = (size_t)(lo + w < fa->n ? w : fa->n - lo);
+        HTN_CUDA(cudaMemset2DAsync(fa->linv + (size_t)lo * fa->ld + lo, fa->ld * sizeof(double), 0, wj * sizeof(double), wj, ctx->stream));
+        HTN_CUDA(cudaMemset2DAsync(fa->linvt + (size_t)lo * fa->ld + lo, fa->ld * sizeof(double), 0, wj * sizeof(double), wj, ctx->stream));
+    }
     {
         const size_t half = htn_round_up((size_t)(w / 2), HTN_NB) + HTN_NB;
         const size_t ldt = htn_round_up(half, 16);
