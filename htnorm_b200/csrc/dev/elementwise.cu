@@ -48,16 +48,19 @@ sym_expand_kernel(const double* __restrict__ src, size_t lds, int n, int lower_s
     }
 }
 
+// src_lower != 0: src is lower triangular (zeros above its diagonal, e.g. a Cholesky factor): the tiles above the diagonal
+// are not read, their transposes are written as zeros
 __global__ void __launch_bounds__(256)
 transpose_kernel(const double* __restrict__ src, size_t lds, int rows, int cols, double* __restrict__ dst,
-                 size_t ldd)
+                 size_t ldd, int src_lower)
 {
     __shared__ double t[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const bool skip = src_lower && c0 > r0 + 31;
     for (int r = ty; r < 32; r += 8) {
         int i = r0 + r, j = c0 + tx;
-        t[r][tx] = (i < rows && j < cols) ? src[(size_t)i * lds + j] : 0.0;
+        t[r][tx] = (!skip && i < rows && j < cols) ? src[(size_t)i * lds + j] : 0.0;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -373,7 +376,15 @@ extern "C" int htnk_transpose(cudaStream_t st, const double* src, size_t lds, in
 {
     if (rows <= 0 || cols <= 0) return 0;
     dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, rows, cols, dst, ldd, 0);
+    return status();
+}
+
+extern "C" int htnk_transpose_lower(cudaStream_t st, const double* src, size_t lds, int n, double* dst, size_t ldd)
+{
+    if (n <= 0) return 0;
+    dim3 grid((n + 31) / 32, (n + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, n, n, dst, ldd, 1);
     return status();
 }
 

@@ -99,6 +99,8 @@ int htnk_sym_expand(cudaStream_t st, const double* src, size_t lds, int n, int l
 /* dst[c][r] = src[r][c], src rows x cols */
 int htnk_transpose(cudaStream_t st, const double* src, size_t lds, int rows, int cols, double* dst,
                    size_t ldd);
+/* the same for a lower-triangular n x n source (zeros above the diagonal are not read; every element of dst is written) */
+int htnk_transpose_lower(cudaStream_t st, const double* src, size_t lds, int n, double* dst, size_t ldd);
 /* dst[r][c] = src[r][c] (rows x cols), optional bias[c] added; strided 2-D copy */
 /* all nb x nb diagonal-block inverses (stored block after block) and their transposes -> the diagonals of linv / linvt */
 int htnk_scatter_diag_blocks(cudaStream_t st, const double* dinv, const double* dinvt, int nb, int n, double* linv,

@@ -52,8 +52,11 @@ int htn_factor_make_u(htn_ctx_t* ctx, htn_factor_t* fa)
 {
     int rc = 0;
     if (!fa->u) HTN_TRY(htn_dalloc(ctx, (void**)&fa->u, (size_t)fa->n * fa->ld * sizeof(double)));
-    HTN_CUDA(cudaMemsetAsync(fa->u, 0, (size_t)fa->n * fa->ld * sizeof(double), ctx->stream));
-    HTN_TRY(htnk_transpose(ctx->stream, fa->f, fa->ld, fa->n, fa->n, fa->u, fa->ld));
+    /* the transpose writes every element of the n x n square (zeros below the diagonal without reading L's upper half):
+     * only the padding columns, if any, need the memset */
+    if ((size_t)fa->n != fa->ld)
+        HTN_CUDA(cudaMemsetAsync(fa->u, 0, (size_t)fa->n * fa->ld * sizeof(double), ctx->stream));
+    HTN_TRY(htnk_transpose_lower(ctx->stream, fa->f, fa->ld, fa->n, fa->u, fa->ld));
 done:
     return rc;
 }
