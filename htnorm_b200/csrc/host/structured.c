@@ -67,7 +67,8 @@ static int factor_dense(htn_ctx_t* ctx, const double* src, int n, int lower_src,
     int rc = 0;
     const size_t ld = htn_round_up((size_t)n, 16);
     HTN_TRY(htn_dalloc(ctx, (void**)buf, (size_t)n * ld * 8));
-    HTN_CUDA(cudaMemsetAsync(*buf, 0, (size_t)n * ld * 8, ctx->stream));
+    if (ld != (size_t)n) /* sym_expand writes the whole n x n square (zeros above the diagonal): only padding needs the memset */
+        HTN_CUDA(cudaMemsetAsync(*buf, 0, (size_t)n * ld * 8, ctx->stream));
     HTN_TRY(htnk_sym_expand(ctx->stream, src, (size_t)n, n, lower_src, NULL, 0, *buf, ld));
     HTN_TRY(htn_factor_init(ctx, fa, *buf, ld, n, 1));
     sp_trace("  (before potrf)");
