@@ -533,7 +533,15 @@ int htn_ht_device(htn_ctx_t* ctx, const htn_streams_t* s, size_t nsamples, int i
         return HTN_E_ARG;
     }
     if (independent) {
-        if (k <= SMALL_K_MAX && k2 <= SMALL_K2_MAX) {
+        /* (64, 128]: the CTA-per-problem kernel of round 1, unless the batched mid-size path is asked to take over from a
+         * smaller order (HTN_MID_MIN_K, experiments; it needs k2 <= 4, a dense cov and at least two problems) */
+        static int mid_min_k = -1;
+        if (mid_min_k < 0) {
+            const char* e = getenv("HTN_MID_MIN_K");
+            mid_min_k = e && atoi(e) > 64 ? atoi(e) : SMALL_K_MAX + 1;
+        }
+        const int mid_takes = !diag && (int)k >= mid_min_k && k2 <= MID_K2_MAX && nsamples >= 2 && !s->states && !s->zpre;
+        if (k <= SMALL_K_MAX && k2 <= SMALL_K2_MAX && !mid_takes) {
             int* info_dev = d_info_out;
             int* tmp = NULL;
             double* zs = NULL;

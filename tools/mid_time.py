@@ -7,7 +7,8 @@ import numpy as np, torch, cases
 import htnorm_b200 as h
 dev = "cuda:0"
 peak = h.fp64_tensor_peak_tflops(0, 50.0)
-for k, P in ((256, 4096), (512, 1024), (1000, 256), (192, 4096)):
+shapes = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(256, 4096), (512, 1024), (1000, 256), (192, 4096)]
+for k, P in shapes:
     k2 = 4
     rng = np.random.default_rng(k)
     base = torch.from_numpy(np.stack([cases.spd(rng, k) for _ in range(8)])).to(dev)
